@@ -1,0 +1,134 @@
+/* mi_b200.h — C ABI of libmi_b200.so: the B200-native (sm_100a) MI critic / estimator hot path.
+ *
+ * The reference (vnoz/Mutual-Information-MultiModal) is pure Python and has no FFI; its hot path is
+ * three attribute lookups inside MultiModalManager.train (mutual_info_img_txt/main_utils.py:220-226):
+ *
+ *     mi_input  = self.create_mi_pairs(embedding_img, embedding_txt, study_id, device)   # :80-110
+ *     mi_output = self.mi_discriminator(mi_input)                                          # :222, model.py:18-32
+ *     loss      = mi_critic(mi_output, args.batch_size, device)                            # :224, mi_critics.py:3-23
+ *     loss.backward()                                                                      # :226
+ *
+ * The entry points below are what a binding for that sequence calls (see INTEGRATION.md for the
+ * ctypes stub).  Conventions: all pointers are DEVICE pointers owned by the caller (except where a
+ * name ends in _host); row-major; bf16 operands; fp32 / fp64 results; nothing is allocated or freed
+ * inside; work is enqueued on `stream` and the call returns without synchronising; return value is
+ * 0 on success or a negative mi_status.  Re-entrant; one call per workspace at a time.
+ *
+ * Score block:   S[q,k] = scale * <Q[q,:], K[k,:]>,   q in [0,Bq), k in [0,Bk)
+ * Sample of row q is column (q_offset + q)  (the positive pair / diagonal).
+ * Negatives mask (main_utils.py:105):  M[q,k] = sid_q[q] != sid_k[k]   (the diagonal has equal ids).
+ */
+#ifndef MI_B200_H_
+#define MI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mi_stream_t;   /* == cudaStream_t */
+
+enum mi_status {
+  MI_OK = 0,
+  MI_ERR_BAD_ARG = -1,        /* null pointer, non-positive size, D % 8 != 0, misaligned pointer */
+  MI_ERR_WORKSPACE = -2,      /* workspace too small: call the matching *_workspace_bytes */
+  MI_ERR_CUDA = -3,           /* a CUDA runtime / driver call failed (see mi_last_cuda_error) */
+  MI_ERR_NO_DEVICE = -4,      /* no sm_100 device: there is NO CPU fallback */
+  MI_ERR_NO_NEGATIVES = -5    /* reported by the host layer when N_neg == 0 (reference yields nan/-inf) */
+};
+
+enum mi_critic { MI_CRITIC_DOT = 0, MI_CRITIC_BILINEAR = 1 };
+
+/* estimator codes.  DV and INFONCE_REF restate mi_critics.py:3-12 and :14-23 (the reference's
+ * "infonce" is DV + log N_neg); INFONCE_ROW / INFONCE_SYM are the true row / symmetric InfoNCE
+ * bounds the north star adds (no counterpart in the reference). */
+enum mi_estimator { MI_EST_DV = 0, MI_EST_INFONCE_REF = 1, MI_EST_INFONCE_ROW = 2, MI_EST_INFONCE_SYM = 3 };
+
+enum mi_precision { MI_PREC_BF16_FAST = 0,   /* dS panel rounded once to bf16 */
+                    MI_PREC_BF16_STRICT = 1  /* dS = hi + lo bf16 split (fp32-accumulate mode) */ };
+
+const char* mi_status_string(int status);
+const char* mi_last_cuda_error(void);
+int mi_abi_version(void);
+/* 0 when a compute-capability-10.x device is current, MI_ERR_NO_DEVICE otherwise */
+int mi_device_check(void);
+
+/* ---- building blocks --------------------------------------------------------------------------- */
+
+/* C[M,N] = alpha * ( A[M,K] * B[N,K]^T - gamma * SUB[M,N] ), bf16 operands (K contiguous), fp32
+ * accumulate on tcgen05.  out_f32 and/or out_bf16 may be NULL; SUB may be NULL.  Replaces the
+ * nn.Linear-style contractions around the critic (T = X W, dX = dT W^T, dW = X^T dT). */
+size_t mi_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int mi_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                 float alpha, float gamma, const void* sub, int64_t ld_sub,
+                 float* out_f32, void* out_bf16, int64_t ld_out,
+                 void* workspace, size_t workspace_bytes, mi_stream_t stream);
+
+/* out[C,R] = in[R,C]^T (bf16) */
+int mi_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, mi_stream_t stream);
+/* out = bf16(in), n elements */
+int mi_cast_f32_to_bf16(const float* in, void* out, int64_t n, mi_stream_t stream);
+
+/* Score statistics without materialising S (replaces create_mi_pairs + critic + the reductions of
+ * mi_critics.py:7-10 / :18-20):
+ *   row_out[q] = { lse_neg, n_neg, diag, lse_all }   natural log; lse_neg = LSE_k M[q,k] S[q,k],
+ *                                                    lse_all = logaddexp(lse_neg, diag)
+ *   scal_out   = { m = max_q lse_neg, sum_q exp(lse_neg - m), sum_q n_neg, sum_q diag,
+ *                  sum_q (lse_all - diag), #rows without negatives, 0, 0 }          (fp64) */
+size_t mi_score_stats_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D);
+int mi_score_stats(const void* Q, int64_t ldq, const void* K, int64_t ldk,
+                   const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                   int64_t Bq, int64_t Bk, int64_t D, float scale,
+                   float* row_out /*[Bq,4]*/, double* scal_out /*[8]*/,
+                   void* workspace, size_t workspace_bytes, mi_stream_t stream);
+
+/* Fused gradient pass (replaces loss.backward() through mi_critics.py and the pair tensor,
+ * main_utils.py:226): recomputes score tiles, forms
+ *   G[q,k] = incl[q,k] * ( wq * exp(S - refq[q]) + wk * exp(S - refk[k]) )
+ *   incl   = M  (include_diag = 0, DV)   or   M + diagonal  (include_diag = 1, InfoNCE)
+ * and returns  O[Bq,D] = alpha * ( G * K - gamma * SUB ).  refq / refk may be NULL (term unused).
+ * The B x B matrix never exists: G is staged as a bounded bf16 row panel in `workspace`. */
+size_t mi_score_grad_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision);
+int mi_score_grad(const void* Q, int64_t ldq, const void* K, int64_t ldk,
+                  const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                  int64_t Bq, int64_t Bk, int64_t D, float scale,
+                  const float* refq, float wq, const float* refk, float wk,
+                  int include_diag, int precision,
+                  float alpha, float gamma, const void* sub, int64_t ld_sub,
+                  float* out_f32, void* out_bf16, int64_t ld_out,
+                  void* workspace, size_t workspace_bytes, mi_stream_t stream);
+
+/* ---- the whole path, one GPU ------------------------------------------------------------------- */
+
+/* loss_out (fp64[8]) = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, #rows w/o negatives, 0 }.
+ * X = image embeddings [B,D], Y = text embeddings [B,D], W = [D,D] (NULL for the dot critic),
+ * S = inv_tau * X W Y^T.  dX, dY (fp32 [B,D]) and dW (fp32 [D,D]) may all be NULL (forward only). */
+size_t mi_critic_workspace_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads);
+int mi_critic_loss_fwd_bwd(const void* X, const void* Y, const void* W, const int32_t* sid,
+                           int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                           double* loss_out, float* dX, float* dY, float* dW,
+                           void* workspace, size_t workspace_bytes, mi_stream_t stream);
+
+/* Same call with HOST buffers (fp32 embeddings as the encoders produce them): copies X, Y, W, sid
+ * to the device, runs mi_critic_loss_fwd_bwd, copies loss and gradients back, synchronises.
+ * dev_scratch is a device buffer of mi_critic_host_scratch_bytes(...) bytes. */
+size_t mi_critic_host_scratch_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads);
+int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const float* W_host, const int32_t* sid_host,
+                                int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                                double* loss_out_host, float* dX_host, float* dY_host, float* dW_host,
+                                void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t mi_launch_count(void);
+
+/* bring-up / A-B knob: 2 (default) = CTA pairs, cta_group::2 MMAs with M = 256; 1 = single-CTA M = 128.
+ * Also settable through the environment variable MI_CTA_GROUP before the first call. */
+void mi_set_cta_group(int group);
+int mi_get_cta_group(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MI_B200_H_ */

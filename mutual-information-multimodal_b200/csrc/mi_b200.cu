@@ -1,0 +1,716 @@
+// libmi_b200.so — host launchers, auxiliary kernels and the extern "C" ABI declared in
+// include/mi_b200.h.  The tensor-core work is in engine.cuh (tcgen05 / TMEM / TMA, sm_100a only).
+// There is no CPU path: every entry point fails with MI_ERR_NO_DEVICE / MI_ERR_CUDA when no
+// Blackwell device is available.
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_bf16.h>
+
+#include "../../include/mi_b200.h"
+#include "engine.cuh"
+
+namespace {
+
+using mi::Sched;
+
+// ------------------------------------------------------------------------------------ errors
+thread_local char g_cuda_err[512] = "";
+std::atomic<long long> g_launches{0};
+int g_cta_group = -1;   // resolved lazily: env MI_CTA_GROUP or 2
+
+int cta_group() {
+  if (g_cta_group < 0) {
+    const char* e = std::getenv("MI_CTA_GROUP");
+    g_cta_group = (e && e[0] == '1') ? 1 : 2;
+  }
+  return g_cta_group;
+}
+
+int set_cuda_err(cudaError_t e, const char* where) {
+  std::snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  return MI_ERR_CUDA;
+}
+#define MI_CUDA(call)                                                   \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return set_cuda_err(e__, #call);            \
+  } while (0)
+#define MI_TRY(call)                                                    \
+  do {                                                                  \
+    int s__ = (call);                                                   \
+    if (s__ != MI_OK) return s__;                                       \
+  } while (0)
+#define MI_LAUNCH_CHECK(name)                                           \
+  do {                                                                  \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                 \
+    cudaError_t e__ = cudaGetLastError();                               \
+    if (e__ != cudaSuccess) return set_cuda_err(e__, name);             \
+  } while (0)
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else { n = 148; (void)cudaGetLastError(); return 148; }   // planning on a box without a GPU
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------ workspace
+struct Bump {
+  uint8_t* base; size_t cap; size_t off; size_t peak; bool dry;
+  Bump(void* b, size_t c, bool d) : base(static_cast<uint8_t*>(b)), cap(c), off(0), peak(0), dry(d) {}
+  template <class T> T* take(size_t n) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    if (off > peak) peak = off;
+    return p;
+  }
+  // stream-ordered reuse: everything taken after mark() is dead once the stage's kernels are enqueued
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+  bool ok() const { return dry || (peak <= cap && (base != nullptr || peak == 0)); }
+};
+
+inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+inline int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+// ------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 matrix [rows, k_extent] with row pitch ld (elements); box = [box_rows x 64], 128 B swizzle,
+// out-of-bounds elements read as zero (ragged rows and K tails need no special casing).
+int make_tmap(CUtensorMap* m, const void* ptr, long long rows, long long k_extent, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { std::snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled unavailable"); return MI_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0 || rows <= 0 || k_extent <= 0) return MI_ERR_BAD_ARG;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_extent), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(mi::BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
+    return MI_ERR_CUDA;
+  }
+  return MI_OK;
+}
+
+// ------------------------------------------------------------------------------------ engine launch
+template <int kCG, class Epi>
+int launch_engine_cg(const void* A, long long a_rows, long long a_k, long long lda,
+                     const void* B, long long b_rows, long long b_k, long long ldb,
+                     const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
+  using C = mi::Cfg<kCG>;
+  CUtensorMap ta, tb;
+  MI_TRY(make_tmap(&ta, A, a_rows, a_k, lda, mi::BLOCK_M));
+  MI_TRY(make_tmap(&tb, B, b_rows, b_k, ldb, C::kBRows));
+  auto kern = mi::tile_engine_kernel<kCG, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int units = sc.n_mblk * sc.n_split * sc.n_ksplit;
+  int pairs = num_sms() / kCG;
+  if (pairs > units) pairs = units;
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(pairs * kCG), 1, 1);
+  cfg.blockDim = dim3(mi::kNumThreads, 1, 1);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MI_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, sc, ep));
+  MI_LAUNCH_CHECK("tile_engine_kernel");
+  return MI_OK;
+}
+
+template <class Epi>
+int launch_engine(const void* A, long long a_rows, long long a_k, long long lda,
+                  const void* B, long long b_rows, long long b_k, long long ldb,
+                  const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
+  if (cta_group() == 1) return launch_engine_cg<1, Epi>(A, a_rows, a_k, lda, B, b_rows, b_k, ldb, sc, ep, stream);
+  return launch_engine_cg<2, Epi>(A, a_rows, a_k, lda, B, b_rows, b_k, ldb, sc, ep, stream);
+}
+
+inline int rows_per_mblk() { return mi::BLOCK_M * cta_group(); }
+inline int num_pairs() { return num_sms() / cta_group(); }
+
+// N-range splits per M block for the streaming (stats / dS-panel) passes: make the unit count a
+// multiple of the number of CTA pairs, then refine while units stay long enough to amortise.
+int choose_split(int n_mblk, int n_ntile, int U) {
+  int ns = U / gcd_i(n_mblk, U);
+  if (ns > n_ntile) {
+    ns = static_cast<int>(cdiv(4LL * U, n_mblk));
+    if (ns > n_ntile) ns = n_ntile;
+    if (ns < 1) ns = 1;
+    return ns;
+  }
+  while (ns * 2 <= n_ntile / 8 && n_mblk * ns < 8 * U) ns *= 2;
+  return ns;
+}
+
+// ------------------------------------------------------------------------------------ aux kernels
+__global__ void pad_int_kernel(const int* __restrict__ src, int* __restrict__ dst, long long n, long long n_pad, int fill) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = (i < n) ? src[i] : fill;
+}
+
+// refk2[c] = (refk[c] - ln wk) * log2(e), zero padded
+__global__ void make_refk2_kernel(const float* __restrict__ refk, float ln_wk, float* __restrict__ dst, long long n, long long n_pad) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = (i < n) ? (refk[i] - ln_wk) * mi::kLog2e : 0.f;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 o; o.x = ptx::pack_bf16(v.x, v.y); o.y = ptx::pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  } else {
+    for (; i < n; ++i) out[i] = __float2bfloat16(in[i]);
+  }
+}
+
+// out[c, r] = in[r, c]; 64x64 tiles through shared memory, coalesced on both sides
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in,
+                                      __nv_bfloat16* __restrict__ out, long long ld_out, long long R, long long C) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const long long r0 = blockIdx.y * 64LL, c0 = blockIdx.x * 64LL;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 256 threads: 64 x 4
+  for (int i = ty; i < 64; i += 4) {
+    const long long r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? in[r * ld_in + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const long long c = c0 + i, r = r0 + tx;
+    if (c < C && r < R) out[c * ld_out + r] = tile[tx][i];
+  }
+}
+
+// merge the (split, half) partials of one row -> {lse_neg, n_neg, diag, lse_all}
+__global__ void stats_merge_kernel(const float4* __restrict__ part, int n_part, int rows_padded, int q_rows,
+                                   float4* __restrict__ row_out) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= q_rows) return;
+  float m = mi::neg_inf();
+  for (int p = 0; p < n_part; ++p) m = fmaxf(m, part[(size_t)p * rows_padded + row].x);
+  float s = 0.f, cnt = 0.f, diag = 0.f;
+  for (int p = 0; p < n_part; ++p) {
+    const float4 v = part[(size_t)p * rows_padded + row];
+    if (v.y > 0.f) s += v.y * exp2f(v.x - m);
+    cnt += v.z; diag += v.w;
+  }
+  const float lse_neg = (cnt > 0.f && s > 0.f) ? (m + log2f(s)) * mi::kLn2 : mi::neg_inf();
+  const float hi = fmaxf(lse_neg, diag), lo = fminf(lse_neg, diag);
+  const float lse_all = hi + log1pf(expf(lo - hi));
+  row_out[row] = make_float4(lse_neg, cnt, diag, lse_all);
+}
+
+// one block: scal = {max lse_neg, sum exp(lse_neg - max), sum n_neg, sum diag, sum (lse_all - diag), #rows w/o neg}
+__global__ void stats_reduce_kernel(const float4* __restrict__ row_out, int q_rows, double* __restrict__ scal) {
+  __shared__ double sh[6][32];
+  __shared__ float shm[32];
+  __shared__ float gmax;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+  float m = mi::neg_inf();
+  for (int r = tid; r < q_rows; r += blockDim.x) m = fmaxf(m, row_out[r].x);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) shm[w] = m;
+  __syncthreads();
+  if (tid == 0) { float g = mi::neg_inf(); for (int i = 0; i < nw; ++i) g = fmaxf(g, shm[i]); gmax = g; }
+  __syncthreads();
+  const float g = gmax;
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int r = tid; r < q_rows; r += blockDim.x) {
+    const float4 v = row_out[r];
+    if (v.x > mi::neg_inf()) acc[0] += exp((double)v.x - (double)g);
+    acc[1] += v.y; acc[2] += v.z; acc[3] += (double)v.w - (double)v.z;
+    if (!(v.y > 0.f)) acc[4] += 1.0;
+  }
+  for (int k = 0; k < 5; ++k) {
+    double a = acc[k];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) sh[k][w] = a;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double t[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k < 5; ++k) for (int i = 0; i < nw; ++i) t[k] += sh[k][i];
+    scal[0] = g; scal[1] = t[0]; scal[2] = t[1]; scal[3] = t[2]; scal[4] = t[3]; scal[5] = t[4]; scal[6] = 0; scal[7] = 0;
+  }
+}
+
+// fused single-GPU glue: loss from the reduced scalars (fp64), and the scalar references as floats
+// loss_out = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, rows w/o negatives, 0 }
+__global__ void loss_finalize_kernel(const double* __restrict__ scal_row, const double* __restrict__ scal_col,
+                                     long long B, int estimator, double* __restrict__ loss_out, float* __restrict__ lse_f) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double lse = scal_row[0] + log(scal_row[1]);
+  const double n_neg = scal_row[2];
+  const double pos = scal_row[3] / (double)B;
+  const double loss_row = scal_row[4] / (double)B;
+  const double loss_col = scal_col ? scal_col[4] / (double)B : 0.0;
+  double loss;
+  if (estimator == MI_EST_DV) loss = lse - log((double)(float)n_neg) - pos;   // fp32 N_neg as mi_critics.py:10
+  else if (estimator == MI_EST_INFONCE_REF) loss = lse - pos;
+  else if (estimator == MI_EST_INFONCE_ROW) loss = loss_row;
+  else loss = 0.5 * (loss_row + loss_col);
+  loss_out[0] = loss; loss_out[1] = pos; loss_out[2] = lse; loss_out[3] = n_neg;
+  loss_out[4] = loss_row; loss_out[5] = loss_col; loss_out[6] = scal_row[5]; loss_out[7] = 0;
+  *lse_f = (float)lse;
+}
+
+// dst[i] = const (from device scalar) or column `col` of row_out
+__global__ void make_ref_kernel(float* __restrict__ dst, const float4* __restrict__ rows, int col,
+                                const float* __restrict__ scalar, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (scalar) { dst[i] = *scalar; return; }
+  const float4 v = rows[i];
+  dst[i] = col == 0 ? v.x : col == 1 ? v.y : col == 2 ? v.z : v.w;
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int n_part, long long stride, float* __restrict__ out, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int p = 0; p < n_part; ++p) a += part[(size_t)p * stride + i];
+  out[i] = a;
+}
+
+inline unsigned blocks_for(long long n, int t) { return static_cast<unsigned>(cdiv(n, t)); }
+
+// ------------------------------------------------------------------------------------ stages
+int gemm_impl(const void* A, long long lda, const void* B, long long ldb, long long M, long long N, long long K,
+              float alpha, float gamma, const void* sub, long long ld_sub,
+              float* out_f32, void* out_bf16, long long ld_out, int ksplit, long long kwrap_blocks,
+              long long b_k_extent, Bump& ws, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return MI_ERR_BAD_ARG;
+  Sched sc;
+  sc.n_mblk = static_cast<int>(cdiv(M, rows_per_mblk()));
+  sc.n_ntile = static_cast<int>(cdiv(N, mi::TILE_N));
+  sc.n_split = sc.n_ntile;           // one tile per unit
+  sc.k_blocks = static_cast<int>(cdiv(K, mi::BLOCK_K));
+  sc.n_ksplit = ksplit < 1 ? 1 : (ksplit > sc.k_blocks ? sc.k_blocks : ksplit);
+  sc.order = 1;                      // all N tiles (and K splits) of an M block run concurrently
+  sc.b_kwrap = kwrap_blocks > 0 ? static_cast<int>(kwrap_blocks) : sc.k_blocks;
+  float* partial = nullptr;
+  if (sc.n_ksplit > 1) partial = ws.take<float>(static_cast<size_t>(sc.n_ksplit) * M * ld_out);
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  if (ws.dry) return MI_OK;
+  if (!A || !B || (!out_f32 && !out_bf16)) return MI_ERR_BAD_ARG;
+  mi::EpiStore::Params ep;
+  ep.out_f32 = sc.n_ksplit > 1 ? partial : out_f32;
+  ep.out_bf16 = sc.n_ksplit > 1 ? nullptr : static_cast<__nv_bfloat16*>(out_bf16);
+  ep.ld_out = ld_out; ep.rows = static_cast<int>(M); ep.cols = static_cast<int>(N);
+  ep.alpha = alpha; ep.gamma = gamma;
+  ep.sub = sc.n_ksplit > 1 ? nullptr : static_cast<const __nv_bfloat16*>(sub);
+  ep.ld_sub = ld_sub;
+  ep.ksplit_stride = static_cast<long long>(M) * ld_out;
+  const long long b_k = b_k_extent > 0 ? b_k_extent : K;
+  MI_TRY(launch_engine<mi::EpiStore>(A, M, K, lda, B, N, b_k, ldb, sc, ep, stream));
+  if (sc.n_ksplit > 1) {
+    if (!out_f32) return MI_ERR_BAD_ARG;
+    const long long n = static_cast<long long>(M) * ld_out;
+    reduce_partials_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(partial, sc.n_ksplit, n, out_f32, n);
+    MI_LAUNCH_CHECK("reduce_partials_kernel");
+  }
+  return MI_OK;
+}
+
+int transpose_impl(const void* in, long long ld_in, void* out, long long ld_out, long long R, long long C, cudaStream_t stream) {
+  if (!in || !out || R <= 0 || C <= 0) return MI_ERR_BAD_ARG;
+  dim3 grid(static_cast<unsigned>(cdiv(C, 64)), static_cast<unsigned>(cdiv(R, 64)));
+  transpose_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), ld_in,
+                                                  static_cast<__nv_bfloat16*>(out), ld_out, R, C);
+  MI_LAUNCH_CHECK("transpose_bf16_kernel");
+  return MI_OK;
+}
+
+int stats_impl(const void* Q, long long ldq, const void* K, long long ldk, const int* sid_q, const int* sid_k,
+               long long q_offset, long long Bq, long long Bk, long long D, float scale,
+               float* row_out, double* scal_out, Bump& ws, cudaStream_t stream) {
+  if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
+  Sched sc;
+  sc.n_mblk = static_cast<int>(cdiv(Bq, rows_per_mblk()));
+  sc.n_ntile = static_cast<int>(cdiv(Bk, mi::TILE_N));
+  sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
+  sc.n_ksplit = 1; sc.order = 0;
+  sc.k_blocks = static_cast<int>(cdiv(D, mi::BLOCK_K));
+  sc.b_kwrap = sc.k_blocks;
+  const long long k_pad = static_cast<long long>(sc.n_ntile) * mi::TILE_N;
+  const int rows_padded = sc.n_mblk * rows_per_mblk();
+  int* sidk_pad = ws.take<int>(k_pad);
+  float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * 2 * rows_padded);
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  if (ws.dry) return MI_OK;
+  if (!Q || !K || !sid_q || !sid_k || !row_out || !scal_out) return MI_ERR_BAD_ARG;
+  pad_int_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(sid_k, sidk_pad, Bk, k_pad, -2);
+  MI_LAUNCH_CHECK("pad_int_kernel");
+  mi::EpiStats::Params ep;
+  ep.sid_q = sid_q; ep.sid_k = sidk_pad; ep.q_rows = static_cast<int>(Bq); ep.k_cols = static_cast<int>(Bk);
+  ep.q_offset = q_offset; ep.scale = scale; ep.part = part; ep.rows_padded = rows_padded;
+  MI_TRY(launch_engine<mi::EpiStats>(Q, Bq, D, ldq, K, Bk, D, ldk, sc, ep, stream));
+  stats_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * 2, rows_padded, static_cast<int>(Bq),
+                                                              reinterpret_cast<float4*>(row_out));
+  MI_LAUNCH_CHECK("stats_merge_kernel");
+  stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out);
+  MI_LAUNCH_CHECK("stats_reduce_kernel");
+  return MI_OK;
+}
+
+// rows of the dS panel per pass: make the panel GEMM's tile count a multiple of the pair count
+long long panel_mblks(long long Bq, long long Bk, long long D, int precision) {
+  const int U = num_pairs();
+  const int ntD = static_cast<int>(cdiv(D, mi::TILE_N));
+  long long mb = U / gcd_i(U, ntD);
+  const long long total = cdiv(Bq, rows_per_mblk());
+  if (mb > total) mb = total;
+  const long long pitch = cdiv(Bk, mi::TILE_N) * mi::TILE_N * (precision == MI_PREC_BF16_STRICT ? 2 : 1);
+  const long long cap = 6LL << 30;
+  while (mb > 1 && mb * rows_per_mblk() * pitch * 2 > cap) mb = (mb + 1) / 2;
+  return mb;
+}
+
+int grad_impl(const void* Q, long long ldq, const void* K, long long ldk, const int* sid_q, const int* sid_k,
+              long long q_offset, long long Bq, long long Bk, long long D, float scale,
+              const float* refq, float wq, const float* refk, float wk, int include_diag, int precision,
+              float alpha, float gamma, const void* sub, long long ld_sub,
+              float* out_f32, void* out_bf16, long long ld_out, Bump& ws, cudaStream_t stream) {
+  if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
+  const bool strict = precision == MI_PREC_BF16_STRICT;
+  const int n_ntile = static_cast<int>(cdiv(Bk, mi::TILE_N));
+  const long long k_pad = static_cast<long long>(n_ntile) * mi::TILE_N;
+  const long long pitch = k_pad * (strict ? 2 : 1);
+  const long long ld_kt = cdiv(Bk, 64) * 64;
+  const long long mb_panel = panel_mblks(Bq, Bk, D, precision);
+  const long long panel_rows = mb_panel * rows_per_mblk();
+  int* sidk_pad = ws.take<int>(k_pad);
+  float* refk2 = ws.take<float>(k_pad);
+  __nv_bfloat16* Kt = ws.take<__nv_bfloat16>(static_cast<size_t>(D) * ld_kt);
+  __nv_bfloat16* P = ws.take<__nv_bfloat16>(static_cast<size_t>(panel_rows) * pitch);
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  if (ws.dry) return MI_OK;
+  if (!Q || !K || !sid_q || !sid_k || (!out_f32 && !out_bf16)) return MI_ERR_BAD_ARG;
+  const bool use_q = refq != nullptr && wq > 0.f, use_k = refk != nullptr && wk > 0.f;
+  if (!use_q && !use_k) return MI_ERR_BAD_ARG;
+
+  pad_int_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(sid_k, sidk_pad, Bk, k_pad, -2);
+  MI_LAUNCH_CHECK("pad_int_kernel");
+  if (use_k) {
+    make_refk2_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(refk, logf(wk), refk2, Bk, k_pad);
+    MI_LAUNCH_CHECK("make_refk2_kernel");
+  }
+  MI_TRY(transpose_impl(K, ldk, Kt, ld_kt, Bk, D, stream));
+
+  for (long long r0 = 0; r0 < Bq; r0 += panel_rows) {
+    const long long rows = (Bq - r0 < panel_rows) ? (Bq - r0) : panel_rows;
+    // pass 1: recompute score tiles, write the dS panel (never the score matrix)
+    Sched sc;
+    sc.n_mblk = static_cast<int>(cdiv(rows, rows_per_mblk()));
+    sc.n_ntile = n_ntile;
+    sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
+    sc.n_ksplit = 1; sc.order = 0;
+    sc.k_blocks = static_cast<int>(cdiv(D, mi::BLOCK_K));
+    sc.b_kwrap = sc.k_blocks;
+    mi::EpiPStore::Params ep;
+    ep.sid_q = sid_q + r0; ep.sid_k = sidk_pad; ep.q_rows = static_cast<int>(rows); ep.k_cols = static_cast<int>(Bk);
+    ep.q_offset = q_offset + r0; ep.scale = scale;
+    ep.refq = use_q ? refq + r0 : nullptr; ep.refq_const = 0.f; ep.ln_wq = use_q ? logf(wq) : 0.f; ep.use_q = use_q ? 1 : 0;
+    ep.refk2 = refk2; ep.use_k = use_k ? 1 : 0; ep.include_diag = include_diag;
+    ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
+    const __nv_bfloat16* Qp = static_cast<const __nv_bfloat16*>(Q) + r0 * ldq;
+    MI_TRY(launch_engine<mi::EpiPStore>(Qp, rows, D, ldq, K, Bk, D, ldk, sc, ep, stream));
+    // pass 2: O[panel] = alpha * (P * K - gamma * SUB): GEMM over the Bk dimension
+    const __nv_bfloat16* subp = sub ? static_cast<const __nv_bfloat16*>(sub) + r0 * ld_sub : nullptr;
+    float* of = out_f32 ? out_f32 + r0 * ld_out : nullptr;
+    __nv_bfloat16* ob = out_bf16 ? static_cast<__nv_bfloat16*>(out_bf16) + r0 * ld_out : nullptr;
+    Bump none(nullptr, 0, false);
+    MI_TRY(gemm_impl(P, pitch, Kt, ld_kt, rows, D, strict ? 2 * k_pad : k_pad, alpha, gamma, subp, ld_sub,
+                     of, ob, ld_out, 1, strict ? k_pad / mi::BLOCK_K : 0, Bk, none, stream));
+  }
+  return MI_OK;
+}
+
+int critic_impl(const void* X, const void* Y, const void* W, const int* sid, long long B, long long D,
+                int critic, int estimator, int precision, float inv_tau,
+                double* loss_out, float* dX, float* dY, float* dW, Bump& ws, cudaStream_t stream) {
+  if (B <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
+  if (estimator < MI_EST_DV || estimator > MI_EST_INFONCE_SYM) return MI_ERR_BAD_ARG;
+  const bool bilinear = critic == MI_CRITIC_BILINEAR;
+  const bool grads = dX != nullptr || dY != nullptr || dW != nullptr;
+  const bool sym = estimator == MI_EST_INFONCE_SYM;
+  const bool dv_like = estimator == MI_EST_DV || estimator == MI_EST_INFONCE_REF;
+  typedef __nv_bfloat16 bf;
+  const long long ldb64 = cdiv(B, 64) * 64;
+  bf* Wt = bilinear ? ws.take<bf>(static_cast<size_t>(D) * D) : nullptr;
+  bf* T = bilinear ? ws.take<bf>(static_cast<size_t>(B) * D) : nullptr;
+  float* rows_r = ws.take<float>(static_cast<size_t>(B) * 4);
+  float* rows_c = sym ? ws.take<float>(static_cast<size_t>(B) * 4) : nullptr;
+  double* scal_r = ws.take<double>(8);
+  double* scal_c = sym ? ws.take<double>(8) : nullptr;
+  float* lse_f = ws.take<float>(1);
+  float* ref_r = ws.take<float>(B);
+  float* ref_c = sym ? ws.take<float>(B) : nullptr;
+  bf* dT16 = (bilinear && ws.dry) || (bilinear && grads) ? ws.take<bf>(static_cast<size_t>(B) * D) : nullptr;
+  bf* Xt = (bilinear && ws.dry) || (bilinear && grads) ? ws.take<bf>(static_cast<size_t>(D) * ldb64) : nullptr;
+  bf* dTt = (bilinear && ws.dry) || (bilinear && grads) ? ws.take<bf>(static_cast<size_t>(D) * ldb64) : nullptr;
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  if (!ws.dry && (!X || !Y || !sid || !loss_out || (bilinear && !W))) return MI_ERR_BAD_ARG;
+
+  const void* Tq = bilinear ? static_cast<const void*>(T) : X;
+  if (bilinear) {
+    if (!ws.dry) MI_TRY(transpose_impl(W, D, Wt, D, D, D, stream));
+    // T = X W  (B operand of the engine is [N, K] = W^T)
+    MI_TRY(gemm_impl(X, D, Wt, D, B, D, D, 1.f, 0.f, nullptr, 0, nullptr, T, D, 1, 0, 0, ws, stream));
+  }
+  size_t mk = ws.mark();
+  MI_TRY(stats_impl(Tq, D, Y, D, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
+  ws.release(mk);
+  if (sym) { MI_TRY(stats_impl(Y, D, Tq, D, sid, sid, 0, B, B, D, inv_tau, rows_c, scal_c, ws, stream)); ws.release(mk); }
+  if (!ws.dry) {
+    loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, scal_c, B, estimator, loss_out, lse_f);
+    MI_LAUNCH_CHECK("loss_finalize_kernel");
+  }
+  if (!grads && !ws.dry) return MI_OK;
+
+  float wq, wk;
+  const float* refq_row; const float* refk_row; const float* refq_col; const float* refk_col;
+  if (!ws.dry) {
+    if (dv_like) make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_r, nullptr, 0, lse_f, B);
+    else make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_r, reinterpret_cast<const float4*>(rows_r), 3, nullptr, B);
+    MI_LAUNCH_CHECK("make_ref_kernel");
+    if (sym) {
+      make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_c, reinterpret_cast<const float4*>(rows_c), 3, nullptr, B);
+      MI_LAUNCH_CHECK("make_ref_kernel");
+    }
+  }
+  const int incl_diag = dv_like ? 0 : 1;
+  if (dv_like)                              { wq = 1.f; wk = 0.f; refq_row = ref_r; refk_row = nullptr; refq_col = ref_r; refk_col = nullptr; }
+  else if (estimator == MI_EST_INFONCE_ROW) { wq = 1.f / B; wk = 1.f / B; refq_row = ref_r; refk_row = nullptr; refq_col = nullptr; refk_col = ref_r; }
+  else                                      { wq = 0.5f / B; wk = 0.5f / B; refq_row = ref_r; refk_row = ref_c; refq_col = ref_c; refk_col = ref_r; }
+  const float gamma = 1.f / static_cast<float>(B);
+
+  // row pass: dT = inv_tau * (G Y - Y/B)
+  float* dT32 = bilinear ? nullptr : dX;
+  if (bilinear || dX || ws.dry) {
+    MI_TRY(grad_impl(Tq, D, Y, D, sid, sid, 0, B, B, D, inv_tau, refq_row, wq, refk_row, wk, incl_diag, precision,
+                     inv_tau, gamma, Y, D, dT32, bilinear ? static_cast<void*>(dT16) : nullptr, D, ws, stream));
+    ws.release(mk);
+  }
+  // column pass: dY = inv_tau * (G^T T - T/B)   (same kernels, operands swapped)
+  if (dY || ws.dry) {
+    MI_TRY(grad_impl(Y, D, Tq, D, sid, sid, 0, B, B, D, inv_tau, refq_col, wq, refk_col, wk, incl_diag, precision,
+                     inv_tau, gamma, Tq, D, dY, nullptr, D, ws, stream));
+    ws.release(mk);
+  }
+  if (bilinear) {
+    // dX = dT W^T : B operand [N = d, K = e] is W itself
+    if (dX || ws.dry)
+      MI_TRY(gemm_impl(dT16, D, W, D, B, D, D, 1.f, 0.f, nullptr, 0, dX, nullptr, D, 1, 0, 0, ws, stream));
+    // dW = X^T dT : A = X^T [D, B], B operand = dT^T [D, B], split-K over the batch
+    if (dW || ws.dry) {
+      if (!ws.dry) {
+        MI_TRY(transpose_impl(X, D, Xt, ldb64, B, D, stream));
+        MI_TRY(transpose_impl(dT16, D, dTt, ldb64, B, D, stream));
+      }
+      const long long tiles = cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N);
+      long long ks = cdiv(num_pairs(), tiles);
+      const long long kb = cdiv(B, mi::BLOCK_K);
+      if (ks > kb / 4) ks = kb / 4;
+      if (ks < 1) ks = 1;
+      MI_TRY(gemm_impl(Xt, ldb64, dTt, ldb64, D, D, B, 1.f, 0.f, nullptr, 0, dW, nullptr, D, static_cast<int>(ks), 0, 0, ws, stream));
+    }
+  }
+  return MI_OK;
+}
+
+int device_check() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return MI_ERR_NO_DEVICE; }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { (void)cudaGetLastError(); return MI_ERR_NO_DEVICE; }
+  return major == 10 ? MI_OK : MI_ERR_NO_DEVICE;
+}
+
+}  // namespace
+
+// ======================================================================================== C ABI
+extern "C" {
+
+const char* mi_status_string(int status) {
+  switch (status) {
+    case MI_OK: return "ok";
+    case MI_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size, D % 8 != 0 or misaligned pointer)";
+    case MI_ERR_WORKSPACE: return "workspace too small";
+    case MI_ERR_CUDA: return "CUDA error";
+    case MI_ERR_NO_DEVICE: return "no sm_100 (Blackwell) device: this library has no CPU fallback";
+    case MI_ERR_NO_NEGATIVES: return "no negative pairs (all study ids equal)";
+    default: return "unknown status";
+  }
+}
+const char* mi_last_cuda_error(void) { return g_cuda_err; }
+int mi_abi_version(void) { return 1; }
+int mi_device_check(void) { return device_check(); }
+int64_t mi_launch_count(void) { return g_launches.load(); }
+void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
+int mi_get_cta_group(void) { return cta_group(); }
+
+size_t mi_gemm_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
+int mi_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                 float alpha, float gamma, const void* sub, int64_t ld_sub,
+                 float* out_f32, void* out_bf16, int64_t ld_out,
+                 void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+  MI_TRY(device_check());
+  Bump ws(workspace, workspace_bytes, false);
+  return gemm_impl(A, lda, B, ldb, M, N, K, alpha, gamma, sub, ld_sub, out_f32, out_bf16, ld_out, 1, 0, 0, ws,
+                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mi_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, mi_stream_t stream) {
+  MI_TRY(device_check());
+  return transpose_impl(in, ld_in, out, ld_out, R, C, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mi_cast_f32_to_bf16(const float* in, void* out, int64_t n, mi_stream_t stream) {
+  MI_TRY(device_check());
+  if (!in || !out || n <= 0) return MI_ERR_BAD_ARG;
+  cast_f32_bf16_kernel<<<blocks_for(cdiv(n, 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__nv_bfloat16*>(out), n);
+  MI_LAUNCH_CHECK("cast_f32_bf16_kernel");
+  return MI_OK;
+}
+
+size_t mi_score_stats_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D) {
+  Bump ws(nullptr, 0, true);
+  if (stats_impl(nullptr, D, nullptr, D, nullptr, nullptr, 0, Bq, Bk, D, 1.f, nullptr, nullptr, ws, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_score_stats(const void* Q, int64_t ldq, const void* K, int64_t ldk,
+                   const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                   int64_t Bq, int64_t Bk, int64_t D, float scale, float* row_out, double* scal_out,
+                   void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+  MI_TRY(device_check());
+  Bump ws(workspace, workspace_bytes, false);
+  return stats_impl(Q, ldq, K, ldk, sid_q, sid_k, q_offset, Bq, Bk, D, scale, row_out, scal_out, ws,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t mi_score_grad_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision) {
+  Bump ws(nullptr, 0, true);
+  if (grad_impl(nullptr, D, nullptr, D, nullptr, nullptr, 0, Bq, Bk, D, 1.f, nullptr, 1.f, nullptr, 0.f, 0, precision,
+                1.f, 0.f, nullptr, 0, nullptr, nullptr, D, ws, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_score_grad(const void* Q, int64_t ldq, const void* K, int64_t ldk,
+                  const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                  int64_t Bq, int64_t Bk, int64_t D, float scale,
+                  const float* refq, float wq, const float* refk, float wk, int include_diag, int precision,
+                  float alpha, float gamma, const void* sub, int64_t ld_sub,
+                  float* out_f32, void* out_bf16, int64_t ld_out,
+                  void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+  MI_TRY(device_check());
+  Bump ws(workspace, workspace_bytes, false);
+  return grad_impl(Q, ldq, K, ldk, sid_q, sid_k, q_offset, Bq, Bk, D, scale, refq, wq, refk, wk, include_diag, precision,
+                   alpha, gamma, sub, ld_sub, out_f32, out_bf16, ld_out, ws, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t mi_critic_workspace_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads) {
+  Bump ws(nullptr, 0, true);
+  (void)need_grads;   // planned for the larger (gradient) case always; forward-only calls simply use less
+  if (critic_impl(nullptr, nullptr, nullptr, nullptr, B, D, critic, estimator, precision, 1.f, nullptr, nullptr, nullptr,
+                  nullptr, ws, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_critic_loss_fwd_bwd(const void* X, const void* Y, const void* W, const int32_t* sid,
+                           int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                           double* loss_out, float* dX, float* dY, float* dW,
+                           void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+  MI_TRY(device_check());
+  Bump ws(workspace, workspace_bytes, false);
+  return critic_impl(X, Y, W, sid, B, D, critic, estimator, precision, inv_tau, loss_out, dX, dY, dW, ws,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t mi_critic_host_scratch_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads) {
+  const size_t core = mi_critic_workspace_bytes(B, D, critic, estimator, precision, need_grads);
+  if (core == 0) return 0;
+  Bump ws(nullptr, 0, true);
+  ws.take<float>(static_cast<size_t>(B) * D); ws.take<float>(static_cast<size_t>(B) * D);     // staging fp32 X, Y
+  ws.take<float>(static_cast<size_t>(D) * D);                                                  // staging fp32 W
+  ws.take<__nv_bfloat16>(static_cast<size_t>(B) * D); ws.take<__nv_bfloat16>(static_cast<size_t>(B) * D);
+  ws.take<__nv_bfloat16>(static_cast<size_t>(D) * D);
+  ws.take<int>(B); ws.take<double>(8);
+  ws.take<float>(static_cast<size_t>(B) * D); ws.take<float>(static_cast<size_t>(B) * D); ws.take<float>(static_cast<size_t>(D) * D);
+  return ws.peak + 256 + core;
+}
+int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const float* W_host, const int32_t* sid_host,
+                                int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                                double* loss_out_host, float* dX_host, float* dY_host, float* dW_host,
+                                void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream_) {
+  MI_TRY(device_check());
+  if (!X_host || !Y_host || !sid_host || !loss_out_host || !dev_scratch || B <= 0 || D <= 0) return MI_ERR_BAD_ARG;
+  const bool bilinear = critic == MI_CRITIC_BILINEAR;
+  if (bilinear && !W_host) return MI_ERR_BAD_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  typedef __nv_bfloat16 bf;
+  Bump ws(dev_scratch, dev_scratch_bytes, false);
+  const size_t nBD = static_cast<size_t>(B) * D, nDD = static_cast<size_t>(D) * D;
+  float* X32 = ws.take<float>(nBD); float* Y32 = ws.take<float>(nBD); float* W32 = ws.take<float>(nDD);
+  bf* X16 = ws.take<bf>(nBD); bf* Y16 = ws.take<bf>(nBD); bf* W16 = ws.take<bf>(nDD);
+  int* sid = ws.take<int>(B); double* loss = ws.take<double>(8);
+  float* dX = ws.take<float>(nBD); float* dY = ws.take<float>(nBD); float* dW = ws.take<float>(nDD);
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  ws.off = (ws.off + 255) & ~static_cast<size_t>(255);
+  uint8_t* core = ws.base + ws.off;
+  const size_t core_bytes = dev_scratch_bytes - ws.off;
+  MI_CUDA(cudaMemcpyAsync(X32, X_host, nBD * 4, cudaMemcpyHostToDevice, stream));
+  MI_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, stream));
+  MI_CUDA(cudaMemcpyAsync(sid, sid_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, stream));
+  MI_TRY(mi_cast_f32_to_bf16(X32, X16, static_cast<int64_t>(nBD), stream_));
+  MI_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
+  if (bilinear) {
+    MI_CUDA(cudaMemcpyAsync(W32, W_host, nDD * 4, cudaMemcpyHostToDevice, stream));
+    MI_TRY(mi_cast_f32_to_bf16(W32, W16, static_cast<int64_t>(nDD), stream_));
+  }
+  MI_TRY(mi_critic_loss_fwd_bwd(X16, Y16, bilinear ? W16 : nullptr, sid, B, D, critic, estimator, precision, inv_tau, loss,
+                                dX_host ? dX : nullptr, dY_host ? dY : nullptr, (dW_host && bilinear) ? dW : nullptr,
+                                core, core_bytes, stream_));
+  MI_CUDA(cudaMemcpyAsync(loss_out_host, loss, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (dX_host) MI_CUDA(cudaMemcpyAsync(dX_host, dX, nBD * 4, cudaMemcpyDeviceToHost, stream));
+  if (dY_host) MI_CUDA(cudaMemcpyAsync(dY_host, dY, nBD * 4, cudaMemcpyDeviceToHost, stream));
+  if (dW_host && bilinear) MI_CUDA(cudaMemcpyAsync(dW_host, dW, nDD * 4, cudaMemcpyDeviceToHost, stream));
+  MI_CUDA(cudaStreamSynchronize(stream));
+  return MI_OK;
+}
+
+}  // extern "C"
