@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — critic pairs/sec, fused fwd+bwd MI critic/estimator (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path (score statistics + both gradient passes + the bilinear
+projections) over one batch of synthetic CXR-shaped embeddings.  N=1: B=65536, D=1024 (the size the
+metric is quoted on).  N>1: the same global batch sharded by rows, strong scaling.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "critic pairs/sec fwd+bwd"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="global batch B")
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--critic", default="bilinear", choices=["dot", "bilinear"])
+    ap.add_argument("--estimator", default="dv", choices=["dv", "infonce", "infonce_row", "infonce_sym"])
+    ap.add_argument("--precision", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {"burst": float(p["bf16_tflops"]), "sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "hbm": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def workload_name(a):
+    return (f"{a.critic} critic + {a.estimator} estimator, fused fwd+bwd, global B={a.batch}, D={a.dim}, "
+            f"bf16 operands / fp32 accumulate, precision={a.precision}")
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_step(B, D, critic, estimator, seed=1234):
+    """One fwd+bwd of the oracle's matrix form on the host (the reference's pair-form is O(B^4) and
+    cannot run at these sizes — BASELINE.md section 2; /root/reference does not travel to the GPU box)."""
+    import torch
+    from oracle import matrix_oracle as mo
+    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=seed, dup_frac=0.05, bilinear=(critic == "bilinear"))
+    inv_tau = 1.0 / math.sqrt(D) if critic == "dot" else 1.0
+
+    def step():
+        out = mo.critic_loss(X, Y, sid, W, inv_tau, estimator, dtype=torch.float32, grads=True)
+        return float(out["loss"])
+    return step
+
+
+def time_cpu(a, steps, warmup, budget_s=25.0):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = a.cpu_sample_batch
+    step = cpu_oracle_step(B, a.dim, a.critic, a.estimator)
+    for _ in range(max(1, warmup)):
+        step()
+    ts = []
+    t_start = time.time()
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+        if time.time() - t_start > budget_s:
+            break
+    t = sum(ts) / len(ts)
+    return {"value": B * B / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle matrix form (fp32, torch CPU), fwd+bwd, B={B}, D={a.dim}, {a.critic}/{a.estimator}, "
+                      f"{len(ts)} steps, {t * 1e3:.0f} ms/step",
+            "ms_per_step": t * 1e3, "steps": len(ts)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = time_cpu(a, a.steps, a.warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": cb["steps"], "warmup": max(1, a.warmup), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "CPU arm: bounded sample of the same workload"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            inside = t0 - 0.05 <= ts <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            if inside:
+                for n, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    import mi_b200  # noqa: F401
+    from mi_b200 import _lib, ops
+    from mi_b200 import dist as mdist
+    from oracle import matrix_oracle as mo
+    lib = _lib.load()
+
+    B, D = a.batch, a.dim
+    assert B % world == 0
+    Bl = B // world
+    off = rank * Bl
+    bilinear = a.critic == "bilinear"
+    inv_tau = 1.0 / math.sqrt(D) if not bilinear else 1.0
+    # synthetic CXR-shaped embeddings, generated once on the host, rounded to bf16
+    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=1234, dup_frac=0.05, bilinear=bilinear)
+    Xh = X[off:off + Bl].contiguous().pin_memory()
+    Yh = Y[off:off + Bl].contiguous().pin_memory()
+    Wh = W.contiguous().pin_memory() if bilinear else None
+    sh = sid[off:off + Bl].to(torch.int32).contiguous().pin_memory()
+    Xd, Yd = Xh.to(dev).bfloat16(), Yh.to(dev).bfloat16()
+    Wd = Wh.to(dev).bfloat16() if bilinear else None
+    sd32 = sh.to(dev)
+    sd64 = sid[off:off + Bl].to(dev)
+    del X, Y
+
+    def step_device():
+        if world == 1:
+            return ops.critic_loss_fwd_bwd(Xd, Yd, Wd, sd32, a.estimator, a.precision, inv_tau, True)
+        out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xd, Yd, Wd, sd64, a.estimator, a.precision, inv_tau, True)
+        return out["loss"], dX, dY, dW
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        sync_all()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1, r
+
+    for _ in range(max(3, a.warmup)):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    lib.mi_set_profiling(1)
+    ms = (ctypes.c_double * 3)()
+    cnt = (ctypes.c_int64 * 3)()
+    lib.mi_profile_read(ms, cnt)                      # drain
+    l0 = ops.launch_count()
+    total_ms, t0, t1, last = timed(step_device, a.steps)
+    launches = ops.launch_count() - l0
+    lib.mi_profile_read(ms, cnt)
+    lib.mi_set_profiling(0)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_per_step = total_ms / a.steps
+    value = B * B / (ms_per_step * 1e-3)
+    loss_val = float(last[0][0].item()) if world == 1 else float(last[0].item())
+
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    e2e = None
+    if not a.no_e2e:
+        n_bd, n_dd = Bl * D * 4, D * D * 4
+        if world == 1:
+            crit, est, prec = (1 if bilinear else 0), ops.ESTIMATOR[a.estimator], ops.PRECISION[a.precision]
+            nbytes = lib.mi_critic_host_scratch_bytes(B, D, crit, est, prec, 1)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            loss_h = torch.zeros(8, dtype=torch.float64).pin_memory()
+            dXh, dYh = torch.empty(Bl, D).pin_memory(), torch.empty(Bl, D).pin_memory()
+            dWh = torch.empty(D, D).pin_memory() if bilinear else None
+            P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+            def step_host():
+                st = lib.mi_critic_loss_fwd_bwd_host(P(Xh), P(Yh), P(Wh), P(sh), B, D, crit, est, prec, inv_tau,
+                                                     P(loss_h), P(dXh), P(dYh), P(dWh), P(scratch), nbytes, stream)
+                if st != 0:
+                    raise RuntimeError(lib.mi_status_string(st).decode())
+                return loss_h
+        else:
+            dXh, dYh = torch.empty(Bl, D).pin_memory(), torch.empty(Bl, D).pin_memory()
+            dWh = torch.empty(D, D).pin_memory() if bilinear else None
+
+            def step_host():
+                x, y = Xh.to(dev, non_blocking=True), Yh.to(dev, non_blocking=True)
+                w = Wh.to(dev, non_blocking=True) if bilinear else None
+                s = sh.to(dev, non_blocking=True).to(torch.int64)
+                out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(x, y, w, s, a.estimator, a.precision, inv_tau, True)
+                dXh.copy_(dX, non_blocking=True); dYh.copy_(dY, non_blocking=True)
+                if bilinear:
+                    dWh.copy_(dW, non_blocking=True)
+                return out["loss"].cpu()
+        step_host(); step_host()
+        e_steps = max(2, min(a.steps, 5))
+        e_ms, _, _, _ = timed(step_host, e_steps)
+        e_ms /= e_steps
+        e2e = {"value": B * B / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "h2d_bytes_per_step": world * (2 * n_bd + (n_dd if bilinear else 0) + Bl * 4),
+               "d2h_bytes_per_step": world * (2 * n_bd + (n_dd if bilinear else 0) + 64),
+               "api": "mi_critic_loss_fwd_bwd_host (C ABI, pinned fp32 host buffers)" if world == 1 else
+                      "mi_b200.dist.sharded_critic_loss_fwd_bwd on pinned host shards"}
+
+    launches_t = torch.tensor([launches], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(launches_t)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    f_alg = 6.0 * B * B * D + (6.0 * B * D * D if bilinear else 0.0)
+    sym = a.estimator == "infonce_sym"
+    strict = a.precision == "strict"
+    f_exec = ((2 + (2 if sym else 0)) + 2 * (2 + 2 * (2 if strict else 1))) * float(B) * B * D + (6.0 * B * D * D if bilinear else 0.0)
+    ach = f_alg / (ms_per_step * 1e-3) / 1e12 / world           # per GPU
+    kinds = ["score_stats", "ds_panel", "gemm"]
+    by_kernel = {k: {"ms_per_step": ms[i] / a.steps, "launches_per_step": cnt[i] / a.steps} for i, k in enumerate(kinds)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": B, "dim": D, "critic": a.critic,
+                   "estimator": a.estimator, "precision": a.precision, "parallelism": f"row-sharded x{world}",
+                   "l2": "inputs (2 x %d MB bf16 + >1 GB dS panel per pass) exceed the 126 MB L2; no flush needed" % (B * D * 2 >> 20),
+                   "loss": loss_val},
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
+                     "frac": ach / pk["sustained"], "traffic": None,
+                     "peak_kind": "sustained bf16 (kernel timed inside a long step), " + pk["source"],
+                     "frac_of_burst_peak": ach / pk["burst"], "burst_peak": pk["burst"],
+                     "algorithmic_flops_per_step": f_alg, "executed_flops_per_step": f_exec,
+                     "executed_tflops": f_exec / (ms_per_step * 1e-3) / 1e12 / world,
+                     "kernel": "tile_engine_kernel (all launches of one step; per-kind CUDA-event times in by_kernel)",
+                     "by_kernel": by_kernel},
+        "clocks": clocks, "gpu_launches": int(launches_t.item()),
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not a.no_cpu_baseline:
+        cb = time_cpu(a, 3, 1, budget_s=25.0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

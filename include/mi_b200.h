@@ -123,6 +123,11 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t mi_launch_count(void);
 
+/* Optional CUDA-event timing of every tile-engine launch (records events on the launch stream).
+ * mi_profile_read drains the records: ms[k] / launches[k], k = 0 score statistics, 1 dS panel, 2 GEMM. */
+void mi_set_profiling(int on);
+int mi_profile_read(double* ms /*[3]*/, int64_t* launches /*[3]*/);
+
 /* bring-up / A-B knob: 2 (default) = CTA pairs, cta_group::2 MMAs with M = 256; 1 = single-CTA M = 128.
  * Also settable through the environment variable MI_CTA_GROUP before the first call. */
 void mi_set_cta_group(int group);

@@ -16,6 +16,8 @@ PROTOTYPES = {
     "mi_abi_version": (c_int, []),
     "mi_device_check": (c_int, []),
     "mi_launch_count": (c_i64, []),
+    "mi_set_profiling": (None, [c_int]),
+    "mi_profile_read": (c_int, [c_vp, c_vp]),
     "mi_set_cta_group": (None, [c_int]),
     "mi_get_cta_group": (c_int, []),
     "mi_gemm_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),

@@ -4,6 +4,8 @@
 // Blackwell device is available.
 #include <atomic>
 #include <cmath>
+#include <mutex>
+#include <vector>
 #include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
@@ -19,6 +21,13 @@ using mi::Sched;
 thread_local char g_cuda_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_cta_group = -1;   // resolved lazily: env MI_CTA_GROUP or 2
+
+// optional per-launch CUDA-event timing of the tile-engine kernels (bench.py's roofline breakdown)
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+bool g_profiling = false;
+std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;
+template <class Epi> struct EpiKind;
 
 int cta_group() {
   if (g_cta_group < 0) {
@@ -146,10 +155,24 @@ int launch_engine_cg(const void* A, long long a_rows, long long a_k, long long l
   attr[0].val.clusterDim.x = kCG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  ProfRec rec; rec.kind = EpiKind<Epi>::value; rec.e0 = nullptr; rec.e1 = nullptr;
+  if (g_profiling) {
+    MI_CUDA(cudaEventCreate(&rec.e0)); MI_CUDA(cudaEventCreate(&rec.e1));
+    MI_CUDA(cudaEventRecord(rec.e0, stream));
+  }
   MI_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, sc, ep));
   MI_LAUNCH_CHECK("tile_engine_kernel");
+  if (g_profiling) {
+    MI_CUDA(cudaEventRecord(rec.e1, stream));
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
   return MI_OK;
 }
+
+template <> struct EpiKind<mi::EpiStats> { static constexpr int value = 0; };
+template <> struct EpiKind<mi::EpiPStore> { static constexpr int value = 1; };
+template <> struct EpiKind<mi::EpiStore> { static constexpr int value = 2; };
 
 template <class Epi>
 int launch_engine(const void* A, long long a_rows, long long a_k, long long lda,
@@ -582,6 +605,21 @@ const char* mi_last_cuda_error(void) { return g_cuda_err; }
 int mi_abi_version(void) { return 1; }
 int mi_device_check(void) { return device_check(); }
 int64_t mi_launch_count(void) { return g_launches.load(); }
+void mi_set_profiling(int on) { g_profiling = on != 0; }
+// ms[k], launches[k] for k = 0 (score statistics), 1 (dS panel), 2 (GEMM); drains the records (synchronises them)
+int mi_profile_read(double* ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int k = 0; k < 3; ++k) { ms[k] = 0.0; launches[k] = 0; }
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    MI_CUDA(cudaEventSynchronize(r.e1));
+    MI_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.kind] += t; launches[r.kind] += 1;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return MI_OK;
+}
 void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
 int mi_get_cta_group(void) { return cta_group(); }
 

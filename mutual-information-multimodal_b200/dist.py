@@ -1,0 +1,137 @@
+"""Batch-sharded MI critic / estimator over torch.distributed (one process per GPU, NCCL on NVLink).
+
+The reference has no distributed code at all; this is the data-parallel form of its
+hot path (main_utils.py:220-226).  Rank r owns rows [r*Bl, (r+1)*Bl) of the image and text
+embeddings.  Rows of the score matrix are independent given all text embeddings and columns are
+independent given all projected image embeddings, so the path needs exactly one exchange step:
+
+  1. T_r = X_r W locally (W replicated);  all-gather Y, T and the study ids            (NCCL)
+  2. row statistics of S[r,:] = T_r Y^T and (symmetric InfoNCE) column statistics of S[:,r]
+     with the fused stats kernel — complete per rank, no B x B collective
+  3. all-gather of 8 fp64 scalars per rank (DV: one (max, sum-exp) pair, N_neg, diagonal sum) and,
+     for the InfoNCE forms, of the per-row / per-column log-sum-exp vectors (B floats)
+  4. gradient passes: dT_r from (T_r, Y_all), dY_r from (Y_r, T_all) — same kernels, operands swapped
+  5. dX_r = dT_r W^T locally; dW = sum_r X_r^T dT_r via all-reduce (DDP-style)
+
+``backend`` is the stage-op provider: ``mi_b200.ops`` (CUDA, the only product backend); the CPU
+gloo tests inject an emulation to exercise the sharding / collective logic without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def _world(group):
+    if not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _all_gather_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
+    if world == 1:
+        return x
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def merge_scalars(scal_all: torch.Tensor) -> dict:
+    """scal_all [world, 8] fp64 rows {m, sum exp(lse-m), n_neg, diag_sum, rowloss_sum, rows_wo_neg, 0, 0}
+    -> global quantities (pure tensor math, no host sync)."""
+    m = scal_all[:, 0]
+    gm = torch.max(m)
+    w = torch.where(torch.isfinite(m), torch.exp(m - gm), torch.zeros_like(m))
+    s = (scal_all[:, 1] * w).sum()
+    return {
+        "lse_neg": gm + torch.log(s),
+        "n_neg": scal_all[:, 2].sum(),
+        "diag_sum": scal_all[:, 3].sum(),
+        "rowloss_sum": scal_all[:, 4].sum(),
+        "rows_without_negatives": scal_all[:, 5].sum(),
+    }
+
+
+def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W: Optional[torch.Tensor],
+                                sid_local: torch.Tensor, estimator: str = "dv", precision: str = "fast",
+                                inv_tau: float = 1.0, need_grads: bool = True, group=None, backend=None):
+    """Returns (stats dict of 0-d fp64 tensors incl. 'loss', dX_local, dY_local, dW) — dW already
+    summed over ranks.  All ranks must hold the same number of rows."""
+    if backend is None:
+        from . import ops as backend  # the CUDA path; raises if the library / device is missing
+    world, rank = _world(group)
+    Bl, D = X_local.shape
+    Bg = Bl * world
+    off = rank * Bl
+    bilinear = W is not None
+    sym = estimator == "infonce_sym"
+    dv_like = estimator in ("dv", "infonce", "infonce_ref")
+
+    Xb, Yb = backend.as_bf16(X_local), backend.as_bf16(Y_local)
+    Wb = backend.as_bf16(W) if bilinear else None
+    T_local = backend.gemm(Xb, backend.transpose(Wb), out_dtype=torch.bfloat16) if bilinear else Xb
+
+    # ---- the exchange step
+    Y_all = _all_gather_rows(Yb, world, group)
+    need_T_all = sym or need_grads
+    T_all = _all_gather_rows(T_local, world, group) if need_T_all else None
+    sid_raw = _all_gather_rows(sid_local.to(torch.int64), world, group)
+    _, inv = torch.unique(sid_raw, return_inverse=True)          # identical on every rank
+    sid_all = inv.to(torch.int32)
+    sid_loc = sid_all[off:off + Bl].contiguous()
+
+    # ---- statistics (S never materialised)
+    rows_r, scal_r = backend.score_stats(T_local, Y_all, sid_loc, sid_all, off, inv_tau)
+    g_r = merge_scalars(_all_gather_rows(scal_r.reshape(1, 8), world, group))
+    out = {"pos_mean": g_r["diag_sum"] / Bg, "lse_neg": g_r["lse_neg"], "n_neg": g_r["n_neg"],
+           "loss_row": g_r["rowloss_sum"] / Bg}
+    rows_c = None
+    if sym:
+        rows_c, scal_c = backend.score_stats(Yb, T_all, sid_loc, sid_all, off, inv_tau)
+        g_c = merge_scalars(_all_gather_rows(scal_c.reshape(1, 8), world, group))
+        out["loss_col"] = g_c["rowloss_sum"] / Bg
+    if estimator == "dv":
+        log_n = torch.log(out["n_neg"].to(torch.float32)).to(torch.float64)     # fp32 log N (mi_critics.py:10)
+        out["loss"] = out["lse_neg"] - log_n - out["pos_mean"]
+    elif estimator in ("infonce", "infonce_ref"):
+        out["loss"] = out["lse_neg"] - out["pos_mean"]
+    elif estimator == "infonce_row":
+        out["loss"] = out["loss_row"]
+    elif sym:
+        out["loss"] = 0.5 * (out["loss_row"] + out["loss_col"])
+    else:
+        raise ValueError(f"unknown estimator {estimator!r}")
+    if not need_grads:
+        return out, None, None, None
+
+    # ---- gradient passes
+    gamma = 1.0 / Bg
+    if dv_like:
+        ref = out["lse_neg"].to(torch.float32).expand(Bl).contiguous()
+        row_args = dict(refq=ref, wq=1.0, refk=None, wk=0.0, include_diag=False)
+        col_args = dict(refq=ref, wq=1.0, refk=None, wk=0.0, include_diag=False)
+    else:
+        r_loc = rows_r[:, 3].contiguous()
+        r_all = _all_gather_rows(r_loc, world, group)
+        if sym:
+            c_loc = rows_c[:, 3].contiguous()
+            c_all = _all_gather_rows(c_loc, world, group)
+            row_args = dict(refq=r_loc, wq=0.5 / Bg, refk=c_all, wk=0.5 / Bg, include_diag=True)
+            col_args = dict(refq=c_loc, wq=0.5 / Bg, refk=r_all, wk=0.5 / Bg, include_diag=True)
+        else:
+            row_args = dict(refq=r_loc, wq=1.0 / Bg, refk=None, wk=0.0, include_diag=True)
+            col_args = dict(refq=None, wq=0.0, refk=r_all, wk=1.0 / Bg, include_diag=True)
+    dT32, dT16 = backend.score_grad(T_local, Y_all, sid_loc, sid_all, off, inv_tau, precision=precision,
+                                    alpha=inv_tau, gamma=gamma, sub=Yb, want_f32=not bilinear, want_bf16=bilinear,
+                                    **row_args)
+    dY, _ = backend.score_grad(Yb, T_all, sid_loc, sid_all, off, inv_tau, precision=precision,
+                               alpha=inv_tau, gamma=gamma, sub=T_local, want_f32=True, want_bf16=False, **col_args)
+    if not bilinear:
+        return out, dT32, dY, None
+    dX = backend.gemm(dT16, Wb)                                               # dT W^T
+    dW = backend.gemm(backend.transpose(Xb), backend.transpose(dT16))         # X^T dT (local rows)
+    if world > 1:
+        dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group)
+    return out, dX, dY, dW

@@ -75,15 +75,18 @@ def gemm(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, gamma: float = 0.
     """C = alpha * (A @ B.T - gamma * sub); A [M,K], B [N,K] bf16."""
     _need_cuda(A, B, sub)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.shape[1] == B.shape[1]
-    A, B = A.contiguous(), B.contiguous()
+    A = A if A.stride(1) == 1 and A.stride(0) % 8 == 0 else A.contiguous()     # row-strided views are fine
+    B = B if B.stride(1) == 1 and B.stride(0) % 8 == 0 else B.contiguous()
     M, K = A.shape
     N = B.shape[0]
+    if A.stride(0) % 8 or B.stride(0) % 8:
+        raise MIError("gemm operands need a row pitch that is a multiple of 8 elements (TMA: 16-byte strides)")
     out = torch.empty((M, N), dtype=out_dtype, device=A.device)
     of = _ptr(out) if out_dtype == torch.float32 else None
     ob = _ptr(out) if out_dtype == torch.bfloat16 else None
     if sub is not None:
         sub = sub.contiguous()
-    _check(_lib.load().mi_gemm_bf16(_ptr(A), K, _ptr(B), K, M, N, K, alpha, gamma, _ptr(sub),
+    _check(_lib.load().mi_gemm_bf16(_ptr(A), A.stride(0), _ptr(B), B.stride(0), M, N, K, alpha, gamma, _ptr(sub),
                                     0 if sub is None else sub.shape[1], of, ob, N, None, 0, _stream()), "mi_gemm_bf16")
     return out
 
@@ -93,10 +96,10 @@ def transpose(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
     assert x.dtype == torch.bfloat16 and x.dim() == 2
     x = x.contiguous()
     R, Cc = x.shape
-    ld = ld_out or R
+    ld = ld_out or ((R + 7) // 8) * 8          # pitch padded so the result can feed the TMA-based GEMM
     out = torch.zeros((Cc, ld), dtype=torch.bfloat16, device=x.device)
     _check(_lib.load().mi_transpose_bf16(_ptr(x), Cc, _ptr(out), ld, R, Cc, _stream()), "mi_transpose_bf16")
-    return out
+    return out[:, :R]
 
 
 def score_stats(Q: torch.Tensor, K: torch.Tensor, sid_q: torch.Tensor, sid_k: torch.Tensor,

@@ -37,13 +37,14 @@ CASES = [
 
 def _inputs(B, D, critic, dups, dtype, seed):
     g = torch.Generator().manual_seed(seed)
-    X = torch.relu(torch.randn(B, D, generator=g)).to(dtype)
-    Y = torch.tanh(0.5 * torch.randn(B, D, generator=g) + 0.3 * X.float()).to(dtype)
+    # inputs are bf16-representable so the CUDA path (bf16 operands) sees IDENTICAL values
+    X = torch.relu(torch.randn(B, D, generator=g)).bfloat16().to(dtype)
+    Y = torch.tanh(0.5 * torch.randn(B, D, generator=g) + 0.3 * X.float()).bfloat16().to(dtype)
     sid = [str(50000000 + 7 * i) for i in range(B)]          # numeric strings (utils.py:16-18)
     for a, b in (dups or []):
         sid[b] = sid[a]
     if critic == "bilinear":
-        W = ((torch.eye(D) + 0.1 * torch.randn(D, D, generator=g)) / D ** 0.5).to(dtype)
+        W = ((torch.eye(D) + 0.1 * torch.randn(D, D, generator=g)) / D ** 0.5).bfloat16().to(dtype)
         inv_tau = 1.0
     else:
         W = None

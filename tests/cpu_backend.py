@@ -1,0 +1,63 @@
+"""TEST INFRASTRUCTURE: a CPU emulation of the stage ops of mi_b200.ops with identical semantics
+(include/mi_b200.h), used ONLY to exercise the host-side sharding / collective logic of
+mi_b200.dist under gloo without a GPU.  Never imported by the product."""
+import torch
+
+
+def as_bf16(x):
+    return x.detach().double().contiguous()      # exact arithmetic: isolates the collective logic
+
+
+def gemm(A, B, alpha=1.0, gamma=0.0, sub=None, out_dtype=torch.float32):
+    C = A.double() @ B.double().t()
+    if sub is not None:
+        C = C - gamma * sub.double()
+    return alpha * C                           # no rounding, whatever out_dtype asks for
+
+
+def transpose(x, ld_out=None):
+    return x.t().contiguous()
+
+
+def _scores(Q, K, sid_q, sid_k, q_offset, scale):
+    S = (Q.double() @ K.double().t()) * scale
+    M = sid_q[:, None] != sid_k[None, :]
+    idx = torch.arange(Q.shape[0])
+    return S, M, idx, idx + q_offset
+
+
+def score_stats(Q, K, sid_q, sid_k, q_offset=0, scale=1.0):
+    S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
+    diag = S[i, j]
+    lse_neg = torch.logsumexp(torch.where(M, S, torch.full_like(S, float("-inf"))), 1)
+    n_neg = M.sum(1).double()
+    lse_all = torch.logaddexp(lse_neg, diag)
+    rows = torch.stack([lse_neg, n_neg, diag, lse_all], 1)
+    m = lse_neg.max()
+    scal = torch.zeros(8, dtype=torch.float64)
+    scal[0] = m
+    scal[1] = torch.exp(lse_neg[torch.isfinite(lse_neg)] - m).sum()
+    scal[2] = n_neg.sum()
+    scal[3] = diag.sum()
+    scal[4] = (lse_all - diag).sum()
+    scal[5] = (n_neg == 0).sum()
+    return rows, scal
+
+
+def score_grad(Q, K, sid_q, sid_k, q_offset, scale, refq, wq, refk, wk, include_diag, precision,
+               alpha, gamma, sub, want_f32=True, want_bf16=False):
+    S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
+    incl = M.clone()
+    if include_diag:
+        incl[i, j] = True
+    G = torch.zeros_like(S)
+    if refq is not None and wq > 0:
+        G = G + wq * torch.exp(S - refq.double()[:, None])
+    if refk is not None and wk > 0:
+        G = G + wk * torch.exp(S - refk.double()[None, :])
+    G = torch.where(incl, G, torch.zeros_like(G))
+    O = G @ K.double()
+    if sub is not None:
+        O = O - gamma * sub.double()
+    O = alpha * O
+    return (O if want_f32 else None), (O if want_bf16 else None)

@@ -1,0 +1,168 @@
+"""CPU-side checks (-m "not gpu"): the C-ABI library builds, loads and exports every symbol the
+header declares; it fails loudly without a GPU; the host adapter mirrors the reference API; the
+sharded path's collective logic is right under gloo with world_size 2."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "mi_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from mi_b200 import _lib
+    names = _header_functions()
+    assert len(names) >= 18
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mi_b200.h but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert set(_lib.PROTOTYPES) == set(names)
+    assert _lib.load().mi_abi_version() == 1
+
+
+def test_status_strings_and_planning_without_gpu():
+    from mi_b200 import _lib
+    lib = _lib.load()
+    assert lib.mi_status_string(0) == b"ok"
+    assert b"no CPU fallback" in lib.mi_status_string(-4)
+    # workspace planning is host-only arithmetic
+    small = lib.mi_critic_workspace_bytes(256, 64, 1, 0, 0, 1)
+    big = lib.mi_critic_workspace_bytes(65536, 1024, 1, 3, 1, 1)
+    assert 0 < small < big < (8 << 30)
+    assert lib.mi_score_stats_workspace_bytes(1024, 4096, 768) > 0
+    assert lib.mi_score_grad_workspace_bytes(1024, 4096, 768, 1) > lib.mi_score_grad_workspace_bytes(1024, 4096, 768, 0)
+    assert lib.mi_critic_workspace_bytes(256, 60, 1, 0, 0, 1) == 0      # D % 8 != 0 is rejected
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import mi_b200
+    from mi_b200 import _lib, ops
+    assert _lib.load().mi_device_check() == -4
+    x = torch.zeros(16, 8)
+    with pytest.raises(ops.MIError):
+        ops.gemm(x.bfloat16(), x.bfloat16())
+    critic = mi_b200.FusedCritic(8, "dot")
+    pairs = mi_b200.create_mi_pairs(x, x, [str(i) for i in range(16)])
+    with pytest.raises(ops.MIError):
+        mi_b200.dv_bound_loss(critic(pairs), 16, torch.device("cpu"))
+
+
+def test_adapter_mirrors_reference_api(golden_dir):
+    import mi_b200
+    z = np.load(os.path.join(golden_dir, "known_answers.npz"))
+    l2 = torch.from_numpy(z["rand_logits"])
+    dv = mi_b200.dv_bound_loss(l2, 16, torch.device("cpu"))
+    nce = mi_b200.infonce_bound_loss(l2, 16, torch.device("cpu"))
+    np.testing.assert_array_equal(dv.numpy(), z["rand_dv"])
+    np.testing.assert_array_equal(nce.numpy(), z["rand_infonce"])
+    assert dv.shape == (1,) and nce.shape == ()
+    assert mi_b200.select_estimator("dv") is mi_b200.dv_bound_loss
+    assert mi_b200.select_estimator("infonce") is mi_b200.infonce_bound_loss
+    with pytest.raises(ValueError):
+        mi_b200.select_estimator("mine")
+    c = mi_b200.FusedCritic(32, "bilinear")
+    assert [tuple(p.shape) for p in c.parameters()] == [(32, 32)]
+    assert list(mi_b200.FusedCritic(32, "dot").parameters()) == []
+    X, Y = torch.randn(6, 32), torch.randn(6, 32)
+    sid = ["5", "7", "5", "9", "7", "11"]
+    pairs = mi_b200.create_mi_pairs(X, Y, sid, torch.device("cpu"))
+    assert isinstance(pairs, mi_b200.PairBatch) and pairs.batch_size == 6
+    assert pairs.sid.tolist() == [0, 1, 0, 2, 1, 3]
+    handle = c(pairs)
+    assert isinstance(handle, mi_b200.ScoreHandle)
+    with pytest.raises(ValueError):
+        mi_b200.dv_bound_loss(handle, 5, None)          # pos_size must be the batch size
+    # compat path: explicit pair rows -> [N,1] logits of the same separable critic
+    from oracle import matrix_oracle as mo
+    rows = mo.create_mi_pairs(X, Y, sid)
+    logits = c(rows)
+    assert logits.shape == (rows.shape[0], 1)
+    torch.testing.assert_close(logits, mo.pair_logits_separable(rows, c.W.detach(), c.inv_tau))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dist_worker(rank, world, port, est, critic, ret):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_backend
+    from mi_b200 import dist as mdist
+    from oracle import matrix_oracle as mo
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        B, D = 24, 16
+        X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=5, dup_frac=0.2, bilinear=(critic == "bilinear"))
+        Xb, Yb = X.bfloat16().float(), Y.bfloat16().float()
+        Wb = None if W is None else W.bfloat16().float()
+        sid_raw = sid * 1000003 + 17                         # arbitrary int64 ids
+        Bl = B // world
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xb[sl], Yb[sl], Wb, sid_raw[sl], est, "strict", 0.5,
+                                                           True, None, backend=cpu_backend)
+        ref = mo.critic_loss(Xb, Yb, sid, Wb, 0.5, est)
+        errs = [abs(float(out["loss"]) - float(ref["loss"])),
+                float((dX.double() - ref["dX"][sl]).abs().max() / ref["dX"].abs().max()),
+                float((dY.double() - ref["dY"][sl]).abs().max() / ref["dY"].abs().max())]
+        if dW is not None:
+            errs.append(float((dW.double() - ref["dW"]).abs().max() / ref["dW"].abs().max()))
+        errs.append(abs(float(out["n_neg"]) - float(ref["n_neg"])))
+        ret[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("est", ["dv", "infonce", "infonce_row", "infonce_sym"])
+@pytest.mark.parametrize("critic", ["dot", "bilinear"])
+def test_sharded_path_world2_gloo(est, critic):
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_dist_worker, args=(2, port, est, critic, ret), nprocs=2, join=True)
+    assert len(ret) == 2
+    for rank in range(2):
+        errs = ret[rank]
+        assert errs[0] < 1e-6, (rank, errs)           # fp32 log N_neg and fp32 reference vectors
+        assert max(errs[1:-1]) < 1e-6, (rank, errs)
+        assert errs[-1] == 0
+
+
+def test_merge_scalars_matches_single_block():
+    from mi_b200 import dist as mdist
+    g = torch.Generator().manual_seed(0)
+    lse = torch.randn(40, generator=g, dtype=torch.float64) * 5
+    parts = []
+    for r in range(4):
+        seg = lse[r * 10:(r + 1) * 10]
+        m = seg.max()
+        parts.append(torch.tensor([m, torch.exp(seg - m).sum(), 10.0, 1.0, 2.0, 0, 0, 0], dtype=torch.float64))
+    out = mdist.merge_scalars(torch.stack(parts))
+    assert abs(float(out["lse_neg"]) - float(torch.logsumexp(lse, 0))) < 1e-12
+    assert float(out["n_neg"]) == 40 and float(out["diag_sum"]) == 4
