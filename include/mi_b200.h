@@ -57,14 +57,18 @@ int mi_device_check(void);
 
 /* ---- building blocks --------------------------------------------------------------------------- */
 
+/* hi/lo split operands ("strict", fp32-accumulate mode): a *_split argument of 2 means the bf16 matrix
+ * is a pair stored as [hi | lo] in each row, lo starting at column round_up(D, 64) (D = the logical
+ * width) with zeros in between; value = hi + lo (16 significant bits).  1 = plain bf16. */
+
 /* C[M,N] = alpha * ( A[M,K] * B[N,K]^T - gamma * SUB[M,N] ), bf16 operands (K contiguous), fp32
- * accumulate on tcgen05.  out_f32 and/or out_bf16 may be NULL; SUB may be NULL.  Replaces the
- * nn.Linear-style contractions around the critic (T = X W, dX = dT W^T, dW = X^T dT). */
-size_t mi_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
-int mi_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                 float alpha, float gamma, const void* sub, int64_t ld_sub,
-                 float* out_f32, void* out_bf16, int64_t ld_out,
-                 void* workspace, size_t workspace_bytes, mi_stream_t stream);
+ * accumulate on tcgen05.  out_f32 and/or out_bf16 may be NULL; SUB may be NULL; out_split = 2 writes
+ * out_bf16 as a [hi | lo] pair.  Replaces the nn.Linear-style contractions around the critic
+ * (T = X W, dX = dT W^T, dW = X^T dT). */
+int mi_gemm_bf16(const void* A, int64_t lda, int a_split, const void* B, int64_t ldb, int b_split,
+                 int64_t M, int64_t N, int64_t K, float alpha, float gamma, const void* sub, int64_t ld_sub,
+                 float* out_f32, int64_t ld_out, void* out_bf16, int64_t ld_out16, int out_split,
+                 mi_stream_t stream);
 
 /* out[C,R] = in[R,C]^T (bf16) */
 int mi_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, mi_stream_t stream);
@@ -78,7 +82,7 @@ int mi_cast_f32_to_bf16(const float* in, void* out, int64_t n, mi_stream_t strea
  *   scal_out   = { m = max_q lse_neg, sum_q exp(lse_neg - m), sum_q n_neg, sum_q diag,
  *                  sum_q (lse_all - diag), #rows without negatives, 0, 0 }          (fp64) */
 size_t mi_score_stats_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D);
-int mi_score_stats(const void* Q, int64_t ldq, const void* K, int64_t ldk,
+int mi_score_stats(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
                    const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
                    int64_t Bq, int64_t Bk, int64_t D, float scale,
                    float* row_out /*[Bq,4]*/, double* scal_out /*[8]*/,
@@ -88,16 +92,19 @@ int mi_score_stats(const void* Q, int64_t ldq, const void* K, int64_t ldk,
  * main_utils.py:226): recomputes score tiles, forms
  *   G[q,k] = incl[q,k] * ( wq * exp(S - refq[q]) + wk * exp(S - refk[k]) )
  *   incl   = M  (include_diag = 0, DV)   or   M + diagonal  (include_diag = 1, InfoNCE)
- * and returns  O[Bq,D] = alpha * ( G * K - gamma * SUB ).  refq / refk may be NULL (term unused).
- * The B x B matrix never exists: G is staged as a bounded bf16 row panel in `workspace`. */
+ * and returns  Oq[q,:] = alpha * ( sum_k G[q,k] K[k,:] - gamma * K[q_offset+q,:] )  (fp32 and/or bf16,
+ * optionally hi/lo)  and, when outk_f32 != NULL,
+ *              Ok[k,:] = alpha * ( sum_q G[q,k] Q[q,:] - gamma * [0 <= k-q_offset < Bq] Q[k-q_offset,:] )
+ * from the same score recompute (gamma is the weight of the positive pair, 1/B).
+ * refq / refk may be NULL (term unused).  The B x B matrix never exists: G is staged as a bounded bf16
+ * row panel in `workspace` and consumed by the two tensor-core contractions. */
 size_t mi_score_grad_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision);
-int mi_score_grad(const void* Q, int64_t ldq, const void* K, int64_t ldk,
+int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
                   const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
                   int64_t Bq, int64_t Bk, int64_t D, float scale,
                   const float* refq, float wq, const float* refk, float wk,
-                  int include_diag, int precision,
-                  float alpha, float gamma, const void* sub, int64_t ld_sub,
-                  float* out_f32, void* out_bf16, int64_t ld_out,
+                  int include_diag, int precision, float alpha, float gamma,
+                  float* outq_f32, void* outq_bf16, int64_t ld_outq16, int outq_split, float* outk_f32,
                   void* workspace, size_t workspace_bytes, mi_stream_t stream);
 
 /* ---- the whole path, one GPU ------------------------------------------------------------------- */

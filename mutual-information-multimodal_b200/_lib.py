@@ -20,18 +20,17 @@ PROTOTYPES = {
     "mi_profile_read": (c_int, [c_vp, c_vp]),
     "mi_set_cta_group": (None, [c_int]),
     "mi_get_cta_group": (c_int, []),
-    "mi_gemm_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
-    "mi_gemm_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_i64,
-                             c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "mi_gemm_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_i64,
+                             c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
     "mi_transpose_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "mi_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "mi_score_stats_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
-    "mi_score_stats": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
+    "mi_score_stats": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
                                c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mi_score_grad_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
-    "mi_score_grad": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
-                              c_vp, c_f32, c_vp, c_f32, c_int, c_int, c_f32, c_f32, c_vp, c_i64,
-                              c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "mi_score_grad": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
+                              c_vp, c_f32, c_vp, c_f32, c_int, c_int, c_f32, c_f32,
+                              c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_sz, c_vp]),
     "mi_critic_workspace_bytes": (c_sz, [c_i64, c_i64, c_int, c_int, c_int, c_int]),
     "mi_critic_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -36,6 +36,7 @@ struct Cfg {
   static constexpr int kBBytes = kBRows * BLOCK_K * 2;           // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + slack for 1024 B alignment
+  template <class Epi> static constexpr int smem_bytes() { return kSmemBytes + Epi::kEpiSmemBytes; }
 };
 
 // Work decomposition.  A "unit" is (m block, N-range split, K split); a CTA (pair) walks units
@@ -46,8 +47,14 @@ struct Sched {
   int n_split;    // contiguous N-range splits per M block
   int n_ksplit;   // K splits (split-K GEMM), 1 otherwise
   int order;      // 0: m fastest (concurrent units share the N range), 1: ksplit, split fastest
-  int k_blocks;   // number of 64-wide K blocks
-  int b_kwrap;    // B-operand K coordinate wraps after this many blocks ([P_hi | P_lo] x [V | V])
+  int k_blocks;   // number of 64-wide K blocks per tile (all segments)
+  // K segments: block kb belongs to segment kb / seg_len and reads A at K block a_seg[seg] + kb % seg_len,
+  // B at b_seg[seg] + kb % seg_len.  One segment = plain GEMM; more = sums of products of hi/lo splits,
+  // e.g. [P_hi | P_lo] x [V ; V] or [T_hi | T_lo] x [Y ; Y] (fp32-accumulate "strict" mode).
+  int seg_len;
+  int a_seg[4];
+  int b_seg[4];
+  int a_moff[4];  // MN-major A only: M-coordinate offset of the segment (e.g. the lo half of a [hi | lo] panel)
 };
 
 struct Unit { int m, s, ks, nt0, nt1, kb0, kb1; };
@@ -70,7 +77,11 @@ __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
   return r;
 }
 
-template <int kCG, class Epi>
+// kAMN: the A operand is stored M-contiguous ("MN-major": A[m,k] at base[k*ld + m], i.e. the transpose
+// of a row-major [K, M] matrix).  Its 128 x 64 tile is fetched as two 64(K) x 64(M) boxes and described
+// to the MMA with the MN-major SWIZZLE_128B canonical layout (LBO = 8 KB between the 64-wide M halves,
+// SBO = 1 KB between 8-row K groups).
+template <int kCG, class Epi, bool kAMN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const Sched sc, const typename Epi::Params ep) {
@@ -93,6 +104,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
+  uint8_t* epi_smem = tiles + C::kStages * C::kStageBytes;     // Epi::kEpiSmemBytes of staging, if any
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -125,20 +137,33 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int a_row = (un.m * kCG + (int)cta_rank) * BLOCK_M;
       for (int nt = un.nt0; nt < un.nt1; ++nt) {
         const int b_row = nt * TILE_N + (int)cta_rank * C::kBRows;
+        int seg = un.kb0 / sc.seg_len, w = un.kb0 % sc.seg_len;
         for (int kb = un.kb0; kb < un.kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           uint8_t* sa = tiles + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
-          const int a_k = kb * BLOCK_K;
-          const int b_k = (kb % sc.b_kwrap) * BLOCK_K;
+          const int a_k = (sc.a_seg[seg] + w) * BLOCK_K;
+          const int b_k = (sc.b_seg[seg] + w) * BLOCK_K;
+          const int a_m = a_row + sc.a_moff[seg];
+          if (++w == sc.seg_len) { w = 0; ++seg; }
           if constexpr (kCG == 1) {
             ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], a_k, a_row);
+            if constexpr (kAMN) {
+              ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], a_m, a_k);
+              ptx::tma_load_2d(sa + C::kABytes / 2, &tmap_a, &full_bar[stage], a_m + 64, a_k);
+            } else {
+              ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], a_k, a_row);
+            }
             ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], b_k, b_row);
           } else {
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
             const uint32_t bar = full0_cluster + (uint32_t)stage * 8u;
-            ptx::tma_load_2d_2sm(sa, &tmap_a, bar, a_k, a_row);
+            if constexpr (kAMN) {
+              ptx::tma_load_2d_2sm(sa, &tmap_a, bar, a_m, a_k);
+              ptx::tma_load_2d_2sm(sa + C::kABytes / 2, &tmap_a, bar, a_m + 64, a_k);
+            } else {
+              ptx::tma_load_2d_2sm(sa, &tmap_a, bar, a_k, a_row);
+            }
             ptx::tma_load_2d_2sm(sb, &tmap_b, bar, b_k, b_row);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -150,7 +175,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * kCG, TILE_N);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * kCG, TILE_N) | (kAMN ? (1u << 15) : 0u);
       int stage = 0; uint32_t phase = 0; uint32_t tile_cnt = 0;
       for (int u = pair_id; u < n_units; u += n_pairs) {
         const Unit un = decode_unit(sc, u);
@@ -163,12 +188,14 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             ptx::mbar_wait(&full_bar[stage], phase, 3);
             ptx::tc_fence_after();
             const uint32_t sa = tiles_addr + stage * C::kStageBytes;
-            const uint64_t da = ptx::make_smem_desc_k128(sa);
+            const uint64_t da = kAMN ? ptx::make_smem_desc_mn128(sa, C::kABytes / 2) : ptx::make_smem_desc_k128(sa);
             const uint64_t db = ptx::make_smem_desc_k128(sa + C::kABytes);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16 B units
-              ptx::umma_bf16<kCG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > un.kb0 || k > 0) ? 1u : 0u);
+              // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle row (+2 in 16 B units);
+              // MN-major: advance 16 K rows = two 1 KB swizzle atoms (+128 in 16 B units)
+              const uint64_t a_adv = kAMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
+              ptx::umma_bf16<kCG>(d_tmem, da + a_adv, db + 2 * k, idesc, (kb > un.kb0 || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit<kCG>(&empty_bar[stage], 0x3);     // smem slot reusable once these MMAs retire
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -185,6 +212,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t half = (warp - kEpiWarp0) >> 2;
     uint32_t tile_cnt = 0;
     typename Epi::State st;
+    st.stage_smem = epi_smem + (warp - kEpiWarp0) * (Epi::kEpiSmemBytes / kNumEpiWarps);
     for (int u = pair_id; u < n_units; u += n_pairs) {
       const Unit un = decode_unit(sc, u);
       const int row = (un.m * kCG + (int)cta_rank) * BLOCK_M + (int)(quarter * 32u + lane);
@@ -200,7 +228,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           uint32_t v[32];
           ptx::tmem_ld_32x32(taddr, v);
           ptx::tmem_ld_wait();
-          Epi::chunk(ep, st, un, row, nt * TILE_N + (int)col_in_tile, v);
+          Epi::chunk(ep, st, un, row, nt * TILE_N + (int)col_in_tile, c, v);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -230,6 +258,7 @@ __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); 
 
 // ---- score statistics: per row online (max, sum-exp) over the negatives, negatives count, diagonal
 struct EpiStats {
+  static constexpr int kEpiSmemBytes = 0;
   struct Params {
     const int* sid_q;      // [q_rows] study index of accumulator rows
     const int* sid_k;      // [n_ntile*256] (padded) study index of accumulator columns
@@ -239,13 +268,13 @@ struct EpiStats {
     float4* part;          // [n_split][2][rows_padded]  {max (log2 units), sum, count, diag}
     int rows_padded;
   };
-  struct State { float m, s, cnt, diag; int sidq; };
+  struct State { uint8_t* stage_smem; float m, s, cnt, diag; int sidq; };
 
   static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
     st.m = neg_inf(); st.s = 0.f; st.cnt = 0.f; st.diag = 0.f;
     st.sidq = (row < p.q_rows) ? __ldg(p.sid_q + row) : -1;
   }
-  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0,
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0, int,
                                                const uint32_t (&v)[32]) {
     const float c2 = p.scale * kLog2e;
     const int limit = p.k_cols - col0;
@@ -284,15 +313,17 @@ struct EpiStats {
 };
 
 // ---- dS panel: P[row, col] = incl * ( wq e^{S - refq[row]} + wk e^{S - refk[col]} ), bf16 (hi [+ lo])
+// Each epilogue warp stages 32 rows x 64 columns (4 KB, XOR-swizzled 16 B chunks) in shared memory and
+// writes them out as full 128 B lines (4 rows per warp store) instead of 16 B per row.
 struct EpiPStore {
+  static constexpr int kEpiSmemBytes = kNumEpiWarps * 4096;
   struct Params {
     const int* sid_q;
     const int* sid_k;       // padded to n_ntile*256
     int q_rows, k_cols;
     long long q_offset;
     float scale;
-    const float* refq;      // [q_rows] natural-log reference per row, or nullptr -> refq_const
-    float refq_const;
+    const float* refq;      // [q_rows] natural-log reference per row (used when use_q)
     float ln_wq;            // ln(weight) of the row term
     int use_q;
     const float* refk2;     // [n_ntile*256] (padded) column reference, log2 units, weight folded in
@@ -302,15 +333,34 @@ struct EpiPStore {
     __nv_bfloat16* P_lo;    // residual panel (strict mode) or nullptr
     long long pitch;
   };
-  struct State { float rq2; int sidq; };
+  struct State { uint8_t* stage_smem; float rq2; int sidq; };
 
   static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
     const bool ok = row < p.q_rows;
     st.sidq = ok ? __ldg(p.sid_q + row) : -1;
-    const float r = (p.refq != nullptr && ok) ? __ldg(p.refq + row) : p.refq_const;
+    const float r = (p.use_q && ok) ? __ldg(p.refq + row) : 0.f;
     st.rq2 = (r - p.ln_wq) * kLog2e;
   }
-  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0,
+  // write this thread's 32 packed bf16 (16 words) into its staging row, chunks [4*hc, 4*hc+4)
+  static __device__ __forceinline__ void stage_row(uint8_t* smem, int lane, int hc, const uint32_t (&w)[16]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int chunk = (hc * 4 + g) ^ (lane & 7);
+      *reinterpret_cast<uint4*>(smem + lane * 128 + chunk * 16) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+    }
+  }
+  // the warp copies its 32 x 64 staging tile to global: lane -> (row = 4*it + lane/8, chunk = lane%8)
+  static __device__ __forceinline__ void flush(uint8_t* smem, int lane, __nv_bfloat16* dst_row0, long long pitch, int rows_valid) {
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3), ch = lane & 7;
+      const uint4 val = *reinterpret_cast<const uint4*>(smem + r * 128 + ((ch ^ (r & 7)) * 16));
+      if (r < rows_valid) *reinterpret_cast<uint4*>(dst_row0 + (size_t)r * pitch + ch * 8) = val;
+    }
+    __syncwarp();
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0, int c_idx,
                                                const uint32_t (&v)[32]) {
     const float c2 = p.scale * kLog2e;
     const int limit = p.k_cols - col0;
@@ -318,6 +368,7 @@ struct EpiPStore {
     const int dcol = (p.include_diag && dcol_ll >= 0 && dcol_ll < 32) ? (int)dcol_ll : -1;
     const int4* sk4 = reinterpret_cast<const int4*>(p.sid_k + col0);
     const float4* rk4 = reinterpret_cast<const float4*>(p.refk2 + col0);
+    const int lane = (int)(threadIdx.x & 31);
     float pv[32];
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -336,52 +387,70 @@ struct EpiPStore {
         pv[c] = incl ? val : 0.f;
       }
     }
-    if (row < p.q_rows) {
-      uint4* dst = reinterpret_cast<uint4*>(p.P + (size_t)row * p.pitch + col0);
-      uint32_t hi[16];
+    uint32_t hi[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(pv[2 * c], pv[2 * c + 1]);
+    for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(pv[2 * c], pv[2 * c + 1]);
+    const int hc = c_idx & 1;                       // which 32-column half of the 64-column staging tile
+    const int row0 = row - lane;                    // first row of this warp
+    const int rows_valid = p.q_rows - row0;
+    const int colbase = col0 - hc * 32;
+    if (p.P_lo == nullptr) {
+      stage_row(st.stage_smem, lane, hc, hi);
+      if (hc == 1) flush(st.stage_smem, lane, p.P + (size_t)row0 * p.pitch + colbase, p.pitch, rows_valid);
+    } else {
+      // strict mode: hi and lo panels go out one 32-column half at a time through the same staging tile
+      uint32_t lo[16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) dst[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-      if (p.P_lo != nullptr) {
-        uint4* dlo = reinterpret_cast<uint4*>(p.P_lo + (size_t)row * p.pitch + col0);
-        uint32_t lo[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float h0 = __uint_as_float(hi[c] << 16), h1 = __uint_as_float(hi[c] & 0xffff0000u);
-          lo[c] = ptx::pack_bf16(pv[2 * c] - h0, pv[2 * c + 1] - h1);
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) dlo[g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+      for (int c = 0; c < 16; ++c) {
+        const float h0 = __uint_as_float(hi[c] << 16), h1 = __uint_as_float(hi[c] & 0xffff0000u);
+        lo[c] = ptx::pack_bf16(pv[2 * c] - h0, pv[2 * c + 1] - h1);
       }
+      stage_row(st.stage_smem, lane, 0, hi);
+      stage_row(st.stage_smem, lane, 1, lo);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(st.stage_smem + r * 128 + ((ch ^ (r & 7)) * 16));
+        __nv_bfloat16* base = (ch < 4 ? p.P : p.P_lo) + (size_t)(row0 + r) * p.pitch + col0 + (ch & 3) * 8;
+        if (r < rows_valid) *reinterpret_cast<uint4*>(base) = val;
+      }
+      __syncwarp();
     }
   }
   static __device__ __forceinline__ void unit_end(const Params&, State&, const Unit&, int, int) {}
 };
 
-// ---- plain GEMM epilogue: C = alpha * (ACC - gamma * SUB)
+// ---- plain GEMM epilogue: C = alpha * (ACC - gamma * SUB) [+ C_prev]
 struct EpiStore {
+  static constexpr int kEpiSmemBytes = 0;
   struct Params {
     float* out_f32;            // optional
     __nv_bfloat16* out_bf16;   // optional
-    long long ld_out;
+    __nv_bfloat16* out_bf16_lo;  // optional residual bf16(C - hi) (hi/lo split output), same pitch
+    long long ld_out;          // pitch of out_f32
+    long long ld_out16;        // pitch of out_bf16 / out_bf16_lo
     int rows, cols;
     float alpha, gamma;
     const __nv_bfloat16* sub;  // optional [rows, ld_sub]
+    const __nv_bfloat16* sub_lo;  // optional residual of SUB (SUB = sub + sub_lo), same pitch
     long long ld_sub;
+    int sub_row0, sub_rows;    // SUB row r applies to output row sub_row0 + r, r in [0, sub_rows)
     long long ksplit_stride;   // elements between split-K partial outputs (fp32 only)
+    int accumulate;            // out_f32 += result (panel-by-panel accumulation)
   };
-  struct State { int dummy; };
+  struct State { uint8_t* stage_smem; };
   static __device__ __forceinline__ void unit_begin(const Params&, State&, const Unit&, int, int) {}
-  static __device__ __forceinline__ void chunk(const Params& p, State&, const Unit& un, int row, int col0,
+  static __device__ __forceinline__ void chunk(const Params& p, State&, const Unit& un, int row, int col0, int,
                                                const uint32_t (&v)[32]) {
     if (row >= p.rows || col0 >= p.cols) return;
     float o[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) o[c] = __uint_as_float(v[c]);
     const bool full = (col0 + 32 <= p.cols);
-    if (p.sub != nullptr) {
-      const __nv_bfloat16* s = p.sub + (size_t)row * p.ld_sub + col0;
+    const int srow = row - p.sub_row0;
+    if (p.sub != nullptr && srow >= 0 && srow < p.sub_rows) {
+      const __nv_bfloat16* s = p.sub + (size_t)srow * p.ld_sub + col0;
       if (full) {
         const uint4* s4 = reinterpret_cast<const uint4*>(s);
 #pragma unroll
@@ -397,6 +466,10 @@ struct EpiStore {
       } else {
         for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) o[c] -= p.gamma * __bfloat162float(s[c]);
       }
+      if (p.sub_lo != nullptr) {
+        const __nv_bfloat16* sl = p.sub_lo + (size_t)srow * p.ld_sub + col0;
+        for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) o[c] -= p.gamma * __bfloat162float(sl[c]);
+      }
     }
 #pragma unroll
     for (int c = 0; c < 32; ++c) o[c] *= p.alpha;
@@ -404,22 +477,47 @@ struct EpiStore {
       float* d = p.out_f32 + (size_t)un.ks * p.ksplit_stride + (size_t)row * p.ld_out + col0;
       if (full) {
         float4* d4 = reinterpret_cast<float4*>(d);
+        if (p.accumulate) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 prev = d4[g];
+            o[4 * g] += prev.x; o[4 * g + 1] += prev.y; o[4 * g + 2] += prev.z; o[4 * g + 3] += prev.w;
+          }
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g) d4[g] = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
       } else {
-        for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) d[c] = o[c];
+        for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) { if (p.accumulate) o[c] += d[c]; d[c] = o[c]; }
       }
     }
     if (p.out_bf16 != nullptr) {
-      __nv_bfloat16* d = p.out_bf16 + (size_t)row * p.ld_out + col0;
+      __nv_bfloat16* d = p.out_bf16 + (size_t)row * p.ld_out16 + col0;
+      uint32_t hi[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(o[2 * c], o[2 * c + 1]);
       if (full) {
         uint4* d4 = reinterpret_cast<uint4*>(d);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          d4[g] = make_uint4(ptx::pack_bf16(o[8 * g], o[8 * g + 1]), ptx::pack_bf16(o[8 * g + 2], o[8 * g + 3]),
-                             ptx::pack_bf16(o[8 * g + 4], o[8 * g + 5]), ptx::pack_bf16(o[8 * g + 6], o[8 * g + 7]));
+        for (int g = 0; g < 4; ++g) d4[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
       } else {
         for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) d[c] = __float2bfloat16(o[c]);
+      }
+      if (p.out_bf16_lo != nullptr) {
+        __nv_bfloat16* dl = p.out_bf16_lo + (size_t)row * p.ld_out16 + col0;
+        uint32_t lo[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float h0 = __uint_as_float(hi[c] << 16), h1 = __uint_as_float(hi[c] & 0xffff0000u);
+          lo[c] = ptx::pack_bf16(o[2 * c] - h0, o[2 * c + 1] - h1);
+        }
+        if (full) {
+          uint4* d4 = reinterpret_cast<uint4*>(dl);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) d4[g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+        } else {
+          for (int c = 0; c < 32; ++c)
+            if (col0 + c < p.cols) dl[c] = __float2bfloat16(o[c] - __bfloat162float(__float2bfloat16(o[c])));
+        }
       }
     }
   }

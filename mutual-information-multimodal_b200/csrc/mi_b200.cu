@@ -126,18 +126,23 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long rows, long long k_exten
 }
 
 // ------------------------------------------------------------------------------------ engine launch
-template <int kCG, class Epi>
-int launch_engine_cg(const void* A, long long a_rows, long long a_k, long long lda,
-                     const void* B, long long b_rows, long long b_k, long long ldb,
-                     const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
+struct MapSpec {          // a 2-D bf16 tensor map: `rows` x `k_extent` elements, row pitch ld
+  const void* ptr; long long rows, k_extent, ld;
+};
+
+template <int kCG, class Epi, bool kAMN>
+int launch_engine_cg(const MapSpec& a, const MapSpec& b, const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
   using C = mi::Cfg<kCG>;
   CUtensorMap ta, tb;
-  MI_TRY(make_tmap(&ta, A, a_rows, a_k, lda, mi::BLOCK_M));
-  MI_TRY(make_tmap(&tb, B, b_rows, b_k, ldb, C::kBRows));
-  auto kern = mi::tile_engine_kernel<kCG, Epi>;
+  // MN-major A: the map's contiguous dimension is M, its rows are K; fetched as 64 x 64 boxes
+  if (kAMN) MI_TRY(make_tmap(&ta, a.ptr, a.rows, a.k_extent, a.ld, 64));
+  else MI_TRY(make_tmap(&ta, a.ptr, a.rows, a.k_extent, a.ld, mi::BLOCK_M));
+  MI_TRY(make_tmap(&tb, b.ptr, b.rows, b.k_extent, b.ld, C::kBRows));
+  auto kern = mi::tile_engine_kernel<kCG, Epi, kAMN>;
+  constexpr int smem = C::template smem_bytes<Epi>();
   static bool attr_set = false;
   if (!attr_set) {
-    MI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    MI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int units = sc.n_mblk * sc.n_split * sc.n_ksplit;
@@ -148,7 +153,7 @@ int launch_engine_cg(const void* A, long long a_rows, long long a_k, long long l
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(pairs * kCG), 1, 1);
   cfg.blockDim = dim3(mi::kNumThreads, 1, 1);
-  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -174,16 +179,15 @@ template <> struct EpiKind<mi::EpiStats> { static constexpr int value = 0; };
 template <> struct EpiKind<mi::EpiPStore> { static constexpr int value = 1; };
 template <> struct EpiKind<mi::EpiStore> { static constexpr int value = 2; };
 
-template <class Epi>
-int launch_engine(const void* A, long long a_rows, long long a_k, long long lda,
-                  const void* B, long long b_rows, long long b_k, long long ldb,
-                  const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
-  if (cta_group() == 1) return launch_engine_cg<1, Epi>(A, a_rows, a_k, lda, B, b_rows, b_k, ldb, sc, ep, stream);
-  return launch_engine_cg<2, Epi>(A, a_rows, a_k, lda, B, b_rows, b_k, ldb, sc, ep, stream);
+template <class Epi, bool kAMN = false>
+int launch_engine(const MapSpec& a, const MapSpec& b, const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
+  if (cta_group() == 1) return launch_engine_cg<1, Epi, kAMN>(a, b, sc, ep, stream);
+  return launch_engine_cg<2, Epi, kAMN>(a, b, sc, ep, stream);
 }
 
 inline int rows_per_mblk() { return mi::BLOCK_M * cta_group(); }
 inline int num_pairs() { return num_sms() / cta_group(); }
+inline long long round_up(long long a, long long b) { return cdiv(a, b) * b; }
 
 // N-range splits per M block for the streaming (stats / dS-panel) passes: make the unit count a
 // multiple of the number of CTA pairs, then refine while units stay long enough to amortise.
@@ -197,6 +201,11 @@ int choose_split(int n_mblk, int n_ntile, int U) {
   }
   while (ns * 2 <= n_ntile / 8 && n_mblk * ns < 8 * U) ns *= 2;
   return ns;
+}
+
+void single_segment(Sched& sc) {
+  sc.seg_len = sc.k_blocks;
+  for (int i = 0; i < 4; ++i) { sc.a_seg[i] = 0; sc.b_seg[i] = 0; sc.a_moff[i] = 0; }
 }
 
 // ------------------------------------------------------------------------------------ aux kernels
@@ -333,41 +342,103 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int n_par
 inline unsigned blocks_for(long long n, int t) { return static_cast<unsigned>(cdiv(n, t)); }
 
 // ------------------------------------------------------------------------------------ stages
-int gemm_impl(const void* A, long long lda, const void* B, long long ldb, long long M, long long N, long long K,
-              float alpha, float gamma, const void* sub, long long ld_sub,
-              float* out_f32, void* out_bf16, long long ld_out, int ksplit, long long kwrap_blocks,
-              long long b_k_extent, Bump& ws, cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0) return MI_ERR_BAD_ARG;
+// A bf16 operand [rows, D]; split == 2 means a hi/lo pair stored as [hi | lo] in one row, lo starting
+// at column round_up(D, 64), with zeros in the gap (fp32-accumulate "strict" mode).
+struct Opnd { const __nv_bfloat16* p; long long ld; int split; };
+
+inline long long opnd_k_extent(const Opnd& o, long long D) { return o.split == 2 ? round_up(D, 64) + D : D; }
+
+// K segments for S = Q K^T when one of the operands is a hi/lo pair: (Q_hi + Q_lo) K^T or Q (K_hi + K_lo)^T
+int score_segments(Sched& sc, const Opnd& q, const Opnd& k, long long D) {
+  const int kb = static_cast<int>(cdiv(D, mi::BLOCK_K));
+  single_segment(sc);
+  sc.seg_len = kb;
+  if (q.split == 2 && k.split == 2) return MI_ERR_BAD_ARG;
+  if (q.split == 2) { sc.k_blocks = 2 * kb; sc.a_seg[1] = kb; }
+  else if (k.split == 2) { sc.k_blocks = 2 * kb; sc.b_seg[1] = kb; }
+  else sc.k_blocks = kb;
+  return MI_OK;
+}
+
+struct GemmArgs {
+  MapSpec a, b;
+  bool a_mn = false;          // A stored M-contiguous (transposed view of a row-major [K, M] matrix)
+  long long M = 0, N = 0;
+  int k_blocks = 0;           // total K blocks (all segments)
+  int seg_len = 0;            // 0: one segment
+  int a_seg[4] = {0, 0, 0, 0}, b_seg[4] = {0, 0, 0, 0}, a_moff[4] = {0, 0, 0, 0};
+  int ksplit = 1;
+  float alpha = 1.f, gamma = 0.f;
+  const __nv_bfloat16* sub = nullptr; const __nv_bfloat16* sub_lo = nullptr; long long ld_sub = 0;
+  long long sub_row0 = 0, sub_rows = -1;   // SUB row r applies to output row sub_row0 + r (default: all rows)
+  float* out_f32 = nullptr; long long ld_out = 0;
+  __nv_bfloat16* out_bf16 = nullptr; __nv_bfloat16* out_bf16_lo = nullptr; long long ld_out16 = 0;
+  bool accumulate = false;
+};
+
+int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.k_blocks <= 0) return MI_ERR_BAD_ARG;
   Sched sc;
-  sc.n_mblk = static_cast<int>(cdiv(M, rows_per_mblk()));
-  sc.n_ntile = static_cast<int>(cdiv(N, mi::TILE_N));
+  sc.n_mblk = static_cast<int>(cdiv(g.M, rows_per_mblk()));
+  sc.n_ntile = static_cast<int>(cdiv(g.N, mi::TILE_N));
   sc.n_split = sc.n_ntile;           // one tile per unit
-  sc.k_blocks = static_cast<int>(cdiv(K, mi::BLOCK_K));
-  sc.n_ksplit = ksplit < 1 ? 1 : (ksplit > sc.k_blocks ? sc.k_blocks : ksplit);
+  sc.k_blocks = g.k_blocks;
+  sc.n_ksplit = g.ksplit < 1 ? 1 : (g.ksplit > sc.k_blocks ? sc.k_blocks : g.ksplit);
   sc.order = 1;                      // all N tiles (and K splits) of an M block run concurrently
-  sc.b_kwrap = kwrap_blocks > 0 ? static_cast<int>(kwrap_blocks) : sc.k_blocks;
+  single_segment(sc);
+  if (g.seg_len > 0) {
+    sc.seg_len = g.seg_len;
+    for (int i = 0; i < 4; ++i) { sc.a_seg[i] = g.a_seg[i]; sc.b_seg[i] = g.b_seg[i]; sc.a_moff[i] = g.a_moff[i]; }
+  }
   float* partial = nullptr;
-  if (sc.n_ksplit > 1) partial = ws.take<float>(static_cast<size_t>(sc.n_ksplit) * M * ld_out);
+  if (sc.n_ksplit > 1) partial = ws.take<float>(static_cast<size_t>(sc.n_ksplit) * g.M * g.ld_out);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
-  if (!A || !B || (!out_f32 && !out_bf16)) return MI_ERR_BAD_ARG;
+  if (!g.a.ptr || !g.b.ptr || (!g.out_f32 && !g.out_bf16)) return MI_ERR_BAD_ARG;
   mi::EpiStore::Params ep;
-  ep.out_f32 = sc.n_ksplit > 1 ? partial : out_f32;
-  ep.out_bf16 = sc.n_ksplit > 1 ? nullptr : static_cast<__nv_bfloat16*>(out_bf16);
-  ep.ld_out = ld_out; ep.rows = static_cast<int>(M); ep.cols = static_cast<int>(N);
-  ep.alpha = alpha; ep.gamma = gamma;
-  ep.sub = sc.n_ksplit > 1 ? nullptr : static_cast<const __nv_bfloat16*>(sub);
-  ep.ld_sub = ld_sub;
-  ep.ksplit_stride = static_cast<long long>(M) * ld_out;
-  const long long b_k = b_k_extent > 0 ? b_k_extent : K;
-  MI_TRY(launch_engine<mi::EpiStore>(A, M, K, lda, B, N, b_k, ldb, sc, ep, stream));
-  if (sc.n_ksplit > 1) {
-    if (!out_f32) return MI_ERR_BAD_ARG;
-    const long long n = static_cast<long long>(M) * ld_out;
-    reduce_partials_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(partial, sc.n_ksplit, n, out_f32, n);
+  const bool sk = sc.n_ksplit > 1;
+  ep.out_f32 = sk ? partial : g.out_f32;
+  ep.out_bf16 = sk ? nullptr : g.out_bf16;
+  ep.out_bf16_lo = sk ? nullptr : g.out_bf16_lo;
+  ep.ld_out = g.ld_out; ep.ld_out16 = g.ld_out16;
+  ep.rows = static_cast<int>(g.M); ep.cols = static_cast<int>(g.N);
+  ep.alpha = g.alpha; ep.gamma = g.gamma;
+  ep.sub = sk ? nullptr : g.sub; ep.sub_lo = sk ? nullptr : g.sub_lo; ep.ld_sub = g.ld_sub;
+  ep.sub_row0 = static_cast<int>(g.sub_row0); ep.sub_rows = static_cast<int>(g.sub_rows < 0 ? g.M : g.sub_rows);
+  ep.ksplit_stride = static_cast<long long>(g.M) * g.ld_out;
+  ep.accumulate = (!sk && g.accumulate) ? 1 : 0;
+  if (g.a_mn) MI_TRY((launch_engine<mi::EpiStore, true>(g.a, g.b, sc, ep, stream)));
+  else MI_TRY((launch_engine<mi::EpiStore, false>(g.a, g.b, sc, ep, stream)));
+  if (sk) {
+    if (!g.out_f32 || g.sub || g.accumulate) return MI_ERR_BAD_ARG;
+    const long long n = static_cast<long long>(g.M) * g.ld_out;
+    reduce_partials_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(partial, sc.n_ksplit, n, g.out_f32, n);
     MI_LAUNCH_CHECK("reduce_partials_kernel");
   }
   return MI_OK;
+}
+
+// C = alpha (A B^T - gamma SUB) with optional hi/lo split operands / output (plain K-major operands)
+int gemm_impl(const Opnd& A, const Opnd& B, long long M, long long N, long long K,
+              float alpha, float gamma, const void* sub, long long ld_sub,
+              float* out_f32, long long ld_out, void* out_bf16, long long ld_out16, int out_split, int ksplit,
+              Bump& ws, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return MI_ERR_BAD_ARG;
+  GemmArgs g;
+  const int kb = static_cast<int>(cdiv(K, mi::BLOCK_K));
+  g.a = MapSpec{A.p, M, opnd_k_extent(A, K), A.ld};
+  g.b = MapSpec{B.p, N, opnd_k_extent(B, K), B.ld};
+  g.M = M; g.N = N; g.k_blocks = kb; g.seg_len = kb;
+  if (A.split == 2 && B.split == 2) {           // hi*hi + lo*hi + hi*lo
+    g.k_blocks = 3 * kb; g.a_seg[1] = kb; g.b_seg[2] = kb;
+  } else if (A.split == 2) { g.k_blocks = 2 * kb; g.a_seg[1] = kb; }
+  else if (B.split == 2) { g.k_blocks = 2 * kb; g.b_seg[1] = kb; }
+  g.ksplit = ksplit;
+  g.alpha = alpha; g.gamma = gamma; g.sub = static_cast<const __nv_bfloat16*>(sub); g.ld_sub = ld_sub;
+  g.out_f32 = out_f32; g.ld_out = ld_out;
+  g.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); g.ld_out16 = ld_out16;
+  g.out_bf16_lo = (out_split == 2 && out_bf16) ? g.out_bf16 + round_up(N, 64) : nullptr;
+  return run_gemm(g, ws, stream);
 }
 
 int transpose_impl(const void* in, long long ld_in, void* out, long long ld_out, long long R, long long C, cudaStream_t stream) {
@@ -379,7 +450,7 @@ int transpose_impl(const void* in, long long ld_in, void* out, long long ld_out,
   return MI_OK;
 }
 
-int stats_impl(const void* Q, long long ldq, const void* K, long long ldk, const int* sid_q, const int* sid_k,
+int stats_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
                long long q_offset, long long Bq, long long Bk, long long D, float scale,
                float* row_out, double* scal_out, Bump& ws, cudaStream_t stream) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
@@ -388,21 +459,21 @@ int stats_impl(const void* Q, long long ldq, const void* K, long long ldk, const
   sc.n_ntile = static_cast<int>(cdiv(Bk, mi::TILE_N));
   sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
   sc.n_ksplit = 1; sc.order = 0;
-  sc.k_blocks = static_cast<int>(cdiv(D, mi::BLOCK_K));
-  sc.b_kwrap = sc.k_blocks;
+  MI_TRY(score_segments(sc, Q, K, D));
   const long long k_pad = static_cast<long long>(sc.n_ntile) * mi::TILE_N;
   const int rows_padded = sc.n_mblk * rows_per_mblk();
   int* sidk_pad = ws.take<int>(k_pad);
   float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * 2 * rows_padded);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
-  if (!Q || !K || !sid_q || !sid_k || !row_out || !scal_out) return MI_ERR_BAD_ARG;
+  if (!Q.p || !K.p || !sid_q || !sid_k || !row_out || !scal_out) return MI_ERR_BAD_ARG;
   pad_int_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(sid_k, sidk_pad, Bk, k_pad, -2);
   MI_LAUNCH_CHECK("pad_int_kernel");
   mi::EpiStats::Params ep;
   ep.sid_q = sid_q; ep.sid_k = sidk_pad; ep.q_rows = static_cast<int>(Bq); ep.k_cols = static_cast<int>(Bk);
   ep.q_offset = q_offset; ep.scale = scale; ep.part = part; ep.rows_padded = rows_padded;
-  MI_TRY(launch_engine<mi::EpiStats>(Q, Bq, D, ldq, K, Bk, D, ldk, sc, ep, stream));
+  MI_TRY(launch_engine<mi::EpiStats>(MapSpec{Q.p, Bq, opnd_k_extent(Q, D), Q.ld}, MapSpec{K.p, Bk, opnd_k_extent(K, D), K.ld},
+                                     sc, ep, stream));
   stats_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * 2, rows_padded, static_cast<int>(Bq),
                                                               reinterpret_cast<float4*>(row_out));
   MI_LAUNCH_CHECK("stats_merge_kernel");
@@ -424,26 +495,42 @@ long long panel_mblks(long long Bq, long long Bk, long long D, int precision) {
   return mb;
 }
 
-int grad_impl(const void* Q, long long ldq, const void* K, long long ldk, const int* sid_q, const int* sid_k,
+struct GradOut {            // fp32 and/or bf16 (split == 2: [hi | lo] rows) destination
+  float* f32 = nullptr; long long ld = 0;
+  __nv_bfloat16* bf16 = nullptr; long long ld16 = 0; int split = 1;
+};
+
+// The fused gradient pass.  For every row panel of Q: (1) recompute score tiles and write the bf16 dS
+// panel P (EpiPStore), (2) Oq[panel] = alpha (P K - gamma K_diag)  and, when `ok` is requested,
+// (3) Ok += alpha (P^T Q[panel] - gamma Q_diag) with P read MN-major from the same panel — one score
+// recompute serves both gradients.  "diag" is the positive-pair term: row q pairs with column
+// q_offset + q.  The B x B matrix never exists; P is a bounded row panel in `ws`.
+int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
               long long q_offset, long long Bq, long long Bk, long long D, float scale,
               const float* refq, float wq, const float* refk, float wk, int include_diag, int precision,
-              float alpha, float gamma, const void* sub, long long ld_sub,
-              float* out_f32, void* out_bf16, long long ld_out, Bump& ws, cudaStream_t stream) {
+              float alpha, float gamma, const GradOut& oq, const GradOut* ok, Bump& ws, cudaStream_t stream) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
+  typedef __nv_bfloat16 bf;
   const bool strict = precision == MI_PREC_BF16_STRICT;
   const int n_ntile = static_cast<int>(cdiv(Bk, mi::TILE_N));
   const long long k_pad = static_cast<long long>(n_ntile) * mi::TILE_N;
+  const int kp = static_cast<int>(k_pad / mi::BLOCK_K);
   const long long pitch = k_pad * (strict ? 2 : 1);
-  const long long ld_kt = cdiv(Bk, 64) * 64;
+  const long long Dp = round_up(D, 64);
+  const bool k_hl = strict && K.split == 2, q_hl = strict && Q.split == 2;
+  const long long ld_kt = k_pad * (k_hl ? 2 : 1);
+  const long long q_pad = round_up(Bq, 64);
+  const long long ld_qt = q_pad * (q_hl ? 2 : 1);
   const long long mb_panel = panel_mblks(Bq, Bk, D, precision);
   const long long panel_rows = mb_panel * rows_per_mblk();
   int* sidk_pad = ws.take<int>(k_pad);
   float* refk2 = ws.take<float>(k_pad);
-  __nv_bfloat16* Kt = ws.take<__nv_bfloat16>(static_cast<size_t>(D) * ld_kt);
-  __nv_bfloat16* P = ws.take<__nv_bfloat16>(static_cast<size_t>(panel_rows) * pitch);
+  bf* Kt = ws.take<bf>(static_cast<size_t>(D) * ld_kt);
+  bf* Qt = ok ? ws.take<bf>(static_cast<size_t>(D) * ld_qt) : nullptr;
+  bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
-  if (!Q || !K || !sid_q || !sid_k || (!out_f32 && !out_bf16)) return MI_ERR_BAD_ARG;
+  if (!Q.p || !K.p || !sid_q || !sid_k || (!oq.f32 && !oq.bf16 && !ok)) return MI_ERR_BAD_ARG;
   const bool use_q = refq != nullptr && wq > 0.f, use_k = refk != nullptr && wk > 0.f;
   if (!use_q && !use_k) return MI_ERR_BAD_ARG;
 
@@ -453,50 +540,101 @@ int grad_impl(const void* Q, long long ldq, const void* K, long long ldk, const 
     make_refk2_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(refk, logf(wk), refk2, Bk, k_pad);
     MI_LAUNCH_CHECK("make_refk2_kernel");
   }
-  MI_TRY(transpose_impl(K, ldk, Kt, ld_kt, Bk, D, stream));
+  // V^T for the P K product (K-major B operand): [D, k_pad] (+ the lo half next to it in strict mode)
+  if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
+  MI_TRY(transpose_impl(K.p, K.ld, Kt, ld_kt, Bk, D, stream));
+  if (k_hl) MI_TRY(transpose_impl(K.p + Dp, K.ld, Kt + k_pad, ld_kt, Bk, D, stream));
+  if (ok) {
+    if (q_hl) MI_CUDA(cudaMemsetAsync(Qt, 0, static_cast<size_t>(D) * ld_qt * sizeof(bf), stream));
+    MI_TRY(transpose_impl(Q.p, Q.ld, Qt, ld_qt, Bq, D, stream));
+    if (q_hl) MI_TRY(transpose_impl(Q.p + Dp, Q.ld, Qt + q_pad, ld_qt, Bq, D, stream));
+  }
+  const Opnd Qe{Q.p, Q.ld, strict ? Q.split : 1}, Ke{K.p, K.ld, strict ? K.split : 1};
 
   for (long long r0 = 0; r0 < Bq; r0 += panel_rows) {
     const long long rows = (Bq - r0 < panel_rows) ? (Bq - r0) : panel_rows;
-    // pass 1: recompute score tiles, write the dS panel (never the score matrix)
+    // (1) dS panel
     Sched sc;
     sc.n_mblk = static_cast<int>(cdiv(rows, rows_per_mblk()));
     sc.n_ntile = n_ntile;
     sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
     sc.n_ksplit = 1; sc.order = 0;
-    sc.k_blocks = static_cast<int>(cdiv(D, mi::BLOCK_K));
-    sc.b_kwrap = sc.k_blocks;
+    MI_TRY(score_segments(sc, Qe, Ke, D));
     mi::EpiPStore::Params ep;
     ep.sid_q = sid_q + r0; ep.sid_k = sidk_pad; ep.q_rows = static_cast<int>(rows); ep.k_cols = static_cast<int>(Bk);
     ep.q_offset = q_offset + r0; ep.scale = scale;
-    ep.refq = use_q ? refq + r0 : nullptr; ep.refq_const = 0.f; ep.ln_wq = use_q ? logf(wq) : 0.f; ep.use_q = use_q ? 1 : 0;
+    ep.refq = use_q ? refq + r0 : nullptr; ep.ln_wq = use_q ? logf(wq) : 0.f; ep.use_q = use_q ? 1 : 0;
     ep.refk2 = refk2; ep.use_k = use_k ? 1 : 0; ep.include_diag = include_diag;
     ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
-    const __nv_bfloat16* Qp = static_cast<const __nv_bfloat16*>(Q) + r0 * ldq;
-    MI_TRY(launch_engine<mi::EpiPStore>(Qp, rows, D, ldq, K, Bk, D, ldk, sc, ep, stream));
-    // pass 2: O[panel] = alpha * (P * K - gamma * SUB): GEMM over the Bk dimension
-    const __nv_bfloat16* subp = sub ? static_cast<const __nv_bfloat16*>(sub) + r0 * ld_sub : nullptr;
-    float* of = out_f32 ? out_f32 + r0 * ld_out : nullptr;
-    __nv_bfloat16* ob = out_bf16 ? static_cast<__nv_bfloat16*>(out_bf16) + r0 * ld_out : nullptr;
+    MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
+                                        MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
     Bump none(nullptr, 0, false);
-    MI_TRY(gemm_impl(P, pitch, Kt, ld_kt, rows, D, strict ? 2 * k_pad : k_pad, alpha, gamma, subp, ld_sub,
-                     of, ob, ld_out, 1, strict ? k_pad / mi::BLOCK_K : 0, Bk, none, stream));
+    // (2) Oq[panel] = alpha (P V - gamma SUB), contraction over the Bk columns
+    if (oq.f32 || oq.bf16) {
+      GemmArgs g;
+      g.a = MapSpec{P, rows, pitch, pitch};
+      g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
+      g.M = rows; g.N = D; g.seg_len = kp; g.k_blocks = kp;
+      if (strict) {                                  // P_hi V_hi + P_lo V_hi (+ P_hi V_lo)
+        g.k_blocks = 2 * kp; g.a_seg[1] = kp;
+        if (k_hl) { g.k_blocks = 3 * kp; g.b_seg[2] = kp; }
+      }
+      g.alpha = alpha; g.gamma = gamma;
+      if (gamma != 0.f) {                            // - gamma K[q_offset + q]
+        g.sub = K.p + (q_offset + r0) * K.ld; g.ld_sub = K.ld;
+        g.sub_lo = k_hl ? g.sub + Dp : nullptr;
+      }
+      g.out_f32 = oq.f32 ? oq.f32 + r0 * oq.ld : nullptr; g.ld_out = oq.ld;
+      g.out_bf16 = oq.bf16 ? oq.bf16 + r0 * oq.ld16 : nullptr; g.ld_out16 = oq.ld16;
+      g.out_bf16_lo = (oq.bf16 && oq.split == 2) ? g.out_bf16 + Dp : nullptr;
+      MI_TRY(run_gemm(g, none, stream));
+    }
+    // (3) Ok += alpha (P^T Q[panel] - gamma SUBk), contraction over the panel's rows; P read MN-major
+    if (ok) {
+      GemmArgs g;
+      const int kr = static_cast<int>(cdiv(rows, mi::BLOCK_K));
+      g.a_mn = true;
+      g.a = MapSpec{P, rows, pitch, pitch};            // map rows = K (panel rows), contiguous = M (columns of S)
+      g.b = MapSpec{Qt + r0, D, q_hl ? q_pad + (Bq - r0) : (Bq - r0), ld_qt};
+      g.M = Bk; g.N = D; g.seg_len = kr; g.k_blocks = kr;
+      const int q_lo_blk = static_cast<int>(q_pad / mi::BLOCK_K);
+      if (strict) {                                  // P_hi^T Q_hi + P_lo^T Q_hi (+ P_hi^T Q_lo)
+        g.k_blocks = 2 * kr; g.a_moff[1] = static_cast<int>(k_pad);
+        if (q_hl) { g.k_blocks = 3 * kr; g.b_seg[2] = q_lo_blk; }
+      }
+      g.alpha = alpha; g.gamma = gamma;
+      g.accumulate = r0 > 0;
+      if (gamma != 0.f) {                            // - gamma Q[k - q_offset] on this panel's own columns
+        g.sub = Q.p + r0 * Q.ld; g.ld_sub = Q.ld;
+        g.sub_lo = q_hl ? g.sub + Dp : nullptr;
+        g.sub_row0 = q_offset + r0; g.sub_rows = rows;
+      }
+      g.out_f32 = ok->f32; g.ld_out = ok->ld;
+      MI_TRY(run_gemm(g, none, stream));
+    }
   }
   return MI_OK;
 }
 
-int critic_impl(const void* X, const void* Y, const void* W, const int* sid, long long B, long long D,
+int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, long long B, long long D,
                 int critic, int estimator, int precision, float inv_tau,
                 double* loss_out, float* dX, float* dY, float* dW, Bump& ws, cudaStream_t stream) {
   if (B <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   if (estimator < MI_EST_DV || estimator > MI_EST_INFONCE_SYM) return MI_ERR_BAD_ARG;
+  typedef __nv_bfloat16 bf;
+  const bf* X = static_cast<const bf*>(X_); const bf* Y = static_cast<const bf*>(Y_); const bf* W = static_cast<const bf*>(W_);
   const bool bilinear = critic == MI_CRITIC_BILINEAR;
   const bool grads = dX != nullptr || dY != nullptr || dW != nullptr;
+  const bool plan = ws.dry || grads;
   const bool sym = estimator == MI_EST_INFONCE_SYM;
   const bool dv_like = estimator == MI_EST_DV || estimator == MI_EST_INFONCE_REF;
-  typedef __nv_bfloat16 bf;
-  const long long ldb64 = cdiv(B, 64) * 64;
+  const bool strict = precision == MI_PREC_BF16_STRICT;
+  const int tsplit = (bilinear && strict) ? 2 : 1;        // T = X W kept as a hi/lo bf16 pair in strict mode
+  const long long Dp = round_up(D, 64);
+  const long long ldT = tsplit == 2 ? 2 * Dp : D;
+  const long long b_pad = round_up(B, 64);
   bf* Wt = bilinear ? ws.take<bf>(static_cast<size_t>(D) * D) : nullptr;
-  bf* T = bilinear ? ws.take<bf>(static_cast<size_t>(B) * D) : nullptr;
+  bf* T = bilinear ? ws.take<bf>(static_cast<size_t>(B) * ldT) : nullptr;
   float* rows_r = ws.take<float>(static_cast<size_t>(B) * 4);
   float* rows_c = sym ? ws.take<float>(static_cast<size_t>(B) * 4) : nullptr;
   double* scal_r = ws.take<double>(8);
@@ -504,30 +642,33 @@ int critic_impl(const void* X, const void* Y, const void* W, const int* sid, lon
   float* lse_f = ws.take<float>(1);
   float* ref_r = ws.take<float>(B);
   float* ref_c = sym ? ws.take<float>(B) : nullptr;
-  bf* dT16 = (bilinear && ws.dry) || (bilinear && grads) ? ws.take<bf>(static_cast<size_t>(B) * D) : nullptr;
-  bf* Xt = (bilinear && ws.dry) || (bilinear && grads) ? ws.take<bf>(static_cast<size_t>(D) * ldb64) : nullptr;
-  bf* dTt = (bilinear && ws.dry) || (bilinear && grads) ? ws.take<bf>(static_cast<size_t>(D) * ldb64) : nullptr;
+  bf* dT16 = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(B) * ldT) : nullptr;
+  bf* Xt = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(D) * b_pad) : nullptr;
+  bf* dTt = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(D) * b_pad * tsplit) : nullptr;
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (!ws.dry && (!X || !Y || !sid || !loss_out || (bilinear && !W))) return MI_ERR_BAD_ARG;
 
-  const void* Tq = bilinear ? static_cast<const void*>(T) : X;
-  if (bilinear) {
-    if (!ws.dry) MI_TRY(transpose_impl(W, D, Wt, D, D, D, stream));
-    // T = X W  (B operand of the engine is [N, K] = W^T)
-    MI_TRY(gemm_impl(X, D, Wt, D, B, D, D, 1.f, 0.f, nullptr, 0, nullptr, T, D, 1, 0, 0, ws, stream));
-  }
+  const Opnd Xo{X, D, 1}, Yo{Y, D, 1};
+  const Opnd To = bilinear ? Opnd{T, ldT, tsplit} : Xo;
   size_t mk = ws.mark();
-  MI_TRY(stats_impl(Tq, D, Y, D, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
+  if (bilinear) {
+    if (!ws.dry) {
+      MI_TRY(transpose_impl(W, D, Wt, D, D, D, stream));
+      if (tsplit == 2) MI_CUDA(cudaMemsetAsync(T, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
+    }
+    // T = X W  (B operand of the engine is [N, K] = W^T)
+    MI_TRY(gemm_impl(Xo, Opnd{Wt, D, 1}, B, D, D, 1.f, 0.f, nullptr, 0, nullptr, 0, T, ldT, tsplit, 1, ws, stream));
+    ws.release(mk);
+  }
+  MI_TRY(stats_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
   ws.release(mk);
-  if (sym) { MI_TRY(stats_impl(Y, D, Tq, D, sid, sid, 0, B, B, D, inv_tau, rows_c, scal_c, ws, stream)); ws.release(mk); }
+  if (sym) { MI_TRY(stats_impl(Yo, To, sid, sid, 0, B, B, D, inv_tau, rows_c, scal_c, ws, stream)); ws.release(mk); }
   if (!ws.dry) {
     loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, scal_c, B, estimator, loss_out, lse_f);
     MI_LAUNCH_CHECK("loss_finalize_kernel");
   }
-  if (!grads && !ws.dry) return MI_OK;
+  if (!plan) return MI_OK;
 
-  float wq, wk;
-  const float* refq_row; const float* refk_row; const float* refq_col; const float* refk_col;
   if (!ws.dry) {
     if (dv_like) make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_r, nullptr, 0, lse_f, B);
     else make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_r, reinterpret_cast<const float4*>(rows_r), 3, nullptr, B);
@@ -537,41 +678,58 @@ int critic_impl(const void* X, const void* Y, const void* W, const int* sid, lon
       MI_LAUNCH_CHECK("make_ref_kernel");
     }
   }
+  // G = incl (wq e^{S - refq[row]} + wk e^{S - refk[col]}):  DV: e^{S - LSE} on the negatives;
+  // InfoNCE row: (1/B) e^{S - r_i};  symmetric: (1/2B)(e^{S - r_i} + e^{S - c_j}); positives included.
+  float wq = 1.f, wk = 0.f;
+  const float* refq = ref_r; const float* refk = nullptr;
+  if (estimator == MI_EST_INFONCE_ROW) { wq = 1.f / B; }
+  else if (sym) { wq = 0.5f / B; wk = 0.5f / B; refk = ref_c; }
   const int incl_diag = dv_like ? 0 : 1;
-  if (dv_like)                              { wq = 1.f; wk = 0.f; refq_row = ref_r; refk_row = nullptr; refq_col = ref_r; refk_col = nullptr; }
-  else if (estimator == MI_EST_INFONCE_ROW) { wq = 1.f / B; wk = 1.f / B; refq_row = ref_r; refk_row = nullptr; refq_col = nullptr; refk_col = ref_r; }
-  else                                      { wq = 0.5f / B; wk = 0.5f / B; refq_row = ref_r; refk_row = ref_c; refq_col = ref_c; refk_col = ref_r; }
   const float gamma = 1.f / static_cast<float>(B);
 
-  // row pass: dT = inv_tau * (G Y - Y/B)
-  float* dT32 = bilinear ? nullptr : dX;
-  if (bilinear || dX || ws.dry) {
-    MI_TRY(grad_impl(Tq, D, Y, D, sid, sid, 0, B, B, D, inv_tau, refq_row, wq, refk_row, wk, incl_diag, precision,
-                     inv_tau, gamma, Y, D, dT32, bilinear ? static_cast<void*>(dT16) : nullptr, D, ws, stream));
-    ws.release(mk);
-  }
-  // column pass: dY = inv_tau * (G^T T - T/B)   (same kernels, operands swapped)
-  if (dY || ws.dry) {
-    MI_TRY(grad_impl(Y, D, Tq, D, sid, sid, 0, B, B, D, inv_tau, refq_col, wq, refk_col, wk, incl_diag, precision,
-                     inv_tau, gamma, Tq, D, dY, nullptr, D, ws, stream));
+  // one pass: dT = inv_tau (G Y - Y/B)  and  dY = inv_tau (G^T T - T/B)
+  GradOut oq, okk;
+  if (bilinear) { oq.bf16 = dT16; oq.ld16 = ldT; oq.split = tsplit; }
+  else { oq.f32 = dX; oq.ld = D; }
+  okk.f32 = dY; okk.ld = D;
+  const bool want_q = bilinear ? (dX || dW || ws.dry) : (dX || ws.dry);
+  const bool want_k = dY || ws.dry;
+  GradOut oq_none;
+  if (want_q || want_k) {
+    if (tsplit == 2 && !ws.dry) MI_CUDA(cudaMemsetAsync(dT16, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
+    MI_TRY(grad_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, refq, wq, refk, wk, incl_diag, precision,
+                     inv_tau, gamma, want_q ? oq : oq_none, want_k ? &okk : nullptr, ws, stream));
     ws.release(mk);
   }
   if (bilinear) {
+    const Opnd dTo{dT16, ldT, tsplit};
     // dX = dT W^T : B operand [N = d, K = e] is W itself
-    if (dX || ws.dry)
-      MI_TRY(gemm_impl(dT16, D, W, D, B, D, D, 1.f, 0.f, nullptr, 0, dX, nullptr, D, 1, 0, 0, ws, stream));
-    // dW = X^T dT : A = X^T [D, B], B operand = dT^T [D, B], split-K over the batch
+    if (dX || ws.dry) {
+      MI_TRY(gemm_impl(dTo, Opnd{W, D, 1}, B, D, D, 1.f, 0.f, nullptr, 0, dX, D, nullptr, 0, 1, 1, ws, stream));
+      ws.release(mk);
+    }
+    // dW = X^T dT : A = X^T [D, B], B operand = dT^T [D, B] (hi | lo halves side by side), split-K over the batch
     if (dW || ws.dry) {
       if (!ws.dry) {
-        MI_TRY(transpose_impl(X, D, Xt, ldb64, B, D, stream));
-        MI_TRY(transpose_impl(dT16, D, dTt, ldb64, B, D, stream));
+        MI_TRY(transpose_impl(X, D, Xt, b_pad, B, D, stream));
+        if (tsplit == 2) MI_CUDA(cudaMemsetAsync(dTt, 0, static_cast<size_t>(D) * b_pad * tsplit * sizeof(bf), stream));
+        MI_TRY(transpose_impl(dT16, ldT, dTt, b_pad * tsplit, B, D, stream));
+        if (tsplit == 2) MI_TRY(transpose_impl(dT16 + Dp, ldT, dTt + b_pad, b_pad * tsplit, B, D, stream));
       }
+      GemmArgs g;
+      const int kb = static_cast<int>(b_pad / mi::BLOCK_K);
+      g.a = MapSpec{Xt, D, B, b_pad};
+      g.b = MapSpec{dTt, D, tsplit == 2 ? b_pad + B : B, b_pad * tsplit};
+      g.M = D; g.N = D; g.seg_len = kb; g.k_blocks = kb;
+      if (tsplit == 2) { g.k_blocks = 2 * kb; g.b_seg[1] = kb; }
       const long long tiles = cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N);
       long long ks = cdiv(num_pairs(), tiles);
-      const long long kb = cdiv(B, mi::BLOCK_K);
-      if (ks > kb / 4) ks = kb / 4;
+      if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
       if (ks < 1) ks = 1;
-      MI_TRY(gemm_impl(Xt, ldb64, dTt, ldb64, D, D, B, 1.f, 0.f, nullptr, 0, dW, nullptr, D, static_cast<int>(ks), 0, 0, ws, stream));
+      g.ksplit = static_cast<int>(ks);
+      g.out_f32 = dW; g.ld_out = D;
+      MI_TRY(run_gemm(g, ws, stream));
+      ws.release(mk);
     }
   }
   return MI_OK;
@@ -602,7 +760,7 @@ const char* mi_status_string(int status) {
   }
 }
 const char* mi_last_cuda_error(void) { return g_cuda_err; }
-int mi_abi_version(void) { return 1; }
+int mi_abi_version(void) { return 2; }
 int mi_device_check(void) { return device_check(); }
 int64_t mi_launch_count(void) { return g_launches.load(); }
 void mi_set_profiling(int on) { g_profiling = on != 0; }
@@ -623,15 +781,15 @@ int mi_profile_read(double* ms, int64_t* launches) {
 void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
 int mi_get_cta_group(void) { return cta_group(); }
 
-size_t mi_gemm_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-int mi_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                 float alpha, float gamma, const void* sub, int64_t ld_sub,
-                 float* out_f32, void* out_bf16, int64_t ld_out,
-                 void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+int mi_gemm_bf16(const void* A, int64_t lda, int a_split, const void* B, int64_t ldb, int b_split,
+                 int64_t M, int64_t N, int64_t K, float alpha, float gamma, const void* sub, int64_t ld_sub,
+                 float* out_f32, int64_t ld_out, void* out_bf16, int64_t ld_out16, int out_split,
+                 mi_stream_t stream) {
   MI_TRY(device_check());
-  Bump ws(workspace, workspace_bytes, false);
-  return gemm_impl(A, lda, B, ldb, M, N, K, alpha, gamma, sub, ld_sub, out_f32, out_bf16, ld_out, 1, 0, 0, ws,
-                   reinterpret_cast<cudaStream_t>(stream));
+  Bump ws(nullptr, 0, false);
+  return gemm_impl(Opnd{static_cast<const __nv_bfloat16*>(A), lda, a_split == 2 ? 2 : 1},
+                   Opnd{static_cast<const __nv_bfloat16*>(B), ldb, b_split == 2 ? 2 : 1}, M, N, K, alpha, gamma, sub, ld_sub,
+                   out_f32, ld_out, out_bf16, ld_out16, out_split, 1, ws, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mi_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, mi_stream_t stream) {
@@ -650,36 +808,51 @@ int mi_cast_f32_to_bf16(const float* in, void* out, int64_t n, mi_stream_t strea
 
 size_t mi_score_stats_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D) {
   Bump ws(nullptr, 0, true);
-  if (stats_impl(nullptr, D, nullptr, D, nullptr, nullptr, 0, Bq, Bk, D, 1.f, nullptr, nullptr, ws, nullptr) != MI_OK) return 0;
+  if (stats_impl(Opnd{nullptr, D, 1}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, Bk, D, 1.f, nullptr, nullptr, ws, nullptr) != MI_OK) return 0;
   return ws.peak + 256;
 }
-int mi_score_stats(const void* Q, int64_t ldq, const void* K, int64_t ldk,
+int mi_score_stats(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
                    const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
                    int64_t Bq, int64_t Bk, int64_t D, float scale, float* row_out, double* scal_out,
                    void* workspace, size_t workspace_bytes, mi_stream_t stream) {
   MI_TRY(device_check());
   Bump ws(workspace, workspace_bytes, false);
-  return stats_impl(Q, ldq, K, ldk, sid_q, sid_k, q_offset, Bq, Bk, D, scale, row_out, scal_out, ws,
-                    reinterpret_cast<cudaStream_t>(stream));
+  return stats_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
+                    Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
+                    sid_q, sid_k, q_offset, Bq, Bk, D, scale, row_out, scal_out, ws, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t mi_score_grad_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision) {
   Bump ws(nullptr, 0, true);
-  if (grad_impl(nullptr, D, nullptr, D, nullptr, nullptr, 0, Bq, Bk, D, 1.f, nullptr, 1.f, nullptr, 0.f, 0, precision,
-                1.f, 0.f, nullptr, 0, nullptr, nullptr, D, ws, nullptr) != MI_OK) return 0;
-  return ws.peak + 256;
+  GradOut oq, ok;
+  // planned for the largest variant: hi/lo operands and both outputs
+  const int sp = precision == MI_PREC_BF16_STRICT ? 2 : 1;
+  if (grad_impl(Opnd{nullptr, D, sp}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, Bk, D, 1.f, nullptr, 1.f, nullptr, 0.f, 0, precision,
+                1.f, 0.f, oq, &ok, ws, nullptr) != MI_OK) return 0;
+  const size_t a = ws.peak;
+  Bump ws2(nullptr, 0, true);
+  if (grad_impl(Opnd{nullptr, D, 1}, Opnd{nullptr, D, sp}, nullptr, nullptr, 0, Bq, Bk, D, 1.f, nullptr, 1.f, nullptr, 0.f, 0, precision,
+                1.f, 0.f, oq, &ok, ws2, nullptr) != MI_OK) return 0;
+  return (a > ws2.peak ? a : ws2.peak) + 256;
 }
-int mi_score_grad(const void* Q, int64_t ldq, const void* K, int64_t ldk,
+int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
                   const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
                   int64_t Bq, int64_t Bk, int64_t D, float scale,
                   const float* refq, float wq, const float* refk, float wk, int include_diag, int precision,
-                  float alpha, float gamma, const void* sub, int64_t ld_sub,
-                  float* out_f32, void* out_bf16, int64_t ld_out,
+                  float alpha, float gamma,
+                  float* outq_f32, void* outq_bf16, int64_t ld_outq16, int outq_split, float* outk_f32,
                   void* workspace, size_t workspace_bytes, mi_stream_t stream) {
   MI_TRY(device_check());
+  if (q_offset < 0 || q_offset + Bq > Bk) return MI_ERR_BAD_ARG;
   Bump ws(workspace, workspace_bytes, false);
-  return grad_impl(Q, ldq, K, ldk, sid_q, sid_k, q_offset, Bq, Bk, D, scale, refq, wq, refk, wk, include_diag, precision,
-                   alpha, gamma, sub, ld_sub, out_f32, out_bf16, ld_out, ws, reinterpret_cast<cudaStream_t>(stream));
+  GradOut oq, ok;
+  oq.f32 = outq_f32; oq.ld = D;
+  oq.bf16 = static_cast<__nv_bfloat16*>(outq_bf16); oq.ld16 = ld_outq16; oq.split = outq_split == 2 ? 2 : 1;
+  ok.f32 = outk_f32; ok.ld = D;
+  return grad_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
+                   Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
+                   sid_q, sid_k, q_offset, Bq, Bk, D, scale, refq, wq, refk, wk, include_diag, precision,
+                   alpha, gamma, oq, outk_f32 ? &ok : nullptr, ws, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t mi_critic_workspace_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads) {

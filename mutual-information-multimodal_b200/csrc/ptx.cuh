@@ -169,6 +169,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile (element (mn, k) at k*128 B + mn*2 B inside each 64-wide MN group, TMA
+// SWIZZLE_128B): 8-row K groups are 1024 B apart (SBO), 64-element MN groups `mn_group_bytes` apart
+// (LBO).  Matches cute::UMMA canonical layout "B128, Major-MN".  Needs the a_major/b_major idesc bit.
+__device__ __forceinline__ uint64_t make_smem_desc_mn128(uint32_t smem_addr, uint32_t mn_group_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(mn_group_bytes >> 4) << 16;     // leading byte offset
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // bf16 x bf16 -> fp32, both operands K-major, tile M x N
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4)                       // accumulator fp32

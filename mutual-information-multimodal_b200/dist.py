@@ -5,12 +5,14 @@ hot path (main_utils.py:220-226).  Rank r owns rows [r*Bl, (r+1)*Bl) of the imag
 embeddings.  Rows of the score matrix are independent given all text embeddings and columns are
 independent given all projected image embeddings, so the path needs exactly one exchange step:
 
-  1. T_r = X_r W locally (W replicated);  all-gather Y, T and the study ids            (NCCL)
+  1. T_r = X_r W locally (W replicated);  all-gather Y and the study ids (and T for the symmetric
+     estimator's column statistics)                                                       (NCCL)
   2. row statistics of S[r,:] = T_r Y^T and (symmetric InfoNCE) column statistics of S[:,r]
      with the fused stats kernel — complete per rank, no B x B collective
   3. all-gather of 8 fp64 scalars per rank (DV: one (max, sum-exp) pair, N_neg, diagonal sum) and,
-     for the InfoNCE forms, of the per-row / per-column log-sum-exp vectors (B floats)
-  4. gradient passes: dT_r from (T_r, Y_all), dY_r from (Y_r, T_all) — same kernels, operands swapped
+     for the symmetric form, of the per-column log-sum-exp vector (B floats)
+  4. ONE gradient pass per rank over its row block: dT_r (complete) and the rank's contribution to
+     every dY_j from the same score recompute; reduce-scatter of the [B, D] fp32 contributions
   5. dX_r = dT_r W^T locally; dW = sum_r X_r^T dT_r via all-reduce (DDP-style)
 
 ``backend`` is the stage-op provider: ``mi_b200.ops`` (CUDA, the only product backend); the CPU
@@ -54,6 +56,13 @@ def merge_scalars(scal_all: torch.Tensor) -> dict:
     }
 
 
+def _gather_mat(m, world, group):
+    """all-gather rows of a plain tensor or of a hi/lo pair (ops.SplitBF16)."""
+    if hasattr(m, "data") and hasattr(m, "width") and not torch.is_tensor(m):
+        return type(m)(_all_gather_rows(m.data, world, group), m.width)
+    return _all_gather_rows(m, world, group)
+
+
 def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W: Optional[torch.Tensor],
                                 sid_local: torch.Tensor, estimator: str = "dv", precision: str = "fast",
                                 inv_tau: float = 1.0, need_grads: bool = True, group=None, backend=None):
@@ -68,15 +77,16 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     bilinear = W is not None
     sym = estimator == "infonce_sym"
     dv_like = estimator in ("dv", "infonce", "infonce_ref")
+    strict = precision == "strict"
 
     Xb, Yb = backend.as_bf16(X_local), backend.as_bf16(Y_local)
     Wb = backend.as_bf16(W) if bilinear else None
-    T_local = backend.gemm(Xb, backend.transpose(Wb), out_dtype=torch.bfloat16) if bilinear else Xb
+    # strict mode keeps T = X W as a hi/lo bf16 pair (16 significant bits into the score GEMM)
+    T_local = backend.gemm(Xb, backend.transpose(Wb), out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb
 
     # ---- the exchange step
     Y_all = _all_gather_rows(Yb, world, group)
-    need_T_all = sym or need_grads
-    T_all = _all_gather_rows(T_local, world, group) if need_T_all else None
+    T_all = _gather_mat(T_local, world, group) if sym else None
     sid_raw = _all_gather_rows(sid_local.to(torch.int64), world, group)
     _, inv = torch.unique(sid_raw, return_inverse=True)          # identical on every rank
     sid_all = inv.to(torch.int32)
@@ -106,28 +116,28 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     if not need_grads:
         return out, None, None, None
 
-    # ---- gradient passes
+    # ---- one gradient pass per rank: dT_r (complete) and this rank's contribution to every dY_j
     gamma = 1.0 / Bg
     if dv_like:
         ref = out["lse_neg"].to(torch.float32).expand(Bl).contiguous()
-        row_args = dict(refq=ref, wq=1.0, refk=None, wk=0.0, include_diag=False)
-        col_args = dict(refq=ref, wq=1.0, refk=None, wk=0.0, include_diag=False)
+        args = dict(refq=ref, wq=1.0, refk=None, wk=0.0, include_diag=False)
+    elif sym:
+        c_all = _all_gather_rows(rows_c[:, 3].contiguous(), world, group)
+        args = dict(refq=rows_r[:, 3].contiguous(), wq=0.5 / Bg, refk=c_all, wk=0.5 / Bg, include_diag=True)
     else:
-        r_loc = rows_r[:, 3].contiguous()
-        r_all = _all_gather_rows(r_loc, world, group)
-        if sym:
-            c_loc = rows_c[:, 3].contiguous()
-            c_all = _all_gather_rows(c_loc, world, group)
-            row_args = dict(refq=r_loc, wq=0.5 / Bg, refk=c_all, wk=0.5 / Bg, include_diag=True)
-            col_args = dict(refq=c_loc, wq=0.5 / Bg, refk=r_all, wk=0.5 / Bg, include_diag=True)
+        args = dict(refq=rows_r[:, 3].contiguous(), wq=1.0 / Bg, refk=None, wk=0.0, include_diag=True)
+    dT32, dT16, dY_part = backend.score_grad(T_local, Y_all, sid_loc, sid_all, off, inv_tau, precision=precision,
+                                             alpha=inv_tau, gamma=gamma, want_f32=not bilinear, want_bf16=bilinear,
+                                             out_split=bilinear and strict, want_k=True, **args)
+    if world > 1:
+        if dist.get_backend(group) == "gloo":         # gloo (CPU tests) has no reduce-scatter
+            dist.all_reduce(dY_part, op=dist.ReduceOp.SUM, group=group)
+            dY = dY_part[off:off + Bl].contiguous()
         else:
-            row_args = dict(refq=r_loc, wq=1.0 / Bg, refk=None, wk=0.0, include_diag=True)
-            col_args = dict(refq=None, wq=0.0, refk=r_all, wk=1.0 / Bg, include_diag=True)
-    dT32, dT16 = backend.score_grad(T_local, Y_all, sid_loc, sid_all, off, inv_tau, precision=precision,
-                                    alpha=inv_tau, gamma=gamma, sub=Yb, want_f32=not bilinear, want_bf16=bilinear,
-                                    **row_args)
-    dY, _ = backend.score_grad(Yb, T_all, sid_loc, sid_all, off, inv_tau, precision=precision,
-                               alpha=inv_tau, gamma=gamma, sub=T_local, want_f32=True, want_bf16=False, **col_args)
+            dY = torch.empty((Bl, D), dtype=dY_part.dtype, device=dY_part.device)
+            dist.reduce_scatter_tensor(dY, dY_part, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dY = dY_part
     if not bilinear:
         return out, dT32, dY, None
     dX = backend.gemm(dT16, Wb)                                               # dT W^T

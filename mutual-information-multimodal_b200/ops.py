@@ -6,7 +6,7 @@ path runs in libmi_b200.so.  All functions raise ``MIError`` on failure — ther
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional, Tuple, Union
 
 import torch
 
@@ -19,6 +19,31 @@ PRECISION = {"fast": 0, "strict": 1}
 
 class MIError(RuntimeError):
     pass
+
+
+class SplitBF16:
+    """A matrix kept as a hi/lo bf16 pair ("strict", fp32-accumulate mode): ``data`` is
+    [rows, 2 * round_up(width, 64)] with hi in columns [0, width) and lo starting at column
+    round_up(width, 64); value = hi + lo."""
+
+    def __init__(self, data: torch.Tensor, width: int):
+        self.data = data
+        self.width = width
+
+    @property
+    def shape(self):
+        return (self.data.shape[0], self.width)
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def float(self) -> torch.Tensor:
+        dp = self.data.shape[1] // 2
+        return self.data[:, :self.width].float() + self.data[:, dp:dp + self.width].float()
+
+
+Mat = Union[torch.Tensor, SplitBF16]
 
 
 def _check(status: int, what: str) -> None:
@@ -40,8 +65,30 @@ def _stream():
 
 def _need_cuda(*ts):
     for t in ts:
+        if isinstance(t, SplitBF16):
+            t = t.data
         if t is not None and not t.is_cuda:
             raise MIError("mi_b200 has no CPU path: tensors must live on a CUDA (sm_100) device")
+
+
+def _opnd(m: Mat):
+    """(tensor, pitch, split flag, logical width) of a plain or hi/lo operand."""
+    if isinstance(m, SplitBF16):
+        return m.data, m.data.stride(0), 2, m.width
+    assert m.dtype == torch.bfloat16 and m.dim() == 2
+    if m.stride(1) != 1 or m.stride(0) % 8:
+        m = m.contiguous()
+    if m.stride(0) % 8:
+        raise MIError("operands need a row pitch that is a multiple of 8 elements (TMA: 16-byte strides)")
+    return m, m.stride(0), 1, m.shape[1]
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def new_split(rows: int, width: int, device) -> SplitBF16:
+    return SplitBF16(torch.zeros((rows, 2 * _round_up(width, 64)), dtype=torch.bfloat16, device=device), width)
 
 
 _workspaces = {}
@@ -59,10 +106,10 @@ def workspace(nbytes: int, device) -> torch.Tensor:
 
 
 def as_bf16(x: torch.Tensor) -> torch.Tensor:
-    """bf16, contiguous copy/cast through the library's cast kernel for fp32 inputs."""
+    """bf16, contiguous; fp32 inputs go through the library's cast kernel."""
     _need_cuda(x)
     if x.dtype == torch.bfloat16:
-        return x.contiguous()
+        return x.detach().contiguous()
     x = x.detach().contiguous().float()
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     if x.numel():
@@ -70,79 +117,112 @@ def as_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gemm(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, gamma: float = 0.0,
-         sub: Optional[torch.Tensor] = None, out_dtype=torch.float32) -> torch.Tensor:
-    """C = alpha * (A @ B.T - gamma * sub); A [M,K], B [N,K] bf16."""
+def gemm(A: Mat, B: Mat, alpha: float = 1.0, gamma: float = 0.0, sub: Optional[torch.Tensor] = None,
+         out_dtype=torch.float32, out_split: bool = False):
+    """C = alpha * (A @ B.T - gamma * sub); A [M,K], B [N,K] bf16 (plain or hi/lo).  ``out_split``
+    returns a SplitBF16."""
     _need_cuda(A, B, sub)
-    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.shape[1] == B.shape[1]
-    A = A if A.stride(1) == 1 and A.stride(0) % 8 == 0 else A.contiguous()     # row-strided views are fine
-    B = B if B.stride(1) == 1 and B.stride(0) % 8 == 0 else B.contiguous()
-    M, K = A.shape
-    N = B.shape[0]
-    if A.stride(0) % 8 or B.stride(0) % 8:
-        raise MIError("gemm operands need a row pitch that is a multiple of 8 elements (TMA: 16-byte strides)")
-    out = torch.empty((M, N), dtype=out_dtype, device=A.device)
-    of = _ptr(out) if out_dtype == torch.float32 else None
-    ob = _ptr(out) if out_dtype == torch.bfloat16 else None
+    At, lda, asp, K = _opnd(A)
+    Bt, ldb, bsp, Kb = _opnd(B)
+    assert K == Kb, "inner dimensions differ"
+    M, N = At.shape[0], Bt.shape[0]
+    of = ob = None
+    ld16 = 0
+    if out_split:
+        res = new_split(M, N, At.device)
+        ob, ld16 = res.data, res.data.stride(0)
+    elif out_dtype == torch.bfloat16:
+        res = torch.empty((M, N), dtype=torch.bfloat16, device=At.device)
+        ob, ld16 = res, N
+    else:
+        res = torch.empty((M, N), dtype=torch.float32, device=At.device)
+        of = res
     if sub is not None:
         sub = sub.contiguous()
-    _check(_lib.load().mi_gemm_bf16(_ptr(A), A.stride(0), _ptr(B), B.stride(0), M, N, K, alpha, gamma, _ptr(sub),
-                                    0 if sub is None else sub.shape[1], of, ob, N, None, 0, _stream()), "mi_gemm_bf16")
-    return out
+    _check(_lib.load().mi_gemm_bf16(_ptr(At), lda, asp, _ptr(Bt), ldb, bsp, M, N, K, alpha, gamma, _ptr(sub),
+                                    0 if sub is None else sub.stride(0), _ptr(of), N, _ptr(ob), ld16,
+                                    2 if out_split else 1, _stream()), "mi_gemm_bf16")
+    return res
 
 
-def transpose(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
+def transpose(x: Mat):
+    """x^T.  A plain [R,C] matrix gives a [C,R] view with an 8-element-aligned pitch; a hi/lo matrix
+    gives the hi/lo pair of x^T (lo half next to the hi half along the new K axis)."""
     _need_cuda(x)
+    lib = _lib.load()
+    if isinstance(x, SplitBF16):
+        R, Cc = x.shape
+        dp_in = x.data.shape[1] // 2
+        out = new_split(Cc, R, x.device)
+        dp_out = out.data.shape[1] // 2
+        ld_in, ld_out = x.data.stride(0), out.data.stride(0)
+        _check(lib.mi_transpose_bf16(_ptr(x.data), ld_in, _ptr(out.data), ld_out, R, Cc, _stream()), "mi_transpose_bf16")
+        _check(lib.mi_transpose_bf16(C.c_void_p(x.data.data_ptr() + 2 * dp_in), ld_in,
+                                     C.c_void_p(out.data.data_ptr() + 2 * dp_out), ld_out, R, Cc, _stream()), "mi_transpose_bf16")
+        return out
     assert x.dtype == torch.bfloat16 and x.dim() == 2
     x = x.contiguous()
     R, Cc = x.shape
-    ld = ld_out or ((R + 7) // 8) * 8          # pitch padded so the result can feed the TMA-based GEMM
+    ld = _round_up(R, 8)
     out = torch.zeros((Cc, ld), dtype=torch.bfloat16, device=x.device)
-    _check(_lib.load().mi_transpose_bf16(_ptr(x), Cc, _ptr(out), ld, R, Cc, _stream()), "mi_transpose_bf16")
+    _check(lib.mi_transpose_bf16(_ptr(x), Cc, _ptr(out), ld, R, Cc, _stream()), "mi_transpose_bf16")
     return out[:, :R]
 
 
-def score_stats(Q: torch.Tensor, K: torch.Tensor, sid_q: torch.Tensor, sid_k: torch.Tensor,
+def score_stats(Q: Mat, K: Mat, sid_q: torch.Tensor, sid_k: torch.Tensor,
                 q_offset: int = 0, scale: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """rows [Bq,4] = {lse_neg, n_neg, diag, lse_all} (fp32), scal [8] (fp64) — see mi_b200.h."""
     _need_cuda(Q, K, sid_q, sid_k)
     lib = _lib.load()
-    Q, K = Q.contiguous(), K.contiguous()
+    Qt, ldq, qsp, D = _opnd(Q)
+    Kt, ldk, ksp, Dk = _opnd(K)
+    assert D == Dk
     sid_q, sid_k = sid_q.to(torch.int32).contiguous(), sid_k.to(torch.int32).contiguous()
-    Bq, D = Q.shape
-    Bk = K.shape[0]
-    rows = torch.empty((Bq, 4), dtype=torch.float32, device=Q.device)
-    scal = torch.empty(8, dtype=torch.float64, device=Q.device)
+    Bq, Bk = Qt.shape[0], Kt.shape[0]
+    rows = torch.empty((Bq, 4), dtype=torch.float32, device=Qt.device)
+    scal = torch.empty(8, dtype=torch.float64, device=Qt.device)
     nbytes = lib.mi_score_stats_workspace_bytes(Bq, Bk, D)
-    ws = workspace(nbytes, Q.device)
-    _check(lib.mi_score_stats(_ptr(Q), D, _ptr(K), D, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D, scale,
-                              _ptr(rows), _ptr(scal), _ptr(ws), ws.numel(), _stream()), "mi_score_stats")
+    ws = workspace(nbytes, Qt.device)
+    _check(lib.mi_score_stats(_ptr(Qt), ldq, qsp, _ptr(Kt), ldk, ksp, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D,
+                              scale, _ptr(rows), _ptr(scal), _ptr(ws), ws.numel(), _stream()), "mi_score_stats")
     return rows, scal
 
 
-def score_grad(Q, K, sid_q, sid_k, q_offset: int, scale: float,
+def score_grad(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
                refq: Optional[torch.Tensor], wq: float, refk: Optional[torch.Tensor], wk: float,
-               include_diag: bool, precision: str, alpha: float, gamma: float, sub: Optional[torch.Tensor],
-               want_f32: bool = True, want_bf16: bool = False):
-    """O = alpha * (G K - gamma * sub) with G recomputed tile by tile (mi_score_grad)."""
-    _need_cuda(Q, K, sid_q, sid_k, refq, refk, sub)
+               include_diag: bool, precision: str, alpha: float, gamma: float,
+               want_f32: bool = True, want_bf16: bool = False, out_split: bool = False, want_k: bool = False):
+    """Fused gradient pass (mi_score_grad).  Returns (Oq fp32 | None, Oq bf16 / SplitBF16 | None,
+    Ok fp32 [Bk, D] | None):  Oq = alpha (G K - gamma K_diag),  Ok = alpha (G^T Q - gamma Q_diag)."""
+    _need_cuda(Q, K, sid_q, sid_k, refq, refk)
     lib = _lib.load()
-    Q, K = Q.contiguous(), K.contiguous()
+    Qt, ldq, qsp, D = _opnd(Q)
+    Kt, ldk, ksp, Dk = _opnd(K)
+    assert D == Dk
     sid_q, sid_k = sid_q.to(torch.int32).contiguous(), sid_k.to(torch.int32).contiguous()
-    Bq, D = Q.shape
-    Bk = K.shape[0]
+    Bq, Bk = Qt.shape[0], Kt.shape[0]
     prec = PRECISION[precision]
-    o32 = torch.empty((Bq, D), dtype=torch.float32, device=Q.device) if want_f32 else None
-    o16 = torch.empty((Bq, D), dtype=torch.bfloat16, device=Q.device) if want_bf16 else None
+    dev = Qt.device
+    o32 = torch.empty((Bq, D), dtype=torch.float32, device=dev) if want_f32 else None
+    o16 = ob = None
+    ld16 = 0
+    if want_bf16:
+        if out_split:
+            o16 = new_split(Bq, D, dev)
+            ob, ld16 = o16.data, o16.data.stride(0)
+        else:
+            o16 = torch.empty((Bq, D), dtype=torch.bfloat16, device=dev)
+            ob, ld16 = o16, D
+    okk = torch.empty((Bk, D), dtype=torch.float32, device=dev) if want_k else None
     refq = None if refq is None else refq.float().contiguous()
     refk = None if refk is None else refk.float().contiguous()
-    sub = None if sub is None else sub.contiguous()
     nbytes = lib.mi_score_grad_workspace_bytes(Bq, Bk, D, prec)
-    ws = workspace(nbytes, Q.device)
-    _check(lib.mi_score_grad(_ptr(Q), D, _ptr(K), D, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D, scale,
+    ws = workspace(nbytes, dev)
+    _check(lib.mi_score_grad(_ptr(Qt), ldq, qsp, _ptr(Kt), ldk, ksp, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D, scale,
                              _ptr(refq), wq, _ptr(refk), wk, int(include_diag), prec, alpha, gamma,
-                             _ptr(sub), D, _ptr(o32), _ptr(o16), D, _ptr(ws), ws.numel(), _stream()), "mi_score_grad")
-    return o32, o16
+                             _ptr(o32), _ptr(ob), ld16, 2 if out_split else 1, _ptr(okk),
+                             _ptr(ws), ws.numel(), _stream()), "mi_score_grad")
+    return o32, o16, okk
 
 
 def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tensor], sid: torch.Tensor,

@@ -8,14 +8,14 @@ def as_bf16(x):
     return x.detach().double().contiguous()      # exact arithmetic: isolates the collective logic
 
 
-def gemm(A, B, alpha=1.0, gamma=0.0, sub=None, out_dtype=torch.float32):
+def gemm(A, B, alpha=1.0, gamma=0.0, sub=None, out_dtype=torch.float32, out_split=False):
     C = A.double() @ B.double().t()
     if sub is not None:
         C = C - gamma * sub.double()
-    return alpha * C                           # no rounding, whatever out_dtype asks for
+    return alpha * C                           # no rounding, whatever out_dtype / out_split ask for
 
 
-def transpose(x, ld_out=None):
+def transpose(x):
     return x.t().contiguous()
 
 
@@ -45,7 +45,7 @@ def score_stats(Q, K, sid_q, sid_k, q_offset=0, scale=1.0):
 
 
 def score_grad(Q, K, sid_q, sid_k, q_offset, scale, refq, wq, refk, wk, include_diag, precision,
-               alpha, gamma, sub, want_f32=True, want_bf16=False):
+               alpha, gamma, want_f32=True, want_bf16=False, out_split=False, want_k=False):
     S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
     incl = M.clone()
     if include_diag:
@@ -56,8 +56,10 @@ def score_grad(Q, K, sid_q, sid_k, q_offset, scale, refq, wq, refk, wk, include_
     if refk is not None and wk > 0:
         G = G + wk * torch.exp(S - refk.double()[None, :])
     G = torch.where(incl, G, torch.zeros_like(G))
-    O = G @ K.double()
-    if sub is not None:
-        O = O - gamma * sub.double()
-    O = alpha * O
-    return (O if want_f32 else None), (O if want_bf16 else None)
+    Oq = alpha * (G @ K.double() - gamma * K.double()[j])
+    Ok = None
+    if want_k:
+        Ok = G.t() @ Q.double()
+        Ok[j] -= gamma * Q.double()
+        Ok = alpha * Ok
+    return (Oq if want_f32 else None), (Oq if want_bf16 else None), Ok
