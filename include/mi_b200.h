@@ -58,7 +58,7 @@ int mi_device_check(void);
 /* ---- building blocks --------------------------------------------------------------------------- */
 
 /* hi/lo split operands ("strict", fp32-accumulate mode): a *_split argument of 2 means the bf16 matrix
- * is a pair stored as [hi | lo] in each row, lo starting at column round_up(D, 64) (D = the logical
+ * is a pair stored as [hi | lo] in each row, lo starting at column round_up(D, 128) (D = the logical
  * width) with zeros in between; value = hi + lo (16 significant bits).  1 = plain bf16. */
 
 /* C[M,N] = alpha * ( A[M,K] * B[N,K]^T - gamma * SUB[M,N] ), bf16 operands (K contiguous), fp32

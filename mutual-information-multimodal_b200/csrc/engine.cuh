@@ -7,9 +7,9 @@
 //   EpiPStore  recomputes score tiles and writes the bf16 dS panel  P = incl * (a e^{S-rq} + b e^{S-rk})
 //   EpiStore   plain GEMM epilogue  C = alpha * (ACC - gamma * SUB)
 //
-// Roles (384 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (leader CTA only when
-// kCG == 2), warp 2 = TMEM allocator, warps 4..11 = epilogue (warp%4 selects the 32-lane TMEM
-// quarter, (warp-4)/4 the 128-column half of the tile).  Pipelines: smem ring full/empty (TMA <-> MMA)
+// Roles (640 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (leader CTA only when
+// kCG == 2), warp 2 = TMEM allocator, warps 4..19 = epilogue (warp%4 selects the 32-lane TMEM
+// quarter, (warp-4)/4 the 64-column quarter of the tile).  Pipelines: smem ring full/empty (TMA <-> MMA)
 // and a 2-deep TMEM accumulator ring tmem_full/tmem_empty (MMA <-> epilogue), so the epilogue of
 // tile t overlaps the MMAs of tile t+1.  With kCG == 2 a CTA pair (cluster 2x1) shares the B operand:
 // each CTA loads its own 128 A rows and one 128-row half of the 256-row B tile, the leader issues
@@ -21,19 +21,27 @@ namespace mi {
 
 constexpr int BLOCK_M = 128;   // accumulator rows per CTA (TMEM lanes)
 constexpr int TILE_N = 256;    // accumulator columns per tile
-constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int ATOM_K = 64;     // 64 bf16 = 128 B = one swizzle-128B row (TMA box width)
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 384;
+constexpr int kNumThreads = 640;
 constexpr int kEpiWarp0 = 4;
-constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiWarps = 16;    // 4 per SM sub-partition: enough warps in flight to hide TMEM / MUFU / smem latency
 constexpr int kTmemCols = 512;
+
+// K block per pipeline stage: 128 for CTA pairs (8 MMAs per barrier round trip, 3 stages of 64 KB),
+// 64 for the single-CTA variant (4 stages of 48 KB).
+__host__ __device__ constexpr int block_k(int cg) { return cg == 2 ? 128 : 64; }
 
 template <int kCG>
 struct Cfg {
-  static constexpr int kStages = (kCG == 1) ? 4 : 6;
-  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;          // 16 KB
-  static constexpr int kBRows = TILE_N / kCG;                    // B rows this CTA loads
-  static constexpr int kBBytes = kBRows * BLOCK_K * 2;           // 32 KB / 16 KB
+  static constexpr int kBK = block_k(kCG);
+  static constexpr int kAtoms = kBK / ATOM_K;                      // 64-wide swizzle atoms per stage
+  static constexpr int kStages = (kCG == 1) ? 4 : 3;
+  static constexpr int kAAtomBytes = BLOCK_M * ATOM_K * 2;         // 16 KB: 128 rows x 128 B
+  static constexpr int kABytes = kAAtomBytes * kAtoms;
+  static constexpr int kBRows = TILE_N / kCG;                      // B rows this CTA loads
+  static constexpr int kBAtomBytes = kBRows * ATOM_K * 2;
+  static constexpr int kBBytes = kBAtomBytes * kAtoms;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + slack for 1024 B alignment
   template <class Epi> static constexpr int smem_bytes() { return kSmemBytes + Epi::kEpiSmemBytes; }
@@ -47,7 +55,7 @@ struct Sched {
   int n_split;    // contiguous N-range splits per M block
   int n_ksplit;   // K splits (split-K GEMM), 1 otherwise
   int order;      // 0: m fastest (concurrent units share the N range), 1: ksplit, split fastest
-  int k_blocks;   // number of 64-wide K blocks per tile (all segments)
+  int k_blocks;   // number of K blocks (block_k wide) per tile, all segments
   // K segments: block kb belongs to segment kb / seg_len and reads A at K block a_seg[seg] + kb % seg_len,
   // B at b_seg[seg] + kb % seg_len.  One segment = plain GEMM; more = sums of products of hi/lo splits,
   // e.g. [P_hi | P_lo] x [V ; V] or [T_hi | T_lo] x [Y ; Y] (fp32-accumulate "strict" mode).
@@ -60,6 +68,7 @@ struct Sched {
 struct Unit { int m, s, ks, nt0, nt1, kb0, kb1; };
 
 __device__ __forceinline__ int num_units(const Sched& sc) { return sc.n_mblk * sc.n_split * sc.n_ksplit; }
+__device__ __forceinline__ int sel4(const int (&a)[4], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
 
 __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
   Unit r;
@@ -78,9 +87,9 @@ __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
 }
 
 // kAMN: the A operand is stored M-contiguous ("MN-major": A[m,k] at base[k*ld + m], i.e. the transpose
-// of a row-major [K, M] matrix).  Its 128 x 64 tile is fetched as two 64(K) x 64(M) boxes and described
-// to the MMA with the MN-major SWIZZLE_128B canonical layout (LBO = 8 KB between the 64-wide M halves,
-// SBO = 1 KB between 8-row K groups).
+// of a row-major [K, M] matrix).  Its 128(M) x kBK(K) tile is fetched as 64(K) x 64(M) boxes — for each
+// 64-wide M half the K rows are contiguous — and described to the MMA with the MN-major SWIZZLE_128B
+// canonical layout (LBO = bytes between the M halves, SBO = 1 KB between 8-row K groups).
 template <int kCG, class Epi, bool kAMN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -103,8 +112,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
-  uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
-  uint8_t* epi_smem = tiles + C::kStages * C::kStageBytes;     // Epi::kEpiSmemBytes of staging, if any
+  uint8_t* epi_smem = smem_raw + (tiles_addr - raw_addr) + C::kStages * C::kStageBytes;   // Epi staging, if any
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -124,111 +132,123 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if constexpr (kCG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t full0 = ptx::smem_u32(&full_bar[0]);
+  const uint32_t empty0 = ptx::smem_u32(&empty_bar[0]);
 
-  // Whole warps take a role branch; inside, one lane does the work and the warp reconverges at the
-  // __syncwarp() so that the .aligned teardown barrier is reached convergently.
+  // Role loops run warp-uniformly (all 32 lanes walk the same schedule and poll the same barriers);
+  // only the TMA / MMA / commit instructions themselves are issued by lane 0.  This keeps the loop
+  // state in uniform registers instead of paying a divergent-to-uniform move per operand.
   if (warp == 0) {
-   if (lane == 0) {
     // ------------------------------------------------------------ TMA producer
-    int stage = 0; uint32_t phase = 0;
-    const uint32_t full0_cluster = (kCG == 2) ? ptx::mapa(ptx::smem_u32(&full_bar[0]), 0) : 0u;
+    uint32_t stage = 0, phase = 0;
+    const uint32_t full0_lead = (kCG == 2) ? ptx::mapa(full0, 0) : full0;
+    const uint64_t ta = reinterpret_cast<uint64_t>(&tmap_a), tb = reinterpret_cast<uint64_t>(&tmap_b);
     for (int u = pair_id; u < n_units; u += n_pairs) {
       const Unit un = decode_unit(sc, u);
       const int a_row = (un.m * kCG + (int)cta_rank) * BLOCK_M;
       for (int nt = un.nt0; nt < un.nt1; ++nt) {
         const int b_row = nt * TILE_N + (int)cta_rank * C::kBRows;
-        int seg = un.kb0 / sc.seg_len, w = un.kb0 % sc.seg_len;
+        int seg = un.kb0 / sc.seg_len, w = un.kb0 - seg * sc.seg_len;
+        int a_k = (sel4(sc.a_seg, seg) + w) * C::kBK, b_k = (sel4(sc.b_seg, seg) + w) * C::kBK;
+        int a_m = a_row + sel4(sc.a_moff, seg);
         for (int kb = un.kb0; kb < un.kb1; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-          uint8_t* sa = tiles + stage * C::kStageBytes;
-          uint8_t* sb = sa + C::kABytes;
-          const int a_k = (sc.a_seg[seg] + w) * BLOCK_K;
-          const int b_k = (sc.b_seg[seg] + w) * BLOCK_K;
-          const int a_m = a_row + sc.a_moff[seg];
-          if (++w == sc.seg_len) { w = 0; ++seg; }
-          if constexpr (kCG == 1) {
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-            if constexpr (kAMN) {
-              ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], a_m, a_k);
-              ptx::tma_load_2d(sa + C::kABytes / 2, &tmap_a, &full_bar[stage], a_m + 64, a_k);
-            } else {
-              ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], a_k, a_row);
+          ptx::mbar_wait_addr(empty0 + stage * 8u, phase ^ 1u, 1);
+          if (lane == 0) {
+            const uint32_t sa = tiles_addr + stage * C::kStageBytes;
+            const uint32_t sb = sa + C::kABytes;
+            const uint32_t bar = full0_lead + stage * 8u;
+            if (kCG == 1 || leader) ptx::mbar_arrive_expect_tx_addr(full0 + stage * 8u, kCG * C::kStageBytes);
+#pragma unroll
+            for (int t = 0; t < C::kAtoms; ++t) {
+              if constexpr (kAMN) {
+                // per 64-wide M half: kBK contiguous K rows of 128 B
+                ptx::tma_load_2d_addr<kCG>(sa + t * (ATOM_K * 128), ta, bar, a_m, a_k + t * ATOM_K);
+                ptx::tma_load_2d_addr<kCG>(sa + C::kABytes / 2 + t * (ATOM_K * 128), ta, bar, a_m + 64, a_k + t * ATOM_K);
+              } else {
+                ptx::tma_load_2d_addr<kCG>(sa + t * C::kAAtomBytes, ta, bar, a_k + t * ATOM_K, a_row);
+              }
+              ptx::tma_load_2d_addr<kCG>(sb + t * C::kBAtomBytes, tb, bar, b_k + t * ATOM_K, b_row);
             }
-            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], b_k, b_row);
-          } else {
-            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-            const uint32_t bar = full0_cluster + (uint32_t)stage * 8u;
-            if constexpr (kAMN) {
-              ptx::tma_load_2d_2sm(sa, &tmap_a, bar, a_m, a_k);
-              ptx::tma_load_2d_2sm(sa + C::kABytes / 2, &tmap_a, bar, a_m + 64, a_k);
-            } else {
-              ptx::tma_load_2d_2sm(sa, &tmap_a, bar, a_k, a_row);
-            }
-            ptx::tma_load_2d_2sm(sb, &tmap_b, bar, b_k, b_row);
           }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          __syncwarp();
+          a_k += C::kBK; b_k += C::kBK;
+          if (++w == sc.seg_len) {
+            w = 0; ++seg;
+            a_k = sel4(sc.a_seg, seg) * C::kBK; b_k = sel4(sc.b_seg, seg) * C::kBK; a_m = a_row + sel4(sc.a_moff, seg);
+          }
+          if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-   }
-   __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    if (leader) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * kCG, TILE_N) | (kAMN ? (1u << 15) : 0u);
-      int stage = 0; uint32_t phase = 0; uint32_t tile_cnt = 0;
+      const uint32_t tfull0 = ptx::smem_u32(&tmem_full_bar[0]);
+      const uint32_t tempty0 = ptx::smem_u32(&tmem_empty_bar[0]);
+      // descriptor templates (everything but the 14-bit start address)
+      const uint64_t da_hi = kAMN ? ptx::make_smem_desc_mn128(0, C::kABytes / 2) : ptx::make_smem_desc_k128(0);
+      const uint64_t db_hi = ptx::make_smem_desc_k128(0);
+      uint32_t stage = 0, phase = 0, tile_cnt = 0;
       for (int u = pair_id; u < n_units; u += n_pairs) {
         const Unit un = decode_unit(sc, u);
         for (int nt = un.nt0; nt < un.nt1; ++nt) {
           const uint32_t as = tile_cnt & 1u, aphase = (tile_cnt >> 1) & 1u;
-          ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u, 2);
+          ptx::mbar_wait_addr(tempty0 + as * 8u, aphase ^ 1u, 2);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * TILE_N;
+          uint32_t acc = 0;
           for (int kb = un.kb0; kb < un.kb1; ++kb) {
-            ptx::mbar_wait(&full_bar[stage], phase, 3);
+            ptx::mbar_wait_addr(full0 + stage * 8u, phase, 3);
             ptx::tc_fence_after();
-            const uint32_t sa = tiles_addr + stage * C::kStageBytes;
-            const uint64_t da = kAMN ? ptx::make_smem_desc_mn128(sa, C::kABytes / 2) : ptx::make_smem_desc_k128(sa);
-            const uint64_t db = ptx::make_smem_desc_k128(sa + C::kABytes);
+            if (lane == 0) {
+              const uint32_t sa16 = (tiles_addr + stage * C::kStageBytes) >> 4;     // 16 B units
+              const uint64_t da = da_hi | (uint64_t)sa16;
+              const uint64_t db = db_hi | (uint64_t)(sa16 + (C::kABytes >> 4));
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle row (+2 in 16 B units);
-              // MN-major: advance 16 K rows = two 1 KB swizzle atoms (+128 in 16 B units)
-              const uint64_t a_adv = kAMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
-              ptx::umma_bf16<kCG>(d_tmem, da + a_adv, db + 2 * k, idesc, (kb > un.kb0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < C::kBK / UMMA_K; ++k) {
+                // K-major: 16 bf16 = 32 B inside the 128 B swizzle row (+2), next 64-wide atom after 4 steps;
+                // MN-major: 16 K rows = two 1 KB swizzle atoms (+128)
+                const uint32_t a_adv = kAMN ? (uint32_t)(128 * k)
+                                            : (uint32_t)((k / 4) * (C::kAAtomBytes >> 4) + (k % 4) * 2);
+                const uint32_t b_adv = (uint32_t)((k / 4) * (C::kBAtomBytes >> 4) + (k % 4) * 2);
+                ptx::umma_bf16<kCG>(d_tmem, da + a_adv, db + b_adv, idesc, (k == 0) ? acc : 1u);
+              }
+              ptx::umma_commit_addr<kCG>(empty0 + stage * 8u, 0x3);   // smem slot reusable once these MMAs retire
             }
-            ptx::umma_commit<kCG>(&empty_bar[stage], 0x3);     // smem slot reusable once these MMAs retire
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            __syncwarp();
+            acc = 1u;
+            if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
           }
-          ptx::umma_commit<kCG>(&tmem_full_bar[as], 0x3);      // accumulator ready for the epilogue
+          if (lane == 0) ptx::umma_commit_addr<kCG>(tfull0 + as * 8u, 0x3);   // accumulator ready for the epilogue
+          __syncwarp();
           ++tile_cnt;
         }
       }
     }
-    __syncwarp();
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue (8 warps)
-    const uint32_t quarter = warp & 3u;
-    const uint32_t half = (warp - kEpiWarp0) >> 2;
+    const uint32_t quarter = warp & 3u;                 // TMEM lanes 32*quarter .. +31 (hardware: warp % 4)
+    const uint32_t colq = (warp - kEpiWarp0) >> 2;        // 64-column quarter of the 256-column tile
     uint32_t tile_cnt = 0;
     typename Epi::State st;
     st.stage_smem = epi_smem + (warp - kEpiWarp0) * (Epi::kEpiSmemBytes / kNumEpiWarps);
     for (int u = pair_id; u < n_units; u += n_pairs) {
       const Unit un = decode_unit(sc, u);
       const int row = (un.m * kCG + (int)cta_rank) * BLOCK_M + (int)(quarter * 32u + lane);
-      Epi::unit_begin(ep, st, un, row, (int)half);
+      Epi::unit_begin(ep, st, un, row, (int)colq);
       for (int nt = un.nt0; nt < un.nt1; ++nt) {
         const uint32_t as = tile_cnt & 1u, aphase = (tile_cnt >> 1) & 1u;
         ptx::mbar_wait(&tmem_full_bar[as], aphase, 4);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t col_in_tile = half * 128u + (uint32_t)c * 32u;
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t col_in_tile = colq * 64u + (uint32_t)c * 32u;
           const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * TILE_N + col_in_tile;
           uint32_t v[32];
           ptx::tmem_ld_32x32(taddr, v);
           ptx::tmem_ld_wait();
-          Epi::chunk(ep, st, un, row, nt * TILE_N + (int)col_in_tile, c, v);
+          Epi::chunk(ep, st, un, row, nt * TILE_N + (int)col_in_tile, v);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -238,7 +258,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         ++tile_cnt;
       }
-      Epi::unit_end(ep, st, un, row, (int)half);
+      Epi::unit_end(ep, st, un, row, (int)colq);
     }
   }
 
@@ -253,73 +273,116 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // =====================================================================================
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kColQuarters = 4;      // epilogue column quarters per tile (partials per N split)
+constexpr int kMaxExcl = 4;          // same-study columns listed per row; more -> per-element compare path
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 
-// ---- score statistics: per row online (max, sum-exp) over the negatives, negatives count, diagonal
-struct EpiStats {
-  static constexpr int kEpiSmemBytes = 0;
-  struct Params {
-    const int* sid_q;      // [q_rows] study index of accumulator rows
-    const int* sid_k;      // [n_ntile*256] (padded) study index of accumulator columns
-    int q_rows, k_cols;
-    long long q_offset;    // column index of row 0's own sample (diagonal = q_offset + row)
-    float scale;           // S = scale * acc
-    float4* part;          // [n_split][2][rows_padded]  {max (log2 units), sum, count, diag}
-    int rows_padded;
-  };
-  struct State { uint8_t* stage_smem; float m, s, cnt, diag; int sidq; };
+// The negatives mask (main_utils.py:105: study_id[i] != study_id[j]) is sparse: a row is excluded only
+// from the few columns that share its study.  A hash pre-pass lists those columns per row
+// (excl[row] = up to 4 column indices, -1 padded; n_same[row] = their exact number, own sample
+// included), so the epilogue builds a 32-bit exclusion mask per 32-column chunk from 4 compares
+// instead of loading and comparing 32 study ids.  Rows with more than 4 listed columns (n_same > 4)
+// switch their whole warp to the exact per-element compare path.
+struct MaskInfo {
+  const int4* excl;      // [rows]
+  const int* n_same;     // [rows]
+  const int* sid_q;      // [rows]            (per-element path only)
+  const int* sid_k;      // [n_ntile * 256]   (padded; per-element path only)
+};
+struct MaskState { int4 ex; int sidq; bool slow; };
 
-  static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
-    st.m = neg_inf(); st.s = 0.f; st.cnt = 0.f; st.diag = 0.f;
-    st.sidq = (row < p.q_rows) ? __ldg(p.sid_q + row) : -1;
-  }
-  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0, int,
-                                               const uint32_t (&v)[32]) {
-    const float c2 = p.scale * kLog2e;
-    const int limit = p.k_cols - col0;
-    const long long dcol = p.q_offset + row - col0;
-    const int4* sk4 = reinterpret_cast<const int4*>(p.sid_k + col0);
-    float x[32];
-    float cm = neg_inf();
+__device__ __forceinline__ void mask_begin(const MaskInfo& mi, MaskState& ms, int row, int q_rows) {
+  const bool ok = row < q_rows;
+  ms.ex = ok ? __ldg(mi.excl + row) : make_int4(-1, -1, -1, -1);
+  const int n = ok ? __ldg(mi.n_same + row) : 0;
+  ms.sidq = ok ? __ldg(mi.sid_q + row) : -1;
+  ms.slow = __any_sync(0xffffffffu, n > kMaxExcl);
+}
+// bit c set <=> column col0 + c is excluded for this row (same study, or beyond the last column)
+__device__ __forceinline__ uint32_t chunk_mask(const MaskInfo& mi, const MaskState& ms, int col0, int k_cols) {
+  uint32_t m = 0;
+  if (!ms.slow) {
+    const uint32_t d0 = (uint32_t)(ms.ex.x - col0), d1 = (uint32_t)(ms.ex.y - col0);
+    const uint32_t d2 = (uint32_t)(ms.ex.z - col0), d3 = (uint32_t)(ms.ex.w - col0);
+    if (d0 < 32u) m |= 1u << d0;
+    if (d1 < 32u) m |= 1u << d1;
+    if (d2 < 32u) m |= 1u << d2;
+    if (d3 < 32u) m |= 1u << d3;
+  } else {
+    const int4* sk4 = reinterpret_cast<const int4*>(mi.sid_k + col0);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int4 sk = __ldg(sk4 + g);
-      const int sks[4] = {sk.x, sk.y, sk.z, sk.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = g * 4 + j;
-        const bool neg = (sks[j] != st.sidq) && (c < limit);
-        x[c] = neg ? __uint_as_float(v[c]) * c2 : neg_inf();
-        st.cnt += neg ? 1.f : 0.f;
-        cm = fmaxf(cm, x[c]);
-      }
-    }
-    if (dcol >= 0 && dcol < 32) {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) if (c == (int)dcol) st.diag = __uint_as_float(v[c]) * p.scale;
-    }
-    const float m_new = fmaxf(st.m, cm);
-    if (m_new > neg_inf()) {
-      float s = st.s * ptx::ex2(st.m - m_new);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) s += ptx::ex2(x[c] - m_new);
-      st.s = s; st.m = m_new;
+      m |= (sk.x == ms.sidq ? 1u : 0u) << (4 * g);
+      m |= (sk.y == ms.sidq ? 1u : 0u) << (4 * g + 1);
+      m |= (sk.z == ms.sidq ? 1u : 0u) << (4 * g + 2);
+      m |= (sk.w == ms.sidq ? 1u : 0u) << (4 * g + 3);
     }
   }
-  static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit& un, int row, int half) {
-    p.part[((size_t)un.s * 2 + half) * p.rows_padded + row] = make_float4(st.m, st.s, st.cnt, st.diag);
+  const int limit = k_cols - col0;                    // columns >= k_cols do not exist
+  if (limit < 32) m |= (limit <= 0) ? 0xffffffffu : ~((1u << limit) - 1u);
+  return m;
+}
+
+// ---- score statistics: per row online (max, sum-exp) over the negatives (the positive-pair scores
+//      S[q, q_offset+q] are O(B D) work and come from a separate dot-product kernel)
+struct EpiStats {
+  static constexpr int kEpiSmemBytes = 0;
+  struct Params {
+    MaskInfo mask;
+    int q_rows, k_cols;
+    float scale;           // S = scale * acc, scale > 0
+    float4* part;          // [n_split][4][rows_padded]  {max (log2 units), sum, 0, 0}
+    int rows_padded;
+  };
+  struct State { uint8_t* stage_smem; MaskState ms; float m, s; };
+
+  static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
+    st.m = neg_inf(); st.s = 0.f;
+    mask_begin(p.mask, st.ms, row, p.q_rows);
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0,
+                                               uint32_t (&v)[32]) {
+    const float c2 = p.scale * kLog2e;
+    const uint32_t mk = chunk_mask(p.mask, st.ms, col0, p.k_cols);
+    if (mk != 0u) {                                    // rare: knock the excluded columns out
+#pragma unroll
+      for (int c = 0; c < 32; ++c) if ((mk >> c) & 1u) v[c] = 0xff800000u;   // -inf
+    }
+    // max over the chunk (4 independent chains), in accumulator units (scale > 0)
+    float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+    for (int c = 4; c < 32; c += 4) {
+      m0 = fmaxf(m0, __uint_as_float(v[c])); m1 = fmaxf(m1, __uint_as_float(v[c + 1]));
+      m2 = fmaxf(m2, __uint_as_float(v[c + 2])); m3 = fmaxf(m3, __uint_as_float(v[c + 3]));
+    }
+    const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c2;
+    const float m_new = fmaxf(st.m, cm);
+    if (m_new > neg_inf()) {
+      float s0 = st.s * ptx::ex2(st.m - m_new), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        s0 += ptx::ex2(fmaf(__uint_as_float(v[c]), c2, -m_new));
+        s1 += ptx::ex2(fmaf(__uint_as_float(v[c + 1]), c2, -m_new));
+        s2 += ptx::ex2(fmaf(__uint_as_float(v[c + 2]), c2, -m_new));
+        s3 += ptx::ex2(fmaf(__uint_as_float(v[c + 3]), c2, -m_new));
+      }
+      st.s = (s0 + s1) + (s2 + s3); st.m = m_new;
+    }
+  }
+  static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit& un, int row, int colq) {
+    p.part[((size_t)un.s * kColQuarters + colq) * p.rows_padded + row] = make_float4(st.m, st.s, 0.f, 0.f);
   }
 };
 
 // ---- dS panel: P[row, col] = incl * ( wq e^{S - refq[row]} + wk e^{S - refk[col]} ), bf16 (hi [+ lo])
-// Each epilogue warp stages 32 rows x 64 columns (4 KB, XOR-swizzled 16 B chunks) in shared memory and
-// writes them out as full 128 B lines (4 rows per warp store) instead of 16 B per row.
+// Each epilogue warp stages its 32 rows x 32 columns (2 KB, XOR-swizzled 16 B chunks) in shared memory
+// and writes them out as 64 B row segments (8 rows per warp store) instead of 16 B per row.
 struct EpiPStore {
-  static constexpr int kEpiSmemBytes = kNumEpiWarps * 4096;
+  static constexpr int kEpiSmemBytes = kNumEpiWarps * 2048;
   struct Params {
-    const int* sid_q;
-    const int* sid_k;       // padded to n_ntile*256
+    MaskInfo mask;
     int q_rows, k_cols;
     long long q_offset;
     float scale;
@@ -333,89 +396,81 @@ struct EpiPStore {
     __nv_bfloat16* P_lo;    // residual panel (strict mode) or nullptr
     long long pitch;
   };
-  struct State { uint8_t* stage_smem; float rq2; int sidq; };
+  struct State { uint8_t* stage_smem; MaskState ms; float rq2; };
 
   static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
-    const bool ok = row < p.q_rows;
-    st.sidq = ok ? __ldg(p.sid_q + row) : -1;
-    const float r = (p.use_q && ok) ? __ldg(p.refq + row) : 0.f;
+    mask_begin(p.mask, st.ms, row, p.q_rows);
+    const float r = (p.use_q && row < p.q_rows) ? __ldg(p.refq + row) : 0.f;
     st.rq2 = (r - p.ln_wq) * kLog2e;
   }
-  // write this thread's 32 packed bf16 (16 words) into its staging row, chunks [4*hc, 4*hc+4)
-  static __device__ __forceinline__ void stage_row(uint8_t* smem, int lane, int hc, const uint32_t (&w)[16]) {
+  // stage this thread's 32 packed bf16 (16 words = 4 x 16 B) into its row of the warp's 32 x 64 B tile,
+  // then the warp writes the tile to global memory: lane -> (row = 8*it + lane/4, 16 B chunk = lane%4)
+  static __device__ __forceinline__ void stage_and_flush(uint8_t* smem, int lane, const uint32_t (&w)[16],
+                                                         __nv_bfloat16* dst_row0, long long pitch, int rows_valid) {
+    const int sw = (lane >> 1) & 3;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int chunk = (hc * 4 + g) ^ (lane & 7);
-      *reinterpret_cast<uint4*>(smem + lane * 128 + chunk * 16) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
-    }
-  }
-  // the warp copies its 32 x 64 staging tile to global: lane -> (row = 4*it + lane/8, chunk = lane%8)
-  static __device__ __forceinline__ void flush(uint8_t* smem, int lane, __nv_bfloat16* dst_row0, long long pitch, int rows_valid) {
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(smem + lane * 64 + ((g ^ sw) * 16)) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
     __syncwarp();
+    uint4 val[4];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + (lane >> 3), ch = lane & 7;
-      const uint4 val = *reinterpret_cast<const uint4*>(smem + r * 128 + ((ch ^ (r & 7)) * 16));
-      if (r < rows_valid) *reinterpret_cast<uint4*>(dst_row0 + (size_t)r * pitch + ch * 8) = val;
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), ch = lane & 3;
+      val[it] = *reinterpret_cast<const uint4*>(smem + r * 64 + ((ch ^ ((r >> 1) & 3)) * 16));
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), ch = lane & 3;
+      if (r < rows_valid) *reinterpret_cast<uint4*>(dst_row0 + (size_t)r * pitch + ch * 8) = val[it];
     }
     __syncwarp();
   }
-  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0, int c_idx,
-                                               const uint32_t (&v)[32]) {
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0,
+                                               uint32_t (&v)[32]) {
     const float c2 = p.scale * kLog2e;
-    const int limit = p.k_cols - col0;
-    const long long dcol_ll = p.q_offset + row - col0;
-    const int dcol = (p.include_diag && dcol_ll >= 0 && dcol_ll < 32) ? (int)dcol_ll : -1;
-    const int4* sk4 = reinterpret_cast<const int4*>(p.sid_k + col0);
-    const float4* rk4 = reinterpret_cast<const float4*>(p.refk2 + col0);
     const int lane = (int)(threadIdx.x & 31);
-    float pv[32];
+    uint32_t mk = chunk_mask(p.mask, st.ms, col0, p.k_cols);
+    if (p.include_diag) {                              // the positive pair stays in
+      const long long dcol = p.q_offset + row - col0;
+      if (dcol >= 0 && dcol < 32) mk &= ~(1u << (int)dcol);
+    }
+    // v[c] <- p value (fp32 bits), in place
+    if (p.use_q && !p.use_k) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int4 sk = __ldg(sk4 + g);
-      const int sks[4] = {sk.x, sk.y, sk.z, sk.w};
-      float rks[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.use_k) { const float4 rk = __ldg(rk4 + g); rks[0] = rk.x; rks[1] = rk.y; rks[2] = rk.z; rks[3] = rk.w; }
+      for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(ptx::ex2(fmaf(__uint_as_float(v[c]), c2, -st.rq2)));
+    } else {
+      const float4* rk4 = reinterpret_cast<const float4*>(p.refk2 + col0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = g * 4 + j;
-        const float e = __uint_as_float(v[c]) * c2;
-        float val = 0.f;
-        if (p.use_q) val = ptx::ex2(e - st.rq2);
-        if (p.use_k) val += ptx::ex2(e - rks[j]);
-        const bool incl = (c < limit) && ((sks[j] != st.sidq) || (c == dcol));
-        pv[c] = incl ? val : 0.f;
+      for (int g = 0; g < 8; ++g) {
+        const float4 rk = __ldg(rk4 + g);
+        const float rks[4] = {rk.x, rk.y, rk.z, rk.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 4 * g + j;
+          const float a = __uint_as_float(v[c]);
+          float val = ptx::ex2(fmaf(a, c2, -rks[j]));
+          if (p.use_q) val += ptx::ex2(fmaf(a, c2, -st.rq2));
+          v[c] = __float_as_uint(val);
+        }
       }
+    }
+    if (mk != 0u) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) if ((mk >> c) & 1u) v[c] = 0u;
     }
     uint32_t hi[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(pv[2 * c], pv[2 * c + 1]);
-    const int hc = c_idx & 1;                       // which 32-column half of the 64-column staging tile
-    const int row0 = row - lane;                    // first row of this warp
+    for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+    const int row0 = row - lane;                       // first row of this warp
     const int rows_valid = p.q_rows - row0;
-    const int colbase = col0 - hc * 32;
-    if (p.P_lo == nullptr) {
-      stage_row(st.stage_smem, lane, hc, hi);
-      if (hc == 1) flush(st.stage_smem, lane, p.P + (size_t)row0 * p.pitch + colbase, p.pitch, rows_valid);
-    } else {
-      // strict mode: hi and lo panels go out one 32-column half at a time through the same staging tile
-      uint32_t lo[16];
+    stage_and_flush(st.stage_smem, lane, hi, p.P + (size_t)row0 * p.pitch + col0, p.pitch, rows_valid);
+    if (p.P_lo != nullptr) {                           // strict mode: residual panel
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const float h0 = __uint_as_float(hi[c] << 16), h1 = __uint_as_float(hi[c] & 0xffff0000u);
-        lo[c] = ptx::pack_bf16(pv[2 * c] - h0, pv[2 * c + 1] - h1);
+        hi[c] = ptx::pack_bf16(__uint_as_float(v[2 * c]) - h0, __uint_as_float(v[2 * c + 1]) - h1);
       }
-      stage_row(st.stage_smem, lane, 0, hi);
-      stage_row(st.stage_smem, lane, 1, lo);
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3), ch = lane & 7;
-        const uint4 val = *reinterpret_cast<const uint4*>(st.stage_smem + r * 128 + ((ch ^ (r & 7)) * 16));
-        __nv_bfloat16* base = (ch < 4 ? p.P : p.P_lo) + (size_t)(row0 + r) * p.pitch + col0 + (ch & 3) * 8;
-        if (r < rows_valid) *reinterpret_cast<uint4*>(base) = val;
-      }
-      __syncwarp();
+      stage_and_flush(st.stage_smem, lane, hi, p.P_lo + (size_t)row0 * p.pitch + col0, p.pitch, rows_valid);
     }
   }
   static __device__ __forceinline__ void unit_end(const Params&, State&, const Unit&, int, int) {}
@@ -432,7 +487,7 @@ struct EpiStore {
     long long ld_out16;        // pitch of out_bf16 / out_bf16_lo
     int rows, cols;
     float alpha, gamma;
-    const __nv_bfloat16* sub;  // optional [rows, ld_sub]
+    const __nv_bfloat16* sub;  // optional [sub_rows, ld_sub]
     const __nv_bfloat16* sub_lo;  // optional residual of SUB (SUB = sub + sub_lo), same pitch
     long long ld_sub;
     int sub_row0, sub_rows;    // SUB row r applies to output row sub_row0 + r, r in [0, sub_rows)
@@ -441,8 +496,8 @@ struct EpiStore {
   };
   struct State { uint8_t* stage_smem; };
   static __device__ __forceinline__ void unit_begin(const Params&, State&, const Unit&, int, int) {}
-  static __device__ __forceinline__ void chunk(const Params& p, State&, const Unit& un, int row, int col0, int,
-                                               const uint32_t (&v)[32]) {
+  static __device__ __forceinline__ void chunk(const Params& p, State&, const Unit& un, int row, int col0,
+                                               uint32_t (&v)[32]) {
     if (row >= p.rows || col0 >= p.cols) return;
     float o[32];
 #pragma unroll

@@ -113,7 +113,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long rows, long long k_exten
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0 || rows <= 0 || k_extent <= 0) return MI_ERR_BAD_ARG;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_extent), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(mi::BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(mi::ATOM_K), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -188,6 +188,8 @@ int launch_engine(const MapSpec& a, const MapSpec& b, const Sched& sc, const typ
 inline int rows_per_mblk() { return mi::BLOCK_M * cta_group(); }
 inline int num_pairs() { return num_sms() / cta_group(); }
 inline long long round_up(long long a, long long b) { return cdiv(a, b) * b; }
+inline int bk() { return mi::block_k(cta_group()); }      // K block per pipeline stage
+constexpr long long kSplitAlign = 128;                    // lo half of a hi/lo pair starts at round_up(width, 128)
 
 // N-range splits per M block for the streaming (stats / dS-panel) passes: make the unit count a
 // multiple of the number of CTA pairs, then refine while units stay long enough to amortise.
@@ -212,6 +214,49 @@ void single_segment(Sched& sc) {
 __global__ void pad_int_kernel(const int* __restrict__ src, int* __restrict__ dst, long long n, long long n_pad, int fill) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n_pad) dst[i] = (i < n) ? src[i] : fill;
+}
+
+// ---- exclusion lists: for every row, the columns that share its study id (hash grouping, O(B))
+constexpr int kEmptyKey = static_cast<int>(0x80000000u);
+__device__ __forceinline__ uint32_t hash_sid(int key, uint32_t mask) {
+  return (static_cast<uint32_t>(key) * 2654435761u >> 7) & mask;
+}
+__global__ void excl_init_kernel(int* __restrict__ keys, int* __restrict__ counts, int* __restrict__ members, long long slots) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < slots) {
+    keys[i] = kEmptyKey; counts[i] = 0;
+    reinterpret_cast<int4*>(members)[i] = make_int4(-1, -1, -1, -1);
+  }
+}
+__global__ void excl_insert_kernel(const int* __restrict__ sid_k, long long Bk, int* keys, int* counts, int* members, uint32_t mask) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= Bk) return;
+  const int key = sid_k[k];
+  uint32_t h = hash_sid(key, mask);
+  while (true) {
+    const int prev = atomicCAS(&keys[h], kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) break;
+    h = (h + 1) & mask;
+  }
+  const int t = atomicAdd(&counts[h], 1);
+  if (t < mi::kMaxExcl) members[h * mi::kMaxExcl + t] = static_cast<int>(k);
+}
+__global__ void excl_lookup_kernel(const int* __restrict__ sid_q, long long Bq, const int* __restrict__ keys,
+                                   const int* __restrict__ counts, const int* __restrict__ members, uint32_t mask,
+                                   int4* __restrict__ excl, int* __restrict__ n_same) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= Bq) return;
+  const int key = sid_q[q];
+  uint32_t h = hash_sid(key, mask);
+  int4 e = make_int4(-1, -1, -1, -1);
+  int n = 0;
+  while (true) {
+    const int kk = keys[h];
+    if (kk == key) { n = counts[h]; if (n <= mi::kMaxExcl) e = reinterpret_cast<const int4*>(members)[h]; break; }
+    if (kk == kEmptyKey) break;
+    h = (h + 1) & mask;
+  }
+  excl[q] = e; n_same[q] = n;
 }
 
 // refk2[c] = (refk[c] - ln wk) * log2(e), zero padded
@@ -248,19 +293,43 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long
   }
 }
 
+// diag[q] = scale * <Q[q,:], K[q_offset+q,:]> (the positive pair), one warp per row; hi/lo pairs summed
+__global__ void diag_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq, int q_split,
+                            const __nv_bfloat16* __restrict__ K, long long ldk, int k_split,
+                            long long q_offset, long long Bq, long long D, long long Dp, float scale, float* __restrict__ diag) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= Bq) return;
+  const __nv_bfloat16* q = Q + row * ldq;
+  const __nv_bfloat16* k = K + (q_offset + row) * ldk;
+  float acc = 0.f;
+  for (long long d = lane * 2; d < D; d += 64) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + d));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(k + d));
+    float ax = a.x, ay = a.y, bx = b.x, by = b.y;
+    if (q_split == 2) { const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + Dp + d)); ax += l.x; ay += l.y; }
+    if (k_split == 2) { const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(k + Dp + d)); bx += l.x; by += l.y; }
+    acc = fmaf(ax, bx, acc); acc = fmaf(ay, by, acc);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) diag[row] = acc * scale;
+}
+
 // merge the (split, half) partials of one row -> {lse_neg, n_neg, diag, lse_all}
 __global__ void stats_merge_kernel(const float4* __restrict__ part, int n_part, int rows_padded, int q_rows,
+                                   const int* __restrict__ n_same, int k_cols, const float* __restrict__ diag_in,
                                    float4* __restrict__ row_out) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= q_rows) return;
   float m = mi::neg_inf();
   for (int p = 0; p < n_part; ++p) m = fmaxf(m, part[(size_t)p * rows_padded + row].x);
-  float s = 0.f, cnt = 0.f, diag = 0.f;
+  float s = 0.f;
   for (int p = 0; p < n_part; ++p) {
     const float4 v = part[(size_t)p * rows_padded + row];
     if (v.y > 0.f) s += v.y * exp2f(v.x - m);
-    cnt += v.z; diag += v.w;
   }
+  const float diag = diag_in[row];
+  const float cnt = static_cast<float>(k_cols - n_same[row]);     // negatives: columns of a different study
   const float lse_neg = (cnt > 0.f && s > 0.f) ? (m + log2f(s)) * mi::kLn2 : mi::neg_inf();
   const float hi = fmaxf(lse_neg, diag), lo = fminf(lse_neg, diag);
   const float lse_all = hi + log1pf(expf(lo - hi));
@@ -346,17 +415,17 @@ inline unsigned blocks_for(long long n, int t) { return static_cast<unsigned>(cd
 // at column round_up(D, 64), with zeros in the gap (fp32-accumulate "strict" mode).
 struct Opnd { const __nv_bfloat16* p; long long ld; int split; };
 
-inline long long opnd_k_extent(const Opnd& o, long long D) { return o.split == 2 ? round_up(D, 64) + D : D; }
+inline long long opnd_k_extent(const Opnd& o, long long D) { return o.split == 2 ? round_up(D, kSplitAlign) + D : D; }
 
 // K segments for S = Q K^T when one of the operands is a hi/lo pair: (Q_hi + Q_lo) K^T or Q (K_hi + K_lo)^T
 int score_segments(Sched& sc, const Opnd& q, const Opnd& k, long long D) {
-  const int kb = static_cast<int>(cdiv(D, mi::BLOCK_K));
+  const int kb = static_cast<int>(round_up(D, kSplitAlign) / bk());
   single_segment(sc);
   sc.seg_len = kb;
   if (q.split == 2 && k.split == 2) return MI_ERR_BAD_ARG;
   if (q.split == 2) { sc.k_blocks = 2 * kb; sc.a_seg[1] = kb; }
   else if (k.split == 2) { sc.k_blocks = 2 * kb; sc.b_seg[1] = kb; }
-  else sc.k_blocks = kb;
+  else { sc.k_blocks = static_cast<int>(cdiv(D, bk())); sc.seg_len = sc.k_blocks; }
   return MI_OK;
 }
 
@@ -425,7 +494,8 @@ int gemm_impl(const Opnd& A, const Opnd& B, long long M, long long N, long long 
               Bump& ws, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return MI_ERR_BAD_ARG;
   GemmArgs g;
-  const int kb = static_cast<int>(cdiv(K, mi::BLOCK_K));
+  const bool any_split = A.split == 2 || B.split == 2;
+  const int kb = static_cast<int>(any_split ? round_up(K, kSplitAlign) / bk() : cdiv(K, bk()));
   g.a = MapSpec{A.p, M, opnd_k_extent(A, K), A.ld};
   g.b = MapSpec{B.p, N, opnd_k_extent(B, K), B.ld};
   g.M = M; g.N = N; g.k_blocks = kb; g.seg_len = kb;
@@ -437,7 +507,7 @@ int gemm_impl(const Opnd& A, const Opnd& B, long long M, long long N, long long 
   g.alpha = alpha; g.gamma = gamma; g.sub = static_cast<const __nv_bfloat16*>(sub); g.ld_sub = ld_sub;
   g.out_f32 = out_f32; g.ld_out = ld_out;
   g.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); g.ld_out16 = ld_out16;
-  g.out_bf16_lo = (out_split == 2 && out_bf16) ? g.out_bf16 + round_up(N, 64) : nullptr;
+  g.out_bf16_lo = (out_split == 2 && out_bf16) ? g.out_bf16 + round_up(N, kSplitAlign) : nullptr;
   return run_gemm(g, ws, stream);
 }
 
@@ -447,6 +517,33 @@ int transpose_impl(const void* in, long long ld_in, void* out, long long ld_out,
   transpose_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), ld_in,
                                                   static_cast<__nv_bfloat16*>(out), ld_out, R, C);
   MI_LAUNCH_CHECK("transpose_bf16_kernel");
+  return MI_OK;
+}
+
+// hash pre-pass + padded study ids: everything the epilogue's negatives mask needs
+struct MaskBuf { int* sidk_pad; int* keys; int* counts; int* members; int4* excl; int* n_same; long long slots; };
+
+MaskBuf take_mask(Bump& ws, long long Bq, long long k_pad, long long Bk) {
+  MaskBuf b;
+  long long slots = 64;
+  while (slots < 2 * Bk) slots *= 2;
+  b.slots = slots;
+  b.sidk_pad = ws.take<int>(k_pad);
+  b.keys = ws.take<int>(slots); b.counts = ws.take<int>(slots); b.members = ws.take<int>(slots * mi::kMaxExcl);
+  b.excl = ws.take<int4>(Bq); b.n_same = ws.take<int>(Bq);
+  return b;
+}
+
+int build_mask(const MaskBuf& b, const int* sid_q, const int* sid_k, long long Bq, long long Bk, long long k_pad, cudaStream_t stream) {
+  pad_int_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(sid_k, b.sidk_pad, Bk, k_pad, -2);
+  MI_LAUNCH_CHECK("pad_int_kernel");
+  excl_init_kernel<<<blocks_for(b.slots, 256), 256, 0, stream>>>(b.keys, b.counts, b.members, b.slots);
+  MI_LAUNCH_CHECK("excl_init_kernel");
+  const uint32_t mask = static_cast<uint32_t>(b.slots - 1);
+  excl_insert_kernel<<<blocks_for(Bk, 256), 256, 0, stream>>>(sid_k, Bk, b.keys, b.counts, b.members, mask);
+  MI_LAUNCH_CHECK("excl_insert_kernel");
+  excl_lookup_kernel<<<blocks_for(Bq, 256), 256, 0, stream>>>(sid_q, Bq, b.keys, b.counts, b.members, mask, b.excl, b.n_same);
+  MI_LAUNCH_CHECK("excl_lookup_kernel");
   return MI_OK;
 }
 
@@ -462,20 +559,24 @@ int stats_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   MI_TRY(score_segments(sc, Q, K, D));
   const long long k_pad = static_cast<long long>(sc.n_ntile) * mi::TILE_N;
   const int rows_padded = sc.n_mblk * rows_per_mblk();
-  int* sidk_pad = ws.take<int>(k_pad);
-  float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * 2 * rows_padded);
+  const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
+  float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * mi::kColQuarters * rows_padded);
+  float* diag = ws.take<float>(Bq);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
-  if (!Q.p || !K.p || !sid_q || !sid_k || !row_out || !scal_out) return MI_ERR_BAD_ARG;
-  pad_int_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(sid_k, sidk_pad, Bk, k_pad, -2);
-  MI_LAUNCH_CHECK("pad_int_kernel");
+  if (!Q.p || !K.p || !sid_q || !sid_k || !row_out || !scal_out || !(scale > 0.f)) return MI_ERR_BAD_ARG;
+  MI_TRY(build_mask(mb, sid_q, sid_k, Bq, Bk, k_pad, stream));
+  diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Q.p, Q.ld, Q.split, K.p, K.ld, K.split, q_offset, Bq, D,
+                                                             round_up(D, kSplitAlign), scale, diag);
+  MI_LAUNCH_CHECK("diag_kernel");
   mi::EpiStats::Params ep;
-  ep.sid_q = sid_q; ep.sid_k = sidk_pad; ep.q_rows = static_cast<int>(Bq); ep.k_cols = static_cast<int>(Bk);
-  ep.q_offset = q_offset; ep.scale = scale; ep.part = part; ep.rows_padded = rows_padded;
+  ep.mask = mi::MaskInfo{mb.excl, mb.n_same, sid_q, mb.sidk_pad};
+  ep.q_rows = static_cast<int>(Bq); ep.k_cols = static_cast<int>(Bk);
+  ep.scale = scale; ep.part = part; ep.rows_padded = rows_padded;
   MI_TRY(launch_engine<mi::EpiStats>(MapSpec{Q.p, Bq, opnd_k_extent(Q, D), Q.ld}, MapSpec{K.p, Bk, opnd_k_extent(K, D), K.ld},
                                      sc, ep, stream));
-  stats_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * 2, rows_padded, static_cast<int>(Bq),
-                                                              reinterpret_cast<float4*>(row_out));
+  stats_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(Bq),
+                                                              mb.n_same, static_cast<int>(Bk), diag, reinterpret_cast<float4*>(row_out));
   MI_LAUNCH_CHECK("stats_merge_kernel");
   stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out);
   MI_LAUNCH_CHECK("stats_reduce_kernel");
@@ -514,16 +615,16 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   const bool strict = precision == MI_PREC_BF16_STRICT;
   const int n_ntile = static_cast<int>(cdiv(Bk, mi::TILE_N));
   const long long k_pad = static_cast<long long>(n_ntile) * mi::TILE_N;
-  const int kp = static_cast<int>(k_pad / mi::BLOCK_K);
+  const int kp = static_cast<int>(k_pad / bk());
   const long long pitch = k_pad * (strict ? 2 : 1);
-  const long long Dp = round_up(D, 64);
+  const long long Dp = round_up(D, kSplitAlign);
   const bool k_hl = strict && K.split == 2, q_hl = strict && Q.split == 2;
   const long long ld_kt = k_pad * (k_hl ? 2 : 1);
-  const long long q_pad = round_up(Bq, 64);
+  const long long q_pad = round_up(Bq, kSplitAlign);
   const long long ld_qt = q_pad * (q_hl ? 2 : 1);
   const long long mb_panel = panel_mblks(Bq, Bk, D, precision);
   const long long panel_rows = mb_panel * rows_per_mblk();
-  int* sidk_pad = ws.take<int>(k_pad);
+  const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
   float* refk2 = ws.take<float>(k_pad);
   bf* Kt = ws.take<bf>(static_cast<size_t>(D) * ld_kt);
   bf* Qt = ok ? ws.take<bf>(static_cast<size_t>(D) * ld_qt) : nullptr;
@@ -532,10 +633,9 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   if (ws.dry) return MI_OK;
   if (!Q.p || !K.p || !sid_q || !sid_k || (!oq.f32 && !oq.bf16 && !ok)) return MI_ERR_BAD_ARG;
   const bool use_q = refq != nullptr && wq > 0.f, use_k = refk != nullptr && wk > 0.f;
-  if (!use_q && !use_k) return MI_ERR_BAD_ARG;
+  if ((!use_q && !use_k) || !(scale > 0.f)) return MI_ERR_BAD_ARG;
 
-  pad_int_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(sid_k, sidk_pad, Bk, k_pad, -2);
-  MI_LAUNCH_CHECK("pad_int_kernel");
+  MI_TRY(build_mask(mb, sid_q, sid_k, Bq, Bk, k_pad, stream));
   if (use_k) {
     make_refk2_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(refk, logf(wk), refk2, Bk, k_pad);
     MI_LAUNCH_CHECK("make_refk2_kernel");
@@ -561,7 +661,8 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     sc.n_ksplit = 1; sc.order = 0;
     MI_TRY(score_segments(sc, Qe, Ke, D));
     mi::EpiPStore::Params ep;
-    ep.sid_q = sid_q + r0; ep.sid_k = sidk_pad; ep.q_rows = static_cast<int>(rows); ep.k_cols = static_cast<int>(Bk);
+    ep.mask = mi::MaskInfo{mb.excl + r0, mb.n_same + r0, sid_q + r0, mb.sidk_pad};
+    ep.q_rows = static_cast<int>(rows); ep.k_cols = static_cast<int>(Bk);
     ep.q_offset = q_offset + r0; ep.scale = scale;
     ep.refq = use_q ? refq + r0 : nullptr; ep.ln_wq = use_q ? logf(wq) : 0.f; ep.use_q = use_q ? 1 : 0;
     ep.refk2 = refk2; ep.use_k = use_k ? 1 : 0; ep.include_diag = include_diag;
@@ -592,12 +693,12 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     // (3) Ok += alpha (P^T Q[panel] - gamma SUBk), contraction over the panel's rows; P read MN-major
     if (ok) {
       GemmArgs g;
-      const int kr = static_cast<int>(cdiv(rows, mi::BLOCK_K));
+      const int kr = static_cast<int>(cdiv(rows, bk()));
       g.a_mn = true;
       g.a = MapSpec{P, rows, pitch, pitch};            // map rows = K (panel rows), contiguous = M (columns of S)
       g.b = MapSpec{Qt + r0, D, q_hl ? q_pad + (Bq - r0) : (Bq - r0), ld_qt};
       g.M = Bk; g.N = D; g.seg_len = kr; g.k_blocks = kr;
-      const int q_lo_blk = static_cast<int>(q_pad / mi::BLOCK_K);
+      const int q_lo_blk = static_cast<int>(q_pad / bk());
       if (strict) {                                  // P_hi^T Q_hi + P_lo^T Q_hi (+ P_hi^T Q_lo)
         g.k_blocks = 2 * kr; g.a_moff[1] = static_cast<int>(k_pad);
         if (q_hl) { g.k_blocks = 3 * kr; g.b_seg[2] = q_lo_blk; }
@@ -630,9 +731,9 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   const bool dv_like = estimator == MI_EST_DV || estimator == MI_EST_INFONCE_REF;
   const bool strict = precision == MI_PREC_BF16_STRICT;
   const int tsplit = (bilinear && strict) ? 2 : 1;        // T = X W kept as a hi/lo bf16 pair in strict mode
-  const long long Dp = round_up(D, 64);
+  const long long Dp = round_up(D, kSplitAlign);
   const long long ldT = tsplit == 2 ? 2 * Dp : D;
-  const long long b_pad = round_up(B, 64);
+  const long long b_pad = round_up(B, kSplitAlign);
   bf* Wt = bilinear ? ws.take<bf>(static_cast<size_t>(D) * D) : nullptr;
   bf* T = bilinear ? ws.take<bf>(static_cast<size_t>(B) * ldT) : nullptr;
   float* rows_r = ws.take<float>(static_cast<size_t>(B) * 4);
@@ -717,7 +818,7 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
         if (tsplit == 2) MI_TRY(transpose_impl(dT16 + Dp, ldT, dTt + b_pad, b_pad * tsplit, B, D, stream));
       }
       GemmArgs g;
-      const int kb = static_cast<int>(b_pad / mi::BLOCK_K);
+      const int kb = static_cast<int>(b_pad / bk());
       g.a = MapSpec{Xt, D, B, b_pad};
       g.b = MapSpec{dTt, D, tsplit == 2 ? b_pad + B : B, b_pad * tsplit};
       g.M = D; g.N = D; g.seg_len = kb; g.k_blocks = kb;

@@ -77,6 +77,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
 #endif
 }
 
+// address-based variants (shared::cta 32-bit addresses kept in uniform registers by the role loops)
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity, int tag = 0) {
+#if MI_WATCHDOG
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_addr(bar, parity)) {
+    if ((++spins & 0xFFFu) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000LL) {
+        printf("mi_b200 watchdog: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n",
+               tag, (int)blockIdx.x, (int)threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+#else
+  while (!mbar_try_wait_addr(bar, parity)) {}
+#endif
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -96,6 +129,20 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// address-based 2D tile load: smem destination / barrier as 32-bit shared addresses, tensor map as a
+// generic 64-bit address; kCG == 2 signals the (leader's) barrier through the cta_group::2 form
+template <int kCG>
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t smem_dst, uint64_t tmap, uint32_t bar, int c0, int c1) {
+  if constexpr (kCG == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -141,6 +188,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t cta_mask) {
   else
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
+template <int kCG>
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar, uint16_t cta_mask) {
+  if constexpr (kCG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"(cta_mask) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base_lane + t).

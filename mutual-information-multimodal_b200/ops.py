@@ -23,8 +23,8 @@ class MIError(RuntimeError):
 
 class SplitBF16:
     """A matrix kept as a hi/lo bf16 pair ("strict", fp32-accumulate mode): ``data`` is
-    [rows, 2 * round_up(width, 64)] with hi in columns [0, width) and lo starting at column
-    round_up(width, 64); value = hi + lo."""
+    [rows, 2 * round_up(width, 128)] with hi in columns [0, width) and lo starting at column
+    round_up(width, 128); value = hi + lo."""
 
     def __init__(self, data: torch.Tensor, width: int):
         self.data = data
@@ -88,7 +88,7 @@ def _round_up(a, b):
 
 
 def new_split(rows: int, width: int, device) -> SplitBF16:
-    return SplitBF16(torch.zeros((rows, 2 * _round_up(width, 64)), dtype=torch.bfloat16, device=device), width)
+    return SplitBF16(torch.zeros((rows, 2 * _round_up(width, 128)), dtype=torch.bfloat16, device=device), width)
 
 
 _workspaces = {}
@@ -227,8 +227,9 @@ def score_grad(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
 
 def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tensor], sid: torch.Tensor,
                         estimator: str = "dv", precision: str = "fast", inv_tau: float = 1.0,
-                        need_grads: bool = True):
-    """The whole path on one GPU (mi_critic_loss_fwd_bwd).  Returns (loss_out fp64[8], dX, dY, dW)."""
+                        need_grads: bool = True, out=None):
+    """The whole path on one GPU (mi_critic_loss_fwd_bwd).  Returns (loss_out fp64[8], dX, dY, dW).
+    ``out`` = (loss, dX, dY, dW) reuses caller-owned result buffers (no allocation in the call)."""
     _need_cuda(X, Y, W, sid)
     lib = _lib.load()
     X, Y = as_bf16(X), as_bf16(Y)
@@ -237,9 +238,12 @@ def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tens
     B, D = X.shape
     critic = 1 if W is not None else 0
     est, prec = ESTIMATOR[estimator], PRECISION[precision]
-    loss = torch.empty(8, dtype=torch.float64, device=X.device)
     dX = dY = dW = None
-    if need_grads:
+    if out is not None:
+        loss, dX, dY, dW = out
+    else:
+        loss = torch.empty(8, dtype=torch.float64, device=X.device)
+    if need_grads and out is None:
         dX = torch.empty((B, D), dtype=torch.float32, device=X.device)
         dY = torch.empty((B, D), dtype=torch.float32, device=X.device)
         if W is not None:
