@@ -315,7 +315,14 @@ def run_ours(a):
     f_alg = 6.0 * B * B * D + (6.0 * B * D * D if bilinear else 0.0)
     sym = a.estimator == "infonce_sym"
     strict = a.precision == "strict"
-    f_exec = ((2 + (2 if sym else 0)) + 2 * (2 + 2 * (2 if strict else 1))) * float(B) * B * D + (6.0 * B * D * D if bilinear else 0.0)
+    # executed tensor flops: statistics pass(es) 2 B^2 D each, one score recompute 2 B^2 D, two dS x operand
+    # contractions 2 B^2 D each; strict mode adds the hi/lo segments of T and of the dS panel
+    if strict:
+        s_mult = 2.0 if bilinear else 1.0
+        f_exec = ((2 + (2 if sym else 0)) * s_mult + 2 * s_mult + 2 * 2 + 2 * (3 if bilinear else 2)) * float(B) * B * D
+    else:
+        f_exec = ((2 + (2 if sym else 0)) + 2 + 4) * float(B) * B * D
+    f_exec += (6.0 * B * D * D if bilinear else 0.0)
     ach = f_alg / (ms_per_step * 1e-3) / 1e12 / world           # per GPU
     kinds = ["score_stats", "ds_panel", "gemm"]
     by_kernel = {k: {"ms_per_step": ms[i] / a.steps, "launches_per_step": cnt[i] / a.steps} for i, k in enumerate(kinds)}

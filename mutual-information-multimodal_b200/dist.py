@@ -103,7 +103,8 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         g_c = merge_scalars(_all_gather_rows(scal_c.reshape(1, 8), world, group))
         out["loss_col"] = g_c["rowloss_sum"] / Bg
     if estimator == "dv":
-        log_n = torch.log(out["n_neg"].to(torch.float32)).to(torch.float64)     # fp32 log N (mi_critics.py:10)
+        # mi_critics.py:10 rounds N_neg to fp32 before the log; same formula as the fused C path
+        log_n = torch.log(out["n_neg"].to(torch.float32).to(torch.float64))
         out["loss"] = out["lse_neg"] - log_n - out["pos_mean"]
     elif estimator in ("infonce", "infonce_ref"):
         out["loss"] = out["lse_neg"] - out["pos_mean"]
