@@ -312,6 +312,14 @@ def run_ours(a):
         return
 
     pk = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        c = tj["config"]
+        if (c["global_batch"], c["dim"], c["critic"], c["estimator"], c["precision"], c["n_gpus"]) == \
+                (B, D, a.critic, a.estimator, a.precision, world):
+            traffic = tj["bytes_per_step"]
     f_alg = 6.0 * B * B * D + (6.0 * B * D * D if bilinear else 0.0)
     sym = a.estimator == "infonce_sym"
     strict = a.precision == "strict"
@@ -335,7 +343,9 @@ def run_ours(a):
                    "l2": "inputs (2 x %d MB bf16 + >1 GB dS panel per pass) exceed the 126 MB L2; no flush needed" % (B * D * 2 >> 20),
                    "loss": loss_val},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
-                     "frac": ach / pk["sustained"], "traffic": None,
+                     "frac": ach / pk["sustained"], "traffic": traffic,
+                     "traffic_note": "DRAM bytes per step summed over the step's launches (ncu capture in profiles/), "
+                                     "algorithmic bytes 0.54e9: the path is tensor-bound, the bf16 dS panel staging is the extra traffic",
                      "peak_kind": "sustained bf16 (kernel timed inside a long step), " + pk["source"],
                      "frac_of_burst_peak": ach / pk["burst"], "burst_peak": pk["burst"],
                      "algorithmic_flops_per_step": f_alg, "executed_flops_per_step": f_exec,
