@@ -22,6 +22,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; the contract is ONE JSON line there
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "critic pairs/sec fwd+bwd"
 UNIT = "pairs/s"
@@ -180,12 +183,23 @@ def run_ours(a):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    saved_stdout = None
     if world > 1:
+        # NCCL prints a version banner on stdout at communicator creation; keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         entry.build()
     if world > 1:
         dist.barrier()
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     import mi_b200  # noqa: F401
     from mi_b200 import _lib, ops
     from mi_b200 import dist as mdist
@@ -207,7 +221,7 @@ def run_ours(a):
     Xd, Yd = Xh.to(dev).bfloat16(), Yh.to(dev).bfloat16()
     Wd = Wh.to(dev).bfloat16() if bilinear else None
     sd32 = sh.to(dev)
-    sd64 = sid[off:off + Bl].to(dev)
+    sd64 = sd32                      # exact int32 ids: the sharded path uses them as they are
     del X, Y
 
     out_bufs = (torch.empty(8, dtype=torch.float64, device=dev), torch.empty(Bl, D, device=dev),
@@ -287,7 +301,7 @@ def run_ours(a):
             def step_host():
                 x, y = Xh.to(dev, non_blocking=True), Yh.to(dev, non_blocking=True)
                 w = Wh.to(dev, non_blocking=True) if bilinear else None
-                s = sh.to(dev, non_blocking=True).to(torch.int64)
+                s = sh.to(dev, non_blocking=True)
                 out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(x, y, w, s, a.estimator, a.precision, inv_tau, True)
                 dXh.copy_(dX, non_blocking=True); dYh.copy_(dY, non_blocking=True)
                 if bilinear:

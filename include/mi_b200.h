@@ -96,7 +96,8 @@ int mi_score_stats(const void* Q, int64_t ldq, int q_split, const void* K, int64
  * optionally hi/lo)  and, when outk_f32 != NULL,
  *              Ok[k,:] = alpha * ( sum_q G[q,k] Q[q,:] - gamma * [0 <= k-q_offset < Bq] Q[k-q_offset,:] )
  * from the same score recompute (gamma is the weight of the positive pair, 1/B).
- * refq / refk may be NULL (term unused).  The B x B matrix never exists: G is staged as a bounded bf16
+ * refq / refk may be NULL (term unused).  Ok is finished before Oq (event_after_outk marks that point, so a
+ * caller can start the reduce-scatter of Ok under the remaining work).  The B x B matrix never exists: G is staged as a bounded bf16
  * row panel in `workspace` and consumed by the two tensor-core contractions. */
 size_t mi_score_grad_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision);
 int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
@@ -105,6 +106,7 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
                   const float* refq, float wq, const float* refk, float wk,
                   int include_diag, int precision, float alpha, float gamma,
                   float* outq_f32, void* outq_bf16, int64_t ld_outq16, int outq_split, float* outk_f32,
+                  void* event_after_outk /* cudaEvent_t or NULL: recorded on `stream` once Ok is complete */,
                   void* workspace, size_t workspace_bytes, mi_stream_t stream);
 
 /* ---- the whole path, one GPU ------------------------------------------------------------------- */

@@ -30,7 +30,7 @@ PROTOTYPES = {
     "mi_score_grad_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "mi_score_grad": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
                               c_vp, c_f32, c_vp, c_f32, c_int, c_int, c_f32, c_f32,
-                              c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_sz, c_vp]),
+                              c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mi_critic_workspace_bytes": (c_sz, [c_i64, c_i64, c_int, c_int, c_int, c_int]),
     "mi_critic_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

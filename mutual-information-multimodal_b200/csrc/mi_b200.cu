@@ -609,7 +609,8 @@ struct GradOut {            // fp32 and/or bf16 (split == 2: [hi | lo] rows) des
 int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
               long long q_offset, long long Bq, long long Bk, long long D, float scale,
               const float* refq, float wq, const float* refk, float wk, int include_diag, int precision,
-              float alpha, float gamma, const GradOut& oq, const GradOut* ok, Bump& ws, cudaStream_t stream) {
+              float alpha, float gamma, const GradOut& oq, const GradOut* ok, Bump& ws, cudaStream_t stream,
+              cudaEvent_t ev_after_k = nullptr) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
   const bool strict = precision == MI_PREC_BF16_STRICT;
@@ -670,27 +671,7 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
                                         MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
     Bump none(nullptr, 0, false);
-    // (2) Oq[panel] = alpha (P V - gamma SUB), contraction over the Bk columns
-    if (oq.f32 || oq.bf16) {
-      GemmArgs g;
-      g.a = MapSpec{P, rows, pitch, pitch};
-      g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
-      g.M = rows; g.N = D; g.seg_len = kp; g.k_blocks = kp;
-      if (strict) {                                  // P_hi V_hi + P_lo V_hi (+ P_hi V_lo)
-        g.k_blocks = 2 * kp; g.a_seg[1] = kp;
-        if (k_hl) { g.k_blocks = 3 * kp; g.b_seg[2] = kp; }
-      }
-      g.alpha = alpha; g.gamma = gamma;
-      if (gamma != 0.f) {                            // - gamma K[q_offset + q]
-        g.sub = K.p + (q_offset + r0) * K.ld; g.ld_sub = K.ld;
-        g.sub_lo = k_hl ? g.sub + Dp : nullptr;
-      }
-      g.out_f32 = oq.f32 ? oq.f32 + r0 * oq.ld : nullptr; g.ld_out = oq.ld;
-      g.out_bf16 = oq.bf16 ? oq.bf16 + r0 * oq.ld16 : nullptr; g.ld_out16 = oq.ld16;
-      g.out_bf16_lo = (oq.bf16 && oq.split == 2) ? g.out_bf16 + Dp : nullptr;
-      MI_TRY(run_gemm(g, none, stream));
-    }
-    // (3) Ok += alpha (P^T Q[panel] - gamma SUBk), contraction over the panel's rows; P read MN-major
+    // (2) Ok += alpha (P^T Q[panel] - gamma SUBk), contraction over the panel's rows; P read MN-major
     if (ok) {
       GemmArgs g;
       const int kr = static_cast<int>(cdiv(rows, bk()));
@@ -711,6 +692,28 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
         g.sub_row0 = q_offset + r0; g.sub_rows = rows;
       }
       g.out_f32 = ok->f32; g.ld_out = ok->ld;
+      MI_TRY(run_gemm(g, none, stream));
+      // the K-side output is complete after the last panel: let the caller start its reduce-scatter here
+      if (ev_after_k != nullptr && r0 + panel_rows >= Bq) MI_CUDA(cudaEventRecord(ev_after_k, stream));
+    }
+    // (3) Oq[panel] = alpha (P V - gamma SUB), contraction over the Bk columns
+    if (oq.f32 || oq.bf16) {
+      GemmArgs g;
+      g.a = MapSpec{P, rows, pitch, pitch};
+      g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
+      g.M = rows; g.N = D; g.seg_len = kp; g.k_blocks = kp;
+      if (strict) {                                  // P_hi V_hi + P_lo V_hi (+ P_hi V_lo)
+        g.k_blocks = 2 * kp; g.a_seg[1] = kp;
+        if (k_hl) { g.k_blocks = 3 * kp; g.b_seg[2] = kp; }
+      }
+      g.alpha = alpha; g.gamma = gamma;
+      if (gamma != 0.f) {                            // - gamma K[q_offset + q]
+        g.sub = K.p + (q_offset + r0) * K.ld; g.ld_sub = K.ld;
+        g.sub_lo = k_hl ? g.sub + Dp : nullptr;
+      }
+      g.out_f32 = oq.f32 ? oq.f32 + r0 * oq.ld : nullptr; g.ld_out = oq.ld;
+      g.out_bf16 = oq.bf16 ? oq.bf16 + r0 * oq.ld16 : nullptr; g.ld_out16 = oq.ld16;
+      g.out_bf16_lo = (oq.bf16 && oq.split == 2) ? g.out_bf16 + Dp : nullptr;
       MI_TRY(run_gemm(g, none, stream));
     }
   }
@@ -942,7 +945,7 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
                   const float* refq, float wq, const float* refk, float wk, int include_diag, int precision,
                   float alpha, float gamma,
                   float* outq_f32, void* outq_bf16, int64_t ld_outq16, int outq_split, float* outk_f32,
-                  void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+                  void* event_after_outk, void* workspace, size_t workspace_bytes, mi_stream_t stream) {
   MI_TRY(device_check());
   if (q_offset < 0 || q_offset + Bq > Bk) return MI_ERR_BAD_ARG;
   Bump ws(workspace, workspace_bytes, false);
@@ -953,7 +956,8 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
   return grad_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
                    Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
                    sid_q, sid_k, q_offset, Bq, Bk, D, scale, refq, wq, refk, wk, include_diag, precision,
-                   alpha, gamma, oq, outk_f32 ? &ok : nullptr, ws, reinterpret_cast<cudaStream_t>(stream));
+                   alpha, gamma, oq, outk_f32 ? &ok : nullptr, ws, reinterpret_cast<cudaStream_t>(stream),
+                   reinterpret_cast<cudaEvent_t>(event_after_outk));
 }
 
 size_t mi_critic_workspace_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads) {

@@ -56,6 +56,28 @@ def merge_scalars(scal_all: torch.Tensor) -> dict:
     }
 
 
+def dense_labels(sid_raw: torch.Tensor) -> torch.Tensor:
+    """Exact int64 -> dense int32 relabelling (equal ids <=> equal labels) with static shapes only:
+    sort + run boundaries + cumsum + scatter.  Unlike torch.unique it never synchronises with the host."""
+    srt, idx = torch.sort(sid_raw)
+    new = torch.ones_like(srt, dtype=torch.int32)
+    new[1:] = (srt[1:] != srt[:-1]).to(torch.int32)
+    lab_sorted = torch.cumsum(new, 0, dtype=torch.int32) - 1
+    out = torch.empty_like(lab_sorted)
+    out[idx] = lab_sorted
+    return out
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 def _gather_mat(m, world, group):
     """all-gather rows of a plain tensor or of a hi/lo pair (ops.SplitBF16)."""
     if hasattr(m, "data") and hasattr(m, "width") and not torch.is_tensor(m):
@@ -82,14 +104,19 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     Xb, Yb = backend.as_bf16(X_local), backend.as_bf16(Y_local)
     Wb = backend.as_bf16(W) if bilinear else None
     # strict mode keeps T = X W as a hi/lo bf16 pair (16 significant bits into the score GEMM)
+    # ---- the exchange step (the all-gather of Y runs on NCCL's stream under the projection GEMM)
+    Y_all, y_work = Yb, None
+    if world > 1:
+        Y_all = torch.empty((Bg, D), dtype=Yb.dtype, device=Yb.device)
+        y_work = dist.all_gather_into_tensor(Y_all, Yb, group=group, async_op=True)
     T_local = backend.gemm(Xb, backend.transpose(Wb), out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb
-
-    # ---- the exchange step
-    Y_all = _all_gather_rows(Yb, world, group)
+    if y_work is not None:
+        y_work.wait()
     T_all = _gather_mat(T_local, world, group) if sym else None
-    sid_raw = _all_gather_rows(sid_local.to(torch.int64), world, group)
-    _, inv = torch.unique(sid_raw, return_inverse=True)          # identical on every rank
-    sid_all = inv.to(torch.int32)
+    if sid_local.dtype == torch.int32:                           # already exact int32 ids: use as they are
+        sid_all = _all_gather_rows(sid_local.contiguous(), world, group)
+    else:                                                        # identical on every rank, no host sync
+        sid_all = dense_labels(_all_gather_rows(sid_local.to(torch.int64), world, group))
     sid_loc = sid_all[off:off + Bl].contiguous()
 
     # ---- statistics (S never materialised)
@@ -127,22 +154,38 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         args = dict(refq=rows_r[:, 3].contiguous(), wq=0.5 / Bg, refk=c_all, wk=0.5 / Bg, include_diag=True)
     else:
         args = dict(refq=rows_r[:, 3].contiguous(), wq=1.0 / Bg, refk=None, wk=0.0, include_diag=True)
+    nccl = world > 1 and dist.get_backend(group) != "gloo"
+    ev = None
+    if nccl:                                          # marks "dY contributions complete" inside the fused pass
+        ev = torch.cuda.Event()
+        ev.record()
+        args["event_after_k"] = ev
     dT32, dT16, dY_part = backend.score_grad(T_local, Y_all, sid_loc, sid_all, off, inv_tau, precision=precision,
                                              alpha=inv_tau, gamma=gamma, want_f32=not bilinear, want_bf16=bilinear,
                                              out_split=bilinear and strict, want_k=True, **args)
-    if world > 1:
-        if dist.get_backend(group) == "gloo":         # gloo (CPU tests) has no reduce-scatter
-            dist.all_reduce(dY_part, op=dist.ReduceOp.SUM, group=group)
-            dY = dY_part[off:off + Bl].contiguous()
-        else:
-            dY = torch.empty((Bl, D), dtype=dY_part.dtype, device=dY_part.device)
-            dist.reduce_scatter_tensor(dY, dY_part, op=dist.ReduceOp.SUM, group=group)
+    rs_work = None
+    if nccl:
+        # reduce-scatter starts as soon as the dY contributions are complete and runs under the dT
+        # contraction and the dX / dW GEMMs still queued on the compute stream
+        main = torch.cuda.current_stream()
+        side = _side_stream(dY_part.device)
+        side.wait_event(ev)
+        dY = torch.empty((Bl, D), dtype=dY_part.dtype, device=dY_part.device)
+        with torch.cuda.stream(side):
+            rs_work = dist.reduce_scatter_tensor(dY, dY_part, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        dY_part.record_stream(side)
+        dY.record_stream(side)
+    elif world > 1:                                   # gloo (CPU tests) has no reduce-scatter
+        dist.all_reduce(dY_part, op=dist.ReduceOp.SUM, group=group)
+        dY = dY_part[off:off + Bl].contiguous()
     else:
         dY = dY_part
-    if not bilinear:
-        return out, dT32, dY, None
-    dX = backend.gemm(dT16, Wb)                                               # dT W^T
-    dW = backend.gemm(backend.transpose(Xb), backend.transpose(dT16))         # X^T dT (local rows)
-    if world > 1:
-        dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group)
+    dX, dW = dT32, None
+    if bilinear:
+        dX = backend.gemm(dT16, Wb)                                               # dT W^T
+        dW = backend.gemm(backend.transpose(Xb), backend.transpose(dT16))         # X^T dT (local rows)
+        if world > 1:
+            dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group)
+    if rs_work is not None:
+        rs_work.wait()                                # current (compute) stream waits for the collective
     return out, dX, dY, dW

@@ -191,9 +191,12 @@ def score_stats(Q: Mat, K: Mat, sid_q: torch.Tensor, sid_k: torch.Tensor,
 def score_grad(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
                refq: Optional[torch.Tensor], wq: float, refk: Optional[torch.Tensor], wk: float,
                include_diag: bool, precision: str, alpha: float, gamma: float,
-               want_f32: bool = True, want_bf16: bool = False, out_split: bool = False, want_k: bool = False):
+               want_f32: bool = True, want_bf16: bool = False, out_split: bool = False, want_k: bool = False,
+               event_after_k: Optional["torch.cuda.Event"] = None):
     """Fused gradient pass (mi_score_grad).  Returns (Oq fp32 | None, Oq bf16 / SplitBF16 | None,
-    Ok fp32 [Bk, D] | None):  Oq = alpha (G K - gamma K_diag),  Ok = alpha (G^T Q - gamma Q_diag)."""
+    Ok fp32 [Bk, D] | None):  Oq = alpha (G K - gamma K_diag),  Ok = alpha (G^T Q - gamma Q_diag).
+    ``event_after_k`` (a recorded torch.cuda.Event) is re-recorded on the current stream as soon as Ok is
+    complete, before the Oq contraction runs."""
     _need_cuda(Q, K, sid_q, sid_k, refq, refk)
     lib = _lib.load()
     Qt, ldq, qsp, D = _opnd(Q)
@@ -221,6 +224,7 @@ def score_grad(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
     _check(lib.mi_score_grad(_ptr(Qt), ldq, qsp, _ptr(Kt), ldk, ksp, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D, scale,
                              _ptr(refq), wq, _ptr(refk), wk, int(include_diag), prec, alpha, gamma,
                              _ptr(o32), _ptr(ob), ld16, 2 if out_split else 1, _ptr(okk),
+                             None if event_after_k is None else C.c_void_p(event_after_k.cuda_event),
                              _ptr(ws), ws.numel(), _stream()), "mi_score_grad")
     return o32, o16, okk
 
