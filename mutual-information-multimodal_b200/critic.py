@@ -75,6 +75,25 @@ def create_mi_pairs(embedding_img: torch.Tensor, embedding_txt: torch.Tensor,
     return PairBatch(embedding_img, embedding_txt, sid.to(dev, non_blocking=True))
 
 
+def create_mi_pairs_tensor(embedding_img: torch.Tensor, embedding_txt: torch.Tensor,
+                           study_id: Union[Sequence, torch.Tensor], device=None) -> torch.Tensor:
+    """The reference's explicit ``[B + N_neg, 2D]`` pair tensor in the reference's row order
+    (main_utils.py:93-108: B matched rows, then gap-major negatives (i, (i+gap+1) mod B) with different
+    study ids) built by index arithmetic and ONE gather instead of the O(B^2) ``torch.cat`` loop
+    (SURVEY 8f-2).  For critics that are not fused (e.g. the original ``make_mlp``) at small B; differentiable."""
+    B = embedding_img.shape[0]
+    dev = embedding_img.device
+    sid = _dense_ids(study_id).to(dev)
+    pos = torch.cat((embedding_img, embedding_txt), 1)
+    if B < 2:
+        return pos
+    i = torch.arange(B, device=dev).expand(B - 1, B)
+    j = (i + torch.arange(1, B, device=dev)[:, None]) % B
+    keep = (sid[i] != sid[j]).reshape(-1)
+    ii, jj = i.reshape(-1)[keep], j.reshape(-1)[keep]
+    return torch.cat((pos, torch.cat((embedding_img[ii], embedding_txt[jj]), 1)), 0)
+
+
 class ScoreHandle:
     """Lazy stand-in for the ``[N, 1]`` logits tensor (``mi_output``, main_utils.py:222)."""
 
