@@ -395,6 +395,7 @@ struct EpiPStore {
     __nv_bfloat16* P;       // [q_rows, pitch]
     __nv_bfloat16* P_lo;    // residual panel (strict mode) or nullptr
     long long pitch;
+    int dbg;                // experiments: 1 = no global stores, 2 = direct register stores (no smem staging)
   };
   struct State { uint8_t* stage_smem; MaskState ms; float rq2; };
 
@@ -421,7 +422,7 @@ struct EpiPStore {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int r = it * 8 + (lane >> 2), ch = lane & 3;
-      if (r < rows_valid) *reinterpret_cast<uint4*>(dst_row0 + (size_t)r * pitch + ch * 8) = val[it];
+      if (r < rows_valid) ptx::st_global_cs(dst_row0 + (size_t)r * pitch + ch * 8, val[it]);
     }
     __syncwarp();
   }
@@ -463,7 +464,15 @@ struct EpiPStore {
     for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
     const int row0 = row - lane;                       // first row of this warp
     const int rows_valid = p.q_rows - row0;
-    stage_and_flush(st.stage_smem, lane, hi, p.P + (size_t)row0 * p.pitch + col0, p.pitch, rows_valid);
+    if (p.dbg == 2) {
+      if (row < p.q_rows) {
+        uint4* dst = reinterpret_cast<uint4*>(p.P + (size_t)row * p.pitch + col0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dst[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+      }
+      return;
+    }
+    stage_and_flush(st.stage_smem, lane, hi, p.P + (size_t)row0 * p.pitch + col0, p.pitch, p.dbg == 1 ? 0 : rows_valid);
     if (p.P_lo != nullptr) {                           // strict mode: residual panel
 #pragma unroll
       for (int c = 0; c < 16; ++c) {

@@ -20,6 +20,7 @@ using mi::Sched;
 // ------------------------------------------------------------------------------------ errors
 thread_local char g_cuda_err[512] = "";
 std::atomic<long long> g_launches{0};
+int g_debug = 0;
 int g_cta_group = -1;   // resolved lazily: env MI_CTA_GROUP or 2
 
 // optional per-launch CUDA-event timing of the tile-engine kernels (bench.py's roofline breakdown)
@@ -667,7 +668,7 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     ep.q_offset = q_offset + r0; ep.scale = scale;
     ep.refq = use_q ? refq + r0 : nullptr; ep.ln_wq = use_q ? logf(wq) : 0.f; ep.use_q = use_q ? 1 : 0;
     ep.refk2 = refk2; ep.use_k = use_k ? 1 : 0; ep.include_diag = include_diag;
-    ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
+    ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch; ep.dbg = g_debug;
     MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
                                         MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
     Bump none(nullptr, 0, false);
@@ -882,6 +883,7 @@ int mi_profile_read(double* ms, int64_t* launches) {
   g_prof.clear();
   return MI_OK;
 }
+void mi_set_debug(int v) { g_debug = v; }
 void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
 int mi_get_cta_group(void) { return cta_group(); }
 

@@ -245,6 +245,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
        | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// streaming 16 B store: written once, read back later from DRAM -> do not displace the operand tiles in L2
+__device__ __forceinline__ void st_global_cs(void* ptr, const uint4& v) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---------------------------------------------------------------- math
 __device__ __forceinline__ float ex2(float x) {
   float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
