@@ -134,6 +134,49 @@ class _FusedCriticLoss(torch.autograd.Function):
         return gx, gy, gw, None, None, None, None, None
 
 
+class _ShardedFusedCriticLoss(torch.autograd.Function):
+    """Data-parallel form: every rank passes its row shard; the loss is the GLOBAL-batch estimator
+    (identical on all ranks), gradients are returned for the local rows and dW is already summed."""
+
+    @staticmethod
+    def forward(ctx, X, Y, W, sid, estimator, precision, inv_tau, group, grad_scale):
+        from . import dist as mdist
+        need = any(t is not None and t.requires_grad for t in (X, Y, W))
+        out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(X, Y, W, sid, estimator, precision, inv_tau,
+                                                           need_grads=need, group=group)
+        ctx.grads = (dX, dY, dW)
+        ctx.dtypes = (X.dtype, Y.dtype, None if W is None else W.dtype)
+        ctx.grad_scale = grad_scale
+        ctx.stats = out
+        return out["loss"].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dX, dY, dW = ctx.grads
+        tx, ty, tw = ctx.dtypes
+        g = grad_out.to(torch.float32)
+        ge = g * ctx.grad_scale          # encoder grads: DDP averages over ranks, the global loss needs the sum
+        gx = None if dX is None else (dX * ge).to(tx)
+        gy = None if dY is None else (dY * ge).to(ty)
+        gw = None if dW is None else (dW * g).to(tw)
+        return gx, gy, gw, None, None, None, None, None, None
+
+
+def sharded_mi_loss(embedding_img, embedding_txt, critic: "FusedCritic", study_id, estimator: str = "dv",
+                    group=None, ddp_mean_correction: bool = True) -> torch.Tensor:
+    """Global-batch MI loss when every rank holds a row shard of the batch.
+    ``study_id`` is this rank's integer id tensor (raw int64 ids are relabelled consistently across ranks).
+    With ``ddp_mean_correction`` the embedding gradients are multiplied by the world size so that
+    DistributedDataParallel's gradient averaging of the encoders yields the gradient of the global loss."""
+    import torch.distributed as tdist
+    world = tdist.get_world_size(group) if tdist.is_available() and tdist.is_initialized() else 1
+    sid = study_id if torch.is_tensor(study_id) else torch.tensor([int(s) for s in study_id], dtype=torch.int64)
+    sid = sid.to(embedding_img.device)
+    scale = float(world) if ddp_mean_correction else 1.0
+    return _ShardedFusedCriticLoss.apply(embedding_img, embedding_txt, critic.W, sid, estimator, critic.precision,
+                                         critic.inv_tau, group, scale)
+
+
 class FusedCritic(nn.Module):
     """Separable critic f(x, y) = inv_tau * x^T W y in the ``mi_discriminator`` slot
     (main_utils.py:77,222).  ``critic='dot'`` has no parameters (W = I); ``'bilinear'`` owns W [D, D].

@@ -195,6 +195,29 @@ def test_sharded_composition_world1_equals_fused_call(env):
         assert _rel(dW, fW.cpu()) < 1e-5          # split-K order differs
 
 
+def test_sharded_autograd_loss_world1(env):
+    """mi_b200.sharded_mi_loss (the data-parallel entry used with DDP encoders) == the single-GPU adapter."""
+    mi_b200, ops, mo, dev = env
+    B, D = 320, 64
+    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=12, dup_frac=0.1)
+    outs = []
+    for sharded in (False, True):
+        x = X.bfloat16().float().to(dev).requires_grad_(True)
+        y = Y.bfloat16().float().to(dev).requires_grad_(True)
+        critic = mi_b200.FusedCritic(D, "bilinear", precision="strict").to(dev)
+        with torch.no_grad():
+            critic.W.copy_(W.bfloat16().float())
+        if sharded:
+            loss = mi_b200.sharded_mi_loss(x, y, critic, sid * 7 + 3, "infonce_sym")
+        else:
+            loss = mi_b200.select_estimator("infonce_sym")(critic(mi_b200.create_mi_pairs(x, y, [int(s) for s in sid], dev)), B, dev)
+        loss.backward()
+        outs.append((loss.item(), x.grad.clone(), y.grad.clone(), critic.W.grad.clone()))
+    assert abs(outs[0][0] - outs[1][0]) < 1e-6
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert _rel(a, b.cpu()) < 1e-5
+
+
 def test_host_buffer_abi_matches_device_call(env):
     mi_b200, ops, mo, dev = env
     from mi_b200 import _lib
