@@ -47,7 +47,10 @@ enum mi_critic { MI_CRITIC_DOT = 0, MI_CRITIC_BILINEAR = 1 };
 enum mi_estimator { MI_EST_DV = 0, MI_EST_INFONCE_REF = 1, MI_EST_INFONCE_ROW = 2, MI_EST_INFONCE_SYM = 3 };
 
 enum mi_precision { MI_PREC_BF16_FAST = 0,   /* dS panel rounded once to bf16 */
-                    MI_PREC_BF16_STRICT = 1  /* dS = hi + lo bf16 split (fp32-accumulate mode) */ };
+                    MI_PREC_BF16_STRICT = 1, /* dS = hi + lo bf16 split (fp32-accumulate mode) */
+                    MI_PREC_TWO_PASS = 2     /* flag (OR it in): statistics pass + gradient pass with the exact
+                                                log-sum-exp references, instead of the single pass that uses a
+                                                Cauchy-Schwarz score bound as reference (mi_critic_loss_fwd_bwd) */ };
 
 const char* mi_status_string(int status);
 const char* mi_last_cuda_error(void);
@@ -109,9 +112,36 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
                   void* event_after_outk /* cudaEvent_t or NULL: recorded on `stream` once Ok is complete */,
                   void* workspace, size_t workspace_bytes, mi_stream_t stream);
 
+/* Single-pass form of statistics + gradients for dv / infonce / row InfoNCE (one score computation instead
+ * of two).  rho[q] = scale |Q_q| max_k |K_k| bounds the scores of row q (Cauchy-Schwarz), so
+ * P~ = incl e^{S - rho} <= 1 is written without a prior statistics pass; the same tiles give the row sums
+ * (=> row_out / scal_out exactly as mi_score_stats; for include_diag = 1 the sums include the positive pair) and
+ *   oq_raw[q,:] = sum_k P~[q,k] K[k,:]                 ok_raw[k,:] = sum_q P~[q,k] wrow[q] Q[q,:]
+ * with wrow = e^{rho - lambda} (include_diag = 0) or inv_bg / rowsum (include_diag = 1); lambda = the bound of the
+ * largest row norm (qnorm_max_in: device scalar holding max |Q_q| over ALL ranks, NULL = this call's rows).
+ * flag_out counts rows whose bound was > ~60 above all their scores: must be 0, else use the two-pass calls.
+ * The gradients follow from mi_single_finalize_q / _k once the (global) log-sum-exp is known:
+ *   Oq = alpha (c_q oq_raw - gamma Kdiag),  c_q = e^{rho_q - lse} (dv_like) or wrow_q
+ *   Ok = alpha (kappa ok_raw - gamma Qdiag), kappa = e^{lambda - lse} (dv_like) or 1     (in place) */
+size_t mi_score_single_pass_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision);
+int mi_row_norm_max(const void* A, int64_t lda, int a_split, int64_t rows, int64_t D, float* norm_out, float* max_out, mi_stream_t stream);
+int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
+                         const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                         int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag, int precision, float inv_bg,
+                         const float* qnorm_max_in, float* row_out /*[Bq,4]*/, double* scal_out /*[8]*/,
+                         float* oq_raw /*[Bq,D]*/, float* ok_raw /*[Bk,D] or NULL*/,
+                         float* rho /*[Bq]*/, float* wrow /*[Bq]*/, float* lambda_out /*[1]*/, int32_t* flag_out /*[1]*/,
+                         void* event_after_outk, void* workspace, size_t workspace_bytes, mi_stream_t stream);
+int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const float* rho, const float* wrow, const float* lse,
+                         int dv_like, float alpha, float gamma, const void* kdiag, int64_t ldk, int k_split,
+                         float* out_f32, void* out_bf16, int64_t ld16, int out_split, mi_stream_t stream);
+int mi_single_finalize_k(float* ok, int64_t rows, int64_t D, const float* lambda, const float* lse, int dv_like,
+                         float alpha, float gamma, const void* qdiag, int64_t ldq, int q_split, mi_stream_t stream);
+
 /* ---- the whole path, one GPU ------------------------------------------------------------------- */
 
-/* loss_out (fp64[8]) = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, #rows w/o negatives, 0 }.
+/* loss_out (fp64[8]) = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, #rows w/o negatives, #rows whose
+ * single-pass reference was too loose (must be 0; otherwise repeat the call with MI_PREC_TWO_PASS) }.
  * X = image embeddings [B,D], Y = text embeddings [B,D], W = [D,D] (NULL for the dot critic),
  * S = inv_tau * X W Y^T.  dX, dY (fp32 [B,D]) and dW (fp32 [D,D]) may all be NULL (forward only). */
 size_t mi_critic_workspace_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads);
@@ -140,6 +170,8 @@ int mi_profile_read(double* ms /*[3]*/, int64_t* launches /*[3]*/);
 /* bring-up / A-B knob: 2 (default) = CTA pairs, cta_group::2 MMAs with M = 256; 1 = single-CTA M = 128.
  * Also settable through the environment variable MI_CTA_GROUP before the first call. */
 void mi_set_cta_group(int group);
+void mi_set_debug(int value);          /* experiments only */
+void mi_set_single_pass(int on);       /* 0: mi_critic_loss_fwd_bwd always takes the two-pass path */
 int mi_get_cta_group(void);
 
 #ifdef __cplusplus

@@ -395,11 +395,16 @@ struct EpiPStore {
     __nv_bfloat16* P;       // [q_rows, pitch]
     __nv_bfloat16* P_lo;    // residual panel (strict mode) or nullptr
     long long pitch;
+    // single-pass mode: refq is a per-row UPPER BOUND of the scores, so P <= 1 needs no running max; the
+    // row sums of P (fp32, before rounding) are the statistics: sum_part[n_split][4][rows_padded]
+    float* sum_part;
+    int rows_padded;
     int dbg;                // experiments: 1 = no global stores, 2 = direct register stores (no smem staging)
   };
-  struct State { uint8_t* stage_smem; MaskState ms; float rq2; };
+  struct State { uint8_t* stage_smem; MaskState ms; float rq2; float s; };
 
   static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
+    st.s = 0.f;
     mask_begin(p.mask, st.ms, row, p.q_rows);
     const float r = (p.use_q && row < p.q_rows) ? __ldg(p.refq + row) : 0.f;
     st.rq2 = (r - p.ln_wq) * kLog2e;
@@ -459,6 +464,15 @@ struct EpiPStore {
 #pragma unroll
       for (int c = 0; c < 32; ++c) if ((mk >> c) & 1u) v[c] = 0u;
     }
+    if (p.sum_part != nullptr) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        s0 += __uint_as_float(v[c]); s1 += __uint_as_float(v[c + 1]);
+        s2 += __uint_as_float(v[c + 2]); s3 += __uint_as_float(v[c + 3]);
+      }
+      st.s += (s0 + s1) + (s2 + s3);
+    }
     uint32_t hi[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
@@ -482,7 +496,9 @@ struct EpiPStore {
       stage_and_flush(st.stage_smem, lane, hi, p.P_lo + (size_t)row0 * p.pitch + col0, p.pitch, rows_valid);
     }
   }
-  static __device__ __forceinline__ void unit_end(const Params&, State&, const Unit&, int, int) {}
+  static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit& un, int row, int colq) {
+    if (p.sum_part != nullptr) p.sum_part[((size_t)un.s * kColQuarters + colq) * p.rows_padded + row] = st.s;
+  }
 };
 
 // ---- plain GEMM epilogue: C = alpha * (ACC - gamma * SUB) [+ C_prev]

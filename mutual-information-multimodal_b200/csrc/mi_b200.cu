@@ -316,6 +316,133 @@ __global__ void diag_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq, 
   if (lane == 0) diag[row] = acc * scale;
 }
 
+// ---- single-pass ("safe reference") path ------------------------------------------------------------
+// row L2 norms of a bf16 matrix (hi/lo pairs summed), one warp per row
+__global__ void row_norm_kernel(const __nv_bfloat16* __restrict__ A, long long ld, int split, long long Dp,
+                                long long rows, long long D, float* __restrict__ norm) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* a = A + row * ld;
+  float acc = 0.f;
+  for (long long d = lane * 2; d < D; d += 64) {
+    float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + d));
+    if (split == 2) { const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + Dp + d)); v.x += l.x; v.y += l.y; }
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) norm[row] = sqrtf(acc);
+}
+// one block: out[0] = max_i f(in[i]);  mode 0: f = identity, mode 1: f = scale * in[i] * other[0] * 1.001 + 1e-3 written to out2
+__global__ void max_reduce_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float m = mi::neg_inf();
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, in[i]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { float g = mi::neg_inf(); for (int i = 0; i < (int)(blockDim.x >> 5); ++i) g = fmaxf(g, sh[i]); out[0] = g; }
+}
+// Cauchy-Schwarz: S[q,k] = scale <Q_q, K_k> <= scale |Q_q| max_k |K_k| =: rho[q]  (a hair above, for rounding)
+__global__ void rho_kernel(const float* __restrict__ qnorm, const float* __restrict__ kmax, float scale, long long n,
+                           float* __restrict__ rho) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) rho[i] = scale * qnorm[i] * kmax[0] * 1.001f + 1e-3f;
+}
+// rows of one panel: l = sum of the partial row sums of P~ = e^{S - rho};  row_out = {lse_neg, n_neg, diag, lse_all},
+// wrow = weight of the row inside the G^T Q contraction, flag += rows whose reference was too loose
+__global__ void sum_merge_kernel(const float* __restrict__ part, int n_part, int rows_padded, int rows,
+                                 const float* __restrict__ rho, const float* __restrict__ lambda, const int* __restrict__ n_same,
+                                 int k_cols, const float* __restrict__ diag_in, int include_diag, float inv_bg,
+                                 float4* __restrict__ row_out, float* __restrict__ lsum, float* __restrict__ wrow,
+                                 int* __restrict__ flag) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float l = 0.f;
+  for (int p = 0; p < n_part; ++p) l += part[(size_t)p * rows_padded + row];
+  const float cnt = static_cast<float>(k_cols - n_same[row]);
+  const float diag = diag_in[row], r = rho[row];
+  const float n_incl = cnt + (include_diag ? 1.f : 0.f);
+  if (n_incl > 0.f && !(l >= 1e-26f)) atomicAdd(flag, 1);          // reference > ~60 above every score of the row
+  float lse_neg, lse_all;
+  if (include_diag) {
+    lse_all = r + logf(l);
+    lse_neg = cnt > 0.f ? lse_all + log1pf(-fminf(expf(diag - lse_all), 1.f)) : mi::neg_inf();
+    wrow[row] = inv_bg / l;                                          // (1/B) e^{rho - r_i}
+  } else {
+    lse_neg = (cnt > 0.f && l > 0.f) ? r + logf(l) : mi::neg_inf();
+    const float hi = fmaxf(lse_neg, diag), lo = fminf(lse_neg, diag);
+    lse_all = hi + log1pf(expf(lo - hi));
+    wrow[row] = expf(r - lambda[0]);                                 // e^{rho - lambda}; e^{lambda - LSE} is applied at the end
+  }
+  lsum[row] = l;
+  row_out[row] = make_float4(lse_neg, cnt, diag, lse_all);
+}
+// out[c, r] = bf16(w[r] * in[r, c]) (+ residual half at out_lo); in may be a hi/lo pair
+__global__ void transpose_scale_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, int in_split, long long Dp,
+                                       const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo,
+                                       long long ld_out, long long R, long long C) {
+  __shared__ float tile[64][65];
+  const long long r0 = blockIdx.y * 64LL, c0 = blockIdx.x * 64LL;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int i = ty; i < 64; i += 4) {
+    const long long r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = __bfloat162float(in[r * ld_in + c]);
+      if (in_split == 2) v += __bfloat162float(in[r * ld_in + Dp + c]);
+      v *= w[r];
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const long long c = c0 + i, r = r0 + tx;
+    if (c < C && r < R) {
+      const float v = tile[tx][i];
+      const __nv_bfloat16 h = __float2bfloat16(v);
+      out[c * ld_out + r] = h;
+      if (out_lo) out_lo[c * ld_out + r] = __float2bfloat16(v - __bfloat162float(h));
+    }
+  }
+}
+// Oq[i,:] = alpha (c_i Oraw[i,:] - gamma Kdiag[i,:]),  c_i = e^{rho_i - LSE} (DV) or wrow_i (row InfoNCE)
+__global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, long long rows, const float* __restrict__ rho,
+                                  const float* __restrict__ wrow, const float* __restrict__ lse, int dv_like,
+                                  float alpha, float gamma, const __nv_bfloat16* __restrict__ kdiag, long long ldk, int k_split, long long Dp,
+                                  float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ out_lo, long long ld16) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= rows * D) return;
+  const long long i = idx / D, d = idx - i * D;
+  const float c = dv_like ? expf(rho[i] - lse[0]) : wrow[i];
+  float kd = __bfloat162float(kdiag[i * ldk + d]);
+  if (k_split == 2) kd += __bfloat162float(kdiag[i * ldk + Dp + d]);
+  const float o = alpha * (c * raw[idx] - gamma * kd);
+  if (out_f32) out_f32[idx] = o;
+  if (out_bf16) {
+    const __nv_bfloat16 h = __float2bfloat16(o);
+    out_bf16[i * ld16 + d] = h;
+    if (out_lo) out_lo[i * ld16 + d] = __float2bfloat16(o - __bfloat162float(h));
+  }
+}
+// Ok[k,:] = alpha (kappa Ok[k,:] - gamma [0 <= k-q_offset < Bq] Q[k-q_offset,:]),  kappa = e^{lambda - LSE} (DV) or 1
+__global__ void finalize_k_kernel(float* __restrict__ ok, long long D, long long Bk, const float* __restrict__ lambda,
+                                  const float* __restrict__ lse, int dv_like, float alpha, float gamma,
+                                  const __nv_bfloat16* __restrict__ Q, long long ldq, int q_split, long long Dp,
+                                  long long q_offset, long long Bq) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= Bk * D) return;
+  const long long k = idx / D, d = idx - k * D;
+  const float kappa = dv_like ? expf(lambda[0] - lse[0]) : 1.f;
+  float qd = 0.f;
+  const long long q = k - q_offset;
+  if (q >= 0 && q < Bq) {
+    qd = __bfloat162float(Q[q * ldq + d]);
+    if (q_split == 2) qd += __bfloat162float(Q[q * ldq + Dp + d]);
+  }
+  ok[idx] = alpha * (kappa * ok[idx] - gamma * qd);
+}
+
 // merge the (split, half) partials of one row -> {lse_neg, n_neg, diag, lse_all}
 __global__ void stats_merge_kernel(const float4* __restrict__ part, int n_part, int rows_padded, int q_rows,
                                    const int* __restrict__ n_same, int k_cols, const float* __restrict__ diag_in,
@@ -669,6 +796,7 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     ep.refq = use_q ? refq + r0 : nullptr; ep.ln_wq = use_q ? logf(wq) : 0.f; ep.use_q = use_q ? 1 : 0;
     ep.refk2 = refk2; ep.use_k = use_k ? 1 : 0; ep.include_diag = include_diag;
     ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch; ep.dbg = g_debug;
+    ep.sum_part = nullptr; ep.rows_padded = 0;
     MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
                                         MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
     Bump none(nullptr, 0, false);
@@ -721,6 +849,146 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   return MI_OK;
 }
 
+// Single-pass variant of the forward statistics + gradient pass (dv / infonce / row InfoNCE).
+// rho[q] = scale |Q_q| max_k |K_k| bounds every score of row q from above (Cauchy-Schwarz), so
+// P~ = incl * e^{S - rho} <= 1 needs no running max and no statistics pass BEFORE the panel is written:
+// the same score tiles give (a) the row sums l_q = sum_k P~ (=> LSE_q = rho_q + ln l_q, the loss) and
+// (b) the bf16 panel P~ whose two contractions, rescaled per row / globally afterwards, are the gradients:
+//   dV-side   Oq_raw = P~ K                         final: alpha (c_q Oq_raw - gamma K_diag)
+//   dQ-side   Ok_raw = sum_q P~[q,:]^T (w_q Q_q)    final: alpha (kappa Ok_raw - gamma Q_diag)
+//   DV: c_q = e^{rho_q - LSE}, w_q = e^{rho_q - lambda}, kappa = e^{lambda - LSE};  row InfoNCE: c_q = w_q = 1/(B l_q), kappa = 1.
+// One score computation instead of two: 6 B^2 D executed = the algorithmic count.  If a row's reference is
+// more than ~60 above all of its scores (flag_out > 0) the caller must redo the step with the two-pass path.
+int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
+                     long long q_offset, long long Bq, long long Bk, long long D, float scale,
+                     int include_diag, int precision, float inv_bg, const float* qmax_in,
+                     float* row_out, float* oq_raw, float* ok_raw,
+                     float* rho, float* wrow, float* lambda_out, int* flag_out, Bump& ws, cudaStream_t stream,
+                     cudaEvent_t ev_after_k = nullptr) {
+  if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
+  typedef __nv_bfloat16 bf;
+  const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
+  const int n_ntile = static_cast<int>(cdiv(Bk, mi::TILE_N));
+  const long long k_pad = static_cast<long long>(n_ntile) * mi::TILE_N;
+  const int kp = static_cast<int>(k_pad / bk());
+  const long long pitch = k_pad * (strict ? 2 : 1);
+  const long long Dp = round_up(D, kSplitAlign);
+  const bool k_hl = strict && K.split == 2;
+  const long long ld_kt = k_pad * (k_hl ? 2 : 1);
+  const long long mb_panel = panel_mblks(Bq, Bk, D, precision & 1);
+  const long long panel_rows = mb_panel * rows_per_mblk();
+  const long long r_pad = round_up(panel_rows, kSplitAlign);
+  const long long ld_qt = r_pad * (strict ? 2 : 1);
+  const int max_split = n_ntile;
+  const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
+  bf* Kt = ws.take<bf>(static_cast<size_t>(D) * ld_kt);
+  bf* Qt = ok_raw || ws.dry ? ws.take<bf>(static_cast<size_t>(D) * ld_qt) : nullptr;
+  bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
+  float* part = ws.take<float>(static_cast<size_t>(max_split > 64 ? 64 : max_split) * mi::kColQuarters * panel_rows);
+  float* qnorm = ws.take<float>(Bq);
+  float* knorm = ws.take<float>(Bk);
+  float* kmax = ws.take<float>(1);
+  float* diag = ws.take<float>(Bq);
+  float* lsum = ws.take<float>(Bq);
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  if (ws.dry) return MI_OK;
+  if (!Q.p || !K.p || !sid_q || !sid_k || !row_out || !oq_raw || !rho || !wrow || !lambda_out || !flag_out || !(scale > 0.f))
+    return MI_ERR_BAD_ARG;
+
+  MI_TRY(build_mask(mb, sid_q, sid_k, Bq, Bk, k_pad, stream));
+  MI_CUDA(cudaMemsetAsync(flag_out, 0, sizeof(int), stream));
+  const Opnd Qe{Q.p, Q.ld, strict ? Q.split : 1}, Ke{K.p, K.ld, strict ? K.split : 1};
+  // references
+  row_norm_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Dp, Bq, D, qnorm);
+  MI_LAUNCH_CHECK("row_norm_kernel");
+  row_norm_kernel<<<blocks_for(Bk * 32, 256), 256, 0, stream>>>(Ke.p, Ke.ld, Ke.split, Dp, Bk, D, knorm);
+  MI_LAUNCH_CHECK("row_norm_kernel");
+  max_reduce_kernel<<<1, 1024, 0, stream>>>(knorm, Bk, kmax);
+  MI_LAUNCH_CHECK("max_reduce_kernel");
+  rho_kernel<<<blocks_for(Bq, 256), 256, 0, stream>>>(qnorm, kmax, scale, Bq, rho);
+  MI_LAUNCH_CHECK("rho_kernel");
+  // lambda = the same bound for the largest row norm (of ALL ranks when qmax_in is given): a global constant
+  if (qmax_in) { rho_kernel<<<1, 32, 0, stream>>>(qmax_in, kmax, scale, 1, lambda_out); MI_LAUNCH_CHECK("rho_kernel"); }
+  else { max_reduce_kernel<<<1, 1024, 0, stream>>>(rho, Bq, lambda_out); MI_LAUNCH_CHECK("max_reduce_kernel"); }
+  diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split, q_offset, Bq, D, Dp, scale, diag);
+  MI_LAUNCH_CHECK("diag_kernel");
+  // V^T for the P K product
+  if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
+  MI_TRY(transpose_impl(K.p, K.ld, Kt, ld_kt, Bk, D, stream));
+  if (k_hl) MI_TRY(transpose_impl(K.p + Dp, K.ld, Kt + k_pad, ld_kt, Bk, D, stream));
+  if (Qt && strict) MI_CUDA(cudaMemsetAsync(Qt, 0, static_cast<size_t>(D) * ld_qt * sizeof(bf), stream));
+
+  for (long long r0 = 0; r0 < Bq; r0 += panel_rows) {
+    const long long rows = (Bq - r0 < panel_rows) ? (Bq - r0) : panel_rows;
+    // (1) score tiles -> P~ panel + row sums
+    Sched sc;
+    sc.n_mblk = static_cast<int>(cdiv(rows, rows_per_mblk()));
+    sc.n_ntile = n_ntile;
+    sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
+    if (sc.n_split > 64) sc.n_split = 64;
+    sc.n_ksplit = 1; sc.order = 0;
+    MI_TRY(score_segments(sc, Qe, Ke, D));
+    const int rows_padded = sc.n_mblk * rows_per_mblk();
+    mi::EpiPStore::Params ep;
+    ep.mask = mi::MaskInfo{mb.excl + r0, mb.n_same + r0, sid_q + r0, mb.sidk_pad};
+    ep.q_rows = static_cast<int>(rows); ep.k_cols = static_cast<int>(Bk);
+    ep.q_offset = q_offset + r0; ep.scale = scale;
+    ep.refq = rho + r0; ep.ln_wq = 0.f; ep.use_q = 1;
+    ep.refk2 = nullptr; ep.use_k = 0; ep.include_diag = include_diag;
+    ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
+    ep.sum_part = part; ep.rows_padded = rows_padded; ep.dbg = g_debug;
+    MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
+                                        MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
+    sum_merge_kernel<<<blocks_for(rows, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(rows),
+                                                                rho + r0, lambda_out, mb.n_same + r0, static_cast<int>(Bk), diag + r0,
+                                                                include_diag, inv_bg, reinterpret_cast<float4*>(row_out) + r0,
+                                                                lsum + r0, wrow + r0, flag_out);
+    MI_LAUNCH_CHECK("sum_merge_kernel");
+    Bump none(nullptr, 0, false);
+    // (2) Ok_raw += P~^T (w Q)[panel]: contraction over the panel rows, P~ read MN-major
+    if (ok_raw) {
+      dim3 tg(static_cast<unsigned>(cdiv(D, 64)), static_cast<unsigned>(cdiv(rows, 64)));
+      transpose_scale_kernel<<<tg, 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qt, strict ? Qt + r_pad : nullptr,
+                                                     ld_qt, rows, D);
+      MI_LAUNCH_CHECK("transpose_scale_kernel");
+      GemmArgs g;
+      const int kr = static_cast<int>(cdiv(rows, bk()));
+      g.a_mn = true;
+      g.a = MapSpec{P, rows, pitch, pitch};
+      g.b = MapSpec{Qt, D, strict ? r_pad + rows : rows, ld_qt};
+      g.M = Bk; g.N = D; g.seg_len = kr; g.k_blocks = kr;
+      if (strict) {                                  // P_hi^T Q_hi + P_lo^T Q_hi + P_hi^T Q_lo
+        g.k_blocks = 3 * kr; g.a_moff[1] = static_cast<int>(k_pad); g.b_seg[2] = static_cast<int>(r_pad / bk());
+      }
+      g.accumulate = r0 > 0;
+      g.out_f32 = ok_raw; g.ld_out = D;
+      MI_TRY(run_gemm(g, none, stream));
+      if (ev_after_k != nullptr && r0 + panel_rows >= Bq) MI_CUDA(cudaEventRecord(ev_after_k, stream));
+    }
+    // (3) Oq_raw[panel] = P~ K
+    {
+      GemmArgs g;
+      g.a = MapSpec{P, rows, pitch, pitch};
+      g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
+      g.M = rows; g.N = D; g.seg_len = kp; g.k_blocks = kp;
+      if (strict) {
+        g.k_blocks = 2 * kp; g.a_seg[1] = kp;
+        if (k_hl) { g.k_blocks = 3 * kp; g.b_seg[2] = kp; }
+      }
+      g.out_f32 = oq_raw + r0 * D; g.ld_out = D;
+      MI_TRY(run_gemm(g, none, stream));
+    }
+  }
+  return MI_OK;
+}
+
+__global__ void flag_to_loss_kernel(const int* __restrict__ flag, double* __restrict__ loss_out) { loss_out[7] = static_cast<double>(flag[0]); }
+
+bool g_single_pass = true;
+inline bool grads_or_plan_single(int estimator, int precision) {
+  return g_single_pass && estimator != MI_EST_INFONCE_SYM && (precision & MI_PREC_TWO_PASS) == 0;
+}
+
 int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, long long B, long long D,
                 int critic, int estimator, int precision, float inv_tau,
                 double* loss_out, float* dX, float* dY, float* dW, Bump& ws, cudaStream_t stream) {
@@ -733,7 +1001,10 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   const bool plan = ws.dry || grads;
   const bool sym = estimator == MI_EST_INFONCE_SYM;
   const bool dv_like = estimator == MI_EST_DV || estimator == MI_EST_INFONCE_REF;
-  const bool strict = precision == MI_PREC_BF16_STRICT;
+  const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
+  // one score computation instead of two (see single_pass_impl); the symmetric estimator needs column
+  // references and stays on the two-pass path, as does any call that asks for it (MI_PREC_TWO_PASS)
+  const bool single = grads_or_plan_single(estimator, precision) && (dX != nullptr || dY != nullptr || dW != nullptr || ws.dry);
   const int tsplit = (bilinear && strict) ? 2 : 1;        // T = X W kept as a hi/lo bf16 pair in strict mode
   const long long Dp = round_up(D, kSplitAlign);
   const long long ldT = tsplit == 2 ? 2 * Dp : D;
@@ -750,6 +1021,12 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   bf* dT16 = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(B) * ldT) : nullptr;
   bf* Xt = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(D) * b_pad) : nullptr;
   bf* dTt = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(D) * b_pad * tsplit) : nullptr;
+  float* sp_rho = single ? ws.take<float>(B) : nullptr;
+  float* sp_wrow = single ? ws.take<float>(B) : nullptr;
+  float* sp_lambda = single ? ws.take<float>(1) : nullptr;
+  int* sp_flag = single ? ws.take<int>(1) : nullptr;
+  float* sp_oq = (single && (bilinear || !dX)) ? ws.take<float>(static_cast<size_t>(B) * D) : nullptr;   // dot: dX doubles as the raw buffer
+  float* sp_ok = (single && !dY) ? ws.take<float>(static_cast<size_t>(B) * D) : nullptr;
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (!ws.dry && (!X || !Y || !sid || !loss_out || (bilinear && !W))) return MI_ERR_BAD_ARG;
 
@@ -765,6 +1042,36 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     MI_TRY(gemm_impl(Xo, Opnd{Wt, D, 1}, B, D, D, 1.f, 0.f, nullptr, 0, nullptr, 0, T, ldT, tsplit, 1, ws, stream));
     ws.release(mk);
   }
+  if (single) {
+    const int incl = dv_like ? 0 : 1;
+    const float gam = 1.f / static_cast<float>(B);
+    float* oq_raw = sp_oq ? sp_oq : dX;
+    float* ok_raw = dY ? dY : sp_ok;
+    MI_TRY(single_pass_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, precision, gam, nullptr,
+                            rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream));
+    ws.release(mk);
+    if (!ws.dry) {
+      stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(rows_r), static_cast<int>(B), scal_r);
+      MI_LAUNCH_CHECK("stats_reduce_kernel");
+      loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, nullptr, B, estimator, loss_out, lse_f);
+      MI_LAUNCH_CHECK("loss_finalize_kernel");
+      flag_to_loss_kernel<<<1, 1, 0, stream>>>(sp_flag, loss_out);
+      MI_LAUNCH_CHECK("flag_to_loss_kernel");
+      const long long n = B * D;
+      if (tsplit == 2) MI_CUDA(cudaMemsetAsync(dT16, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
+      // dT = inv_tau (c G~ Y - Y/B): fp32 (dot critic: this is dX) or the bf16 (hi/lo) operand of the dX / dW GEMMs
+      finalize_q_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(oq_raw, D, B, sp_rho, sp_wrow, lse_f, dv_like ? 1 : 0, inv_tau, gam,
+                                                                Y, D, 1, Dp, bilinear ? nullptr : dX, bilinear ? dT16 : nullptr,
+                                                                (bilinear && tsplit == 2) ? dT16 + Dp : nullptr, ldT);
+      MI_LAUNCH_CHECK("finalize_q_kernel");
+      if (dY) {
+        finalize_k_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(dY, D, B, sp_lambda, lse_f, dv_like ? 1 : 0, inv_tau, gam,
+                                                                  To.p, To.ld, To.split, Dp, 0, B);
+        MI_LAUNCH_CHECK("finalize_k_kernel");
+      }
+    }
+  }
+  if (!single || ws.dry) {        // (planning covers both paths)
   MI_TRY(stats_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
   ws.release(mk);
   if (sym) { MI_TRY(stats_impl(Yo, To, sid, sid, 0, B, B, D, inv_tau, rows_c, scal_c, ws, stream)); ws.release(mk); }
@@ -802,10 +1109,11 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   GradOut oq_none;
   if (want_q || want_k) {
     if (tsplit == 2 && !ws.dry) MI_CUDA(cudaMemsetAsync(dT16, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
-    MI_TRY(grad_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, refq, wq, refk, wk, incl_diag, precision,
+    MI_TRY(grad_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, refq, wq, refk, wk, incl_diag, precision & 1,
                      inv_tau, gamma, want_q ? oq : oq_none, want_k ? &okk : nullptr, ws, stream));
     ws.release(mk);
   }
+  }   // two-pass path
   if (bilinear) {
     const Opnd dTo{dT16, ldT, tsplit};
     // dX = dT W^T : B operand [N = d, K = e] is W itself
@@ -884,6 +1192,7 @@ int mi_profile_read(double* ms, int64_t* launches) {
   return MI_OK;
 }
 void mi_set_debug(int v) { g_debug = v; }
+void mi_set_single_pass(int on) { g_single_pass = on != 0; }
 void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
 int mi_get_cta_group(void) { return cta_group(); }
 
@@ -960,6 +1269,69 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
                    sid_q, sid_k, q_offset, Bq, Bk, D, scale, refq, wq, refk, wk, include_diag, precision,
                    alpha, gamma, oq, outk_f32 ? &ok : nullptr, ws, reinterpret_cast<cudaStream_t>(stream),
                    reinterpret_cast<cudaEvent_t>(event_after_outk));
+}
+
+size_t mi_score_single_pass_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision) {
+  Bump ws(nullptr, 0, true);
+  const int sp = (precision & 1) ? 2 : 1;
+  if (single_pass_impl(Opnd{nullptr, D, sp}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, Bk, D, 1.f, 0, precision, 1.f, nullptr,
+                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_row_norm_max(const void* A, int64_t lda, int a_split, int64_t rows, int64_t D, float* norm_out, float* max_out, mi_stream_t stream_) {
+  MI_TRY(device_check());
+  if (!A || !norm_out || !max_out || rows <= 0 || D <= 0) return MI_ERR_BAD_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  row_norm_kernel<<<blocks_for(rows * 32, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda, a_split == 2 ? 2 : 1,
+                                                                   round_up(D, kSplitAlign), rows, D, norm_out);
+  MI_LAUNCH_CHECK("row_norm_kernel");
+  max_reduce_kernel<<<1, 1024, 0, stream>>>(norm_out, rows, max_out);
+  MI_LAUNCH_CHECK("max_reduce_kernel");
+  return MI_OK;
+}
+int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
+                         const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                         int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag, int precision, float inv_bg,
+                         const float* qnorm_max_in, float* row_out, double* scal_out, float* oq_raw, float* ok_raw,
+                         float* rho, float* wrow, float* lambda_out, int32_t* flag_out, void* event_after_outk,
+                         void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
+  MI_TRY(device_check());
+  if (q_offset < 0 || q_offset + Bq > Bk || !scal_out) return MI_ERR_BAD_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Bump ws(workspace, workspace_bytes, false);
+  MI_TRY(single_pass_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
+                          Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
+                          sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, precision, inv_bg, qnorm_max_in,
+                          row_out, oq_raw, ok_raw, rho, wrow, lambda_out, flag_out, ws, stream,
+                          reinterpret_cast<cudaEvent_t>(event_after_outk)));
+  stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out);
+  MI_LAUNCH_CHECK("stats_reduce_kernel");
+  return MI_OK;
+}
+int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const float* rho, const float* wrow, const float* lse,
+                         int dv_like, float alpha, float gamma, const void* kdiag, int64_t ldk, int k_split,
+                         float* out_f32, void* out_bf16, int64_t ld16, int out_split, mi_stream_t stream_) {
+  MI_TRY(device_check());
+  if (!oq_raw || !rho || !wrow || !kdiag || rows <= 0 || D <= 0 || (dv_like && !lse) || (!out_f32 && !out_bf16)) return MI_ERR_BAD_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long Dp = round_up(D, kSplitAlign);
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  finalize_q_kernel<<<blocks_for(rows * D, 256), 256, 0, stream>>>(oq_raw, D, rows, rho, wrow, lse, dv_like, alpha, gamma,
+                                                                   static_cast<const __nv_bfloat16*>(kdiag), ldk, k_split == 2 ? 2 : 1, Dp,
+                                                                   out_f32, ob, (ob && out_split == 2) ? ob + Dp : nullptr, ld16);
+  MI_LAUNCH_CHECK("finalize_q_kernel");
+  return MI_OK;
+}
+int mi_single_finalize_k(float* ok, int64_t rows, int64_t D, const float* lambda, const float* lse, int dv_like,
+                         float alpha, float gamma, const void* qdiag, int64_t ldq, int q_split, mi_stream_t stream_) {
+  MI_TRY(device_check());
+  if (!ok || !qdiag || rows <= 0 || D <= 0 || (dv_like && (!lse || !lambda))) return MI_ERR_BAD_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  finalize_k_kernel<<<blocks_for(rows * D, 256), 256, 0, stream>>>(ok, D, rows, lambda, lse, dv_like, alpha, gamma,
+                                                                   static_cast<const __nv_bfloat16*>(qdiag), ldq, q_split == 2 ? 2 : 1,
+                                                                   round_up(D, kSplitAlign), 0, rows);
+  MI_LAUNCH_CHECK("finalize_k_kernel");
+  return MI_OK;
 }
 
 size_t mi_critic_workspace_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads) {

@@ -85,9 +85,73 @@ def _gather_mat(m, world, group):
     return _all_gather_rows(m, world, group)
 
 
+def _loss_from(out, estimator):
+    if estimator == "dv":
+        # mi_critics.py:10 rounds N_neg to fp32 before the log; same formula as the fused C path
+        log_n = torch.log(out["n_neg"].to(torch.float32).to(torch.float64))
+        return out["lse_neg"] - log_n - out["pos_mean"]
+    if estimator in ("infonce", "infonce_ref"):
+        return out["lse_neg"] - out["pos_mean"]
+    if estimator == "infonce_row":
+        return out["loss_row"]
+    raise ValueError(f"unknown estimator {estimator!r}")
+
+
+def _reduce_scatter_rows(part, Bl, off, world, group, nccl, ev):
+    """Sum the [Bg, D] per-rank contributions and keep this rank's rows.  With NCCL the collective starts on a
+    side stream as soon as `ev` fires and runs under the work still queued on the compute stream."""
+    if world == 1:
+        return part, None
+    if not nccl:                                      # gloo (CPU tests) has no reduce-scatter
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+        return part[off:off + Bl].contiguous(), None
+    side = _side_stream(part.device)
+    side.wait_event(ev)
+    out = torch.empty((Bl, part.shape[1]), dtype=part.dtype, device=part.device)
+    with torch.cuda.stream(side):
+        work = dist.reduce_scatter_tensor(out, part, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    part.record_stream(side)
+    out.record_stream(side)
+    return out, work
+
+
+def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
+                      precision, qmax, world, group, nccl):
+    """dv / infonce / row InfoNCE with ONE score computation per rank (see mi_score_single_pass)."""
+    bilinear = Wb is not None
+    strict = precision == "strict"
+    dv_like = estimator != "infonce_row"
+    gamma = 1.0 / Bg
+    ev = None
+    if nccl:
+        ev = torch.cuda.Event()
+        ev.record()
+    sp = backend.score_single_pass(T_local, Y_all, sid_loc, sid_all, off, inv_tau, not dv_like, precision, gamma,
+                                   qmax=qmax, want_k=True, event_after_k=ev)
+    dY, rs_work = _reduce_scatter_rows(sp["ok_raw"], Bl, off, world, group, nccl, ev)
+    g = merge_scalars(_all_gather_rows(sp["scal"].reshape(1, 8), world, group))
+    out = {"pos_mean": g["diag_sum"] / Bg, "lse_neg": g["lse_neg"], "n_neg": g["n_neg"], "loss_row": g["rowloss_sum"] / Bg,
+           "loose_reference_rows": sp["flag"]}
+    out["loss"] = _loss_from(out, estimator)
+    lse32 = out["lse_neg"].to(torch.float32).reshape(1)
+    dT32, dT16 = backend.single_finalize_q(sp["oq_raw"], sp["rho"], sp["wrow"], lse32, dv_like, inv_tau, gamma, Yb,
+                                           want_f32=not bilinear, want_bf16=bilinear, out_split=bilinear and strict)
+    dX, dW = dT32, None
+    if bilinear:
+        dX = backend.gemm(dT16, Wb)
+        dW = backend.gemm(backend.transpose(Xb), backend.transpose(dT16))
+        if world > 1:
+            dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group)
+    if rs_work is not None:
+        rs_work.wait()
+    backend.single_finalize_k(dY, sp["lam"], lse32, dv_like, inv_tau, gamma, T_local)
+    return out, dX, dY, dW
+
+
 def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W: Optional[torch.Tensor],
                                 sid_local: torch.Tensor, estimator: str = "dv", precision: str = "fast",
-                                inv_tau: float = 1.0, need_grads: bool = True, group=None, backend=None):
+                                inv_tau: float = 1.0, need_grads: bool = True, group=None, backend=None,
+                                two_pass: bool = False):
     """Returns (stats dict of 0-d fp64 tensors incl. 'loss', dX_local, dY_local, dW) — dW already
     summed over ranks.  All ranks must hold the same number of rows."""
     if backend is None:
@@ -110,6 +174,12 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         Y_all = torch.empty((Bg, D), dtype=Yb.dtype, device=Yb.device)
         y_work = dist.all_gather_into_tensor(Y_all, Yb, group=group, async_op=True)
     T_local = backend.gemm(Xb, backend.transpose(Wb), out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb
+    single = need_grads and not sym and not two_pass
+    qmax = None
+    if single:                                        # largest |T_i| over ALL ranks: the global constant of the bound
+        _, qmax = backend.row_norm_max(T_local)
+        if world > 1:
+            dist.all_reduce(qmax, op=dist.ReduceOp.MAX, group=group)
     if y_work is not None:
         y_work.wait()
     T_all = _gather_mat(T_local, world, group) if sym else None
@@ -118,6 +188,11 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     else:                                                        # identical on every rank, no host sync
         sid_all = dense_labels(_all_gather_rows(sid_local.to(torch.int64), world, group))
     sid_loc = sid_all[off:off + Bl].contiguous()
+
+    nccl = world > 1 and dist.get_backend(group) != "gloo"
+    if single:
+        return _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
+                                 precision, qmax, world, group, nccl)
 
     # ---- statistics (S never materialised)
     rows_r, scal_r = backend.score_stats(T_local, Y_all, sid_loc, sid_all, off, inv_tau)
@@ -154,7 +229,6 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         args = dict(refq=rows_r[:, 3].contiguous(), wq=0.5 / Bg, refk=c_all, wk=0.5 / Bg, include_diag=True)
     else:
         args = dict(refq=rows_r[:, 3].contiguous(), wq=1.0 / Bg, refk=None, wk=0.0, include_diag=True)
-    nccl = world > 1 and dist.get_backend(group) != "gloo"
     ev = None
     if nccl:                                          # marks "dY contributions complete" inside the fused pass
         ev = torch.cuda.Event()

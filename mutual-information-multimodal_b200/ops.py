@@ -229,11 +229,83 @@ def score_grad(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
     return o32, o16, okk
 
 
+def row_norm_max(A: Mat) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(|A_i| per row, max_i |A_i| as a 1-element tensor) — the ingredients of the single-pass score bound."""
+    _need_cuda(A)
+    At, lda, asp, D = _opnd(A)
+    rows = At.shape[0]
+    norms = torch.empty(rows, dtype=torch.float32, device=At.device)
+    mx = torch.empty(1, dtype=torch.float32, device=At.device)
+    _check(_lib.load().mi_row_norm_max(_ptr(At), lda, asp, rows, D, _ptr(norms), _ptr(mx), _stream()), "mi_row_norm_max")
+    return norms, mx
+
+
+def score_single_pass(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float, include_diag: bool, precision: str,
+                      inv_bg: float, qmax: Optional[torch.Tensor] = None, want_k: bool = True,
+                      event_after_k: Optional["torch.cuda.Event"] = None) -> dict:
+    """mi_score_single_pass: statistics and raw gradient contractions from ONE score computation."""
+    _need_cuda(Q, K, sid_q, sid_k, qmax)
+    lib = _lib.load()
+    Qt, ldq, qsp, D = _opnd(Q)
+    Kt, ldk, ksp, Dk = _opnd(K)
+    assert D == Dk
+    sid_q, sid_k = sid_q.to(torch.int32).contiguous(), sid_k.to(torch.int32).contiguous()
+    Bq, Bk = Qt.shape[0], Kt.shape[0]
+    dev = Qt.device
+    prec = PRECISION[precision]
+    f32 = dict(dtype=torch.float32, device=dev)
+    r = {"rows": torch.empty((Bq, 4), **f32), "scal": torch.empty(8, dtype=torch.float64, device=dev),
+         "oq_raw": torch.empty((Bq, D), **f32), "ok_raw": torch.empty((Bk, D), **f32) if want_k else None,
+         "rho": torch.empty(Bq, **f32), "wrow": torch.empty(Bq, **f32), "lam": torch.empty(1, **f32),
+         "flag": torch.empty(1, dtype=torch.int32, device=dev)}
+    ws = workspace(lib.mi_score_single_pass_workspace_bytes(Bq, Bk, D, prec), dev)
+    _check(lib.mi_score_single_pass(_ptr(Qt), ldq, qsp, _ptr(Kt), ldk, ksp, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D,
+                                    scale, int(include_diag), prec, inv_bg, _ptr(qmax), _ptr(r["rows"]), _ptr(r["scal"]),
+                                    _ptr(r["oq_raw"]), _ptr(r["ok_raw"]), _ptr(r["rho"]), _ptr(r["wrow"]), _ptr(r["lam"]),
+                                    _ptr(r["flag"]),
+                                    None if event_after_k is None else C.c_void_p(event_after_k.cuda_event),
+                                    _ptr(ws), ws.numel(), _stream()), "mi_score_single_pass")
+    return r
+
+
+def single_finalize_q(oq_raw, rho, wrow, lse, dv_like: bool, alpha: float, gamma: float, kdiag: Mat,
+                      want_f32: bool = True, want_bf16: bool = False, out_split: bool = False):
+    """Oq = alpha (c_q oq_raw - gamma Kdiag): fp32 and/or bf16 (hi/lo) result."""
+    Kt, ldk, ksp, D = _opnd(kdiag)
+    rows = oq_raw.shape[0]
+    dev = oq_raw.device
+    o32 = torch.empty((rows, D), dtype=torch.float32, device=dev) if want_f32 else None
+    o16 = ob = None
+    ld16 = 0
+    if want_bf16:
+        if out_split:
+            o16 = new_split(rows, D, dev)
+            ob, ld16 = o16.data, o16.data.stride(0)
+        else:
+            o16 = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
+            ob, ld16 = o16, D
+    _check(_lib.load().mi_single_finalize_q(_ptr(oq_raw), rows, D, _ptr(rho), _ptr(wrow), _ptr(lse), int(dv_like), alpha, gamma,
+                                            _ptr(Kt), ldk, ksp, _ptr(o32), _ptr(ob), ld16, 2 if out_split else 1, _stream()),
+           "mi_single_finalize_q")
+    return o32, o16
+
+
+def single_finalize_k(ok, lam, lse, dv_like: bool, alpha: float, gamma: float, qdiag: Mat) -> torch.Tensor:
+    """Ok = alpha (kappa ok - gamma Qdiag), in place; rows of ok and qdiag correspond one to one."""
+    Qt, ldq, qsp, D = _opnd(qdiag)
+    _check(_lib.load().mi_single_finalize_k(_ptr(ok), ok.shape[0], D, _ptr(lam), _ptr(lse), int(dv_like), alpha, gamma,
+                                            _ptr(Qt), ldq, qsp, _stream()), "mi_single_finalize_k")
+    return ok
+
+
 def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tensor], sid: torch.Tensor,
                         estimator: str = "dv", precision: str = "fast", inv_tau: float = 1.0,
-                        need_grads: bool = True, out=None):
+                        need_grads: bool = True, out=None, two_pass: bool = False):
     """The whole path on one GPU (mi_critic_loss_fwd_bwd).  Returns (loss_out fp64[8], dX, dY, dW).
-    ``out`` = (loss, dX, dY, dW) reuses caller-owned result buffers (no allocation in the call)."""
+    ``out`` = (loss, dX, dY, dW) reuses caller-owned result buffers (no allocation in the call).
+    ``two_pass`` forces the statistics-pass + gradient-pass path (MI_PREC_TWO_PASS); by default dv / infonce /
+    infonce_row take the single pass with a Cauchy-Schwarz score bound as reference — loss_out[7] counts the
+    rows for which that bound was too loose (must be 0, else repeat with two_pass=True)."""
     _need_cuda(X, Y, W, sid)
     lib = _lib.load()
     X, Y = as_bf16(X), as_bf16(Y)
@@ -241,7 +313,7 @@ def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tens
     sid = sid.to(torch.int32).contiguous()
     B, D = X.shape
     critic = 1 if W is not None else 0
-    est, prec = ESTIMATOR[estimator], PRECISION[precision]
+    est, prec = ESTIMATOR[estimator], PRECISION[precision] | (2 if two_pass else 0)
     dX = dY = dW = None
     if out is not None:
         loss, dX, dY, dW = out

@@ -63,3 +63,53 @@ def score_grad(Q, K, sid_q, sid_k, q_offset, scale, refq, wq, refk, wk, include_
         Ok[j] -= gamma * Q.double()
         Ok = alpha * Ok
     return (Oq if want_f32 else None), (Oq if want_bf16 else None), Ok
+
+
+def row_norm_max(A):
+    n = A.double().norm(dim=1)
+    return n, n.max().reshape(1)
+
+
+def score_single_pass(Q, K, sid_q, sid_k, q_offset, scale, include_diag, precision, inv_bg, qmax=None, want_k=True,
+                      event_after_k=None):
+    S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
+    qn, kn = Q.double().norm(dim=1), K.double().norm(dim=1)
+    rho = scale * qn * kn.max() * 1.001 + 1e-3
+    lam = (scale * (qn.max() if qmax is None else qmax.double().reshape(())) * kn.max() * 1.001 + 1e-3).reshape(1)
+    incl = M.clone()
+    if include_diag:
+        incl[i, j] = True
+    P = torch.where(incl, torch.exp(S - rho[:, None]), torch.zeros_like(S))
+    l = P.sum(1)
+    diag = S[i, j]
+    n_neg = M.sum(1).double()
+    if include_diag:
+        lse_all = rho + torch.log(l)
+        lse_neg = torch.logsumexp(torch.where(M, S, torch.full_like(S, float("-inf"))), 1)
+        wrow = inv_bg / l
+    else:
+        lse_neg = rho + torch.log(l)
+        lse_all = torch.logaddexp(lse_neg, diag)
+        wrow = torch.exp(rho - lam)
+    rows = torch.stack([lse_neg, n_neg, diag, lse_all], 1)
+    m = lse_neg.max()
+    scal = torch.zeros(8, dtype=torch.float64)
+    scal[0] = m
+    scal[1] = torch.exp(lse_neg[torch.isfinite(lse_neg)] - m).sum()
+    scal[2] = n_neg.sum()
+    scal[3] = diag.sum()
+    scal[4] = (lse_all - diag).sum()
+    return {"rows": rows, "scal": scal, "oq_raw": P @ K.double(), "ok_raw": (P * wrow[:, None]).t() @ Q.double(),
+            "rho": rho, "wrow": wrow, "lam": lam, "flag": torch.zeros(1, dtype=torch.int32)}
+
+
+def single_finalize_q(oq_raw, rho, wrow, lse, dv_like, alpha, gamma, kdiag, want_f32=True, want_bf16=False, out_split=False):
+    c = torch.exp(rho - lse.double()) if dv_like else wrow
+    O = alpha * (c[:, None] * oq_raw - gamma * kdiag.double())
+    return (O if want_f32 else None), (O if want_bf16 else None)
+
+
+def single_finalize_k(ok, lam, lse, dv_like, alpha, gamma, qdiag):
+    kappa = torch.exp(lam.double() - lse.double()) if dv_like else 1.0
+    ok.copy_(alpha * (kappa * ok - gamma * qdiag.double()))
+    return ok

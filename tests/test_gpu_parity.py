@@ -181,18 +181,48 @@ def test_stage_ops_with_offsets(env):
 
 
 def test_sharded_composition_world1_equals_fused_call(env):
+    """The stage-level composition used by the multi-GPU path (world 1 here) against the fused C call, in both
+    its forms: single pass (Cauchy-Schwarz reference) and two pass (exact log-sum-exp references)."""
     mi_b200, ops, mo, dev = env
     from mi_b200 import dist as mdist
     B, D = 520, 136
     X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=4, dup_frac=0.1)
     Xd, Yd, Wd, sd = X.bfloat16().to(dev), Y.bfloat16().to(dev), W.bfloat16().to(dev), sid.to(dev)
+    ref = {}
     for est in ("dv", "infonce", "infonce_row", "infonce_sym"):
-        out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xd, Yd, Wd, sd, est, "fast", 1.0, True)
-        lo, fX, fY, fW = ops.critic_loss_fwd_bwd(Xd, Yd, Wd, sd.to(torch.int32), est, "fast", 1.0, True)
-        torch.cuda.synchronize()
-        assert abs(float(out["loss"]) - float(lo[0])) < 1e-9 * max(1.0, abs(float(lo[0])))
-        assert torch.equal(dX, fX) and torch.equal(dY, fY)
-        assert _rel(dW, fW.cpu()) < 1e-5          # split-K order differs
+        ref[est] = mo.critic_loss(X.bfloat16().float(), Y.bfloat16().float(), sid, W.bfloat16().float(), 1.0, est)
+        for two_pass in (False, True):
+            out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xd, Yd, Wd, sd, est, "strict", 1.0, True, two_pass=two_pass)
+            lo, fX, fY, fW = ops.critic_loss_fwd_bwd(Xd, Yd, Wd, sd.to(torch.int32), est, "strict", 1.0, True, two_pass=two_pass)
+            torch.cuda.synchronize()
+            assert float(lo[7]) == 0.0 and abs(float(out["loss"]) - float(lo[0])) < 1e-6 * max(1.0, abs(float(lo[0])))
+            for a, b in ((dX, fX), (dY, fY), (dW, fW)):
+                assert _rel(a, b.cpu()) < 1e-4
+            assert _loss_rel(out["loss"], ref[est]["loss"]) < 1e-4
+            assert _rel(dX, ref[est]["dX"]) < 1e-3 and _rel(dY, ref[est]["dY"]) < 1e-3 and _rel(dW, ref[est]["dW"]) < 1e-3
+
+
+def test_single_pass_reference_guard(env):
+    """Rows whose Cauchy-Schwarz bound is far above all of their scores (here: an image embedding that is
+    orthogonal to every text embedding but has a huge norm) must be reported (loss_out[7] > 0) and the adapter
+    must fall back to the exact two-pass path."""
+    mi_b200, ops, mo, dev = env
+    B, D = 256, 64
+    g = torch.Generator().manual_seed(3)
+    Y = torch.zeros(B, D)
+    Y[:, : D // 2] = torch.randn(B, D // 2, generator=g)
+    X = torch.zeros(B, D)
+    X[:, : D // 2] = torch.randn(B, D // 2, generator=g)
+    X[7, :] = 0.0
+    X[7, D // 2:] = 40.0                                  # |X_7| large, <X_7, Y_j> = 0 for all j: bound ~ 1e3, scores 0
+    Xb, Yb = X.bfloat16().float(), Y.bfloat16().float()
+    sid = torch.arange(B)
+    out, *_ = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), None, sid.to(dev), "dv", "strict", 1.0, True)
+    assert float(out[7]) >= 1.0
+    ref = mo.critic_loss(Xb, Yb, sid, None, 1.0, "dv")
+    loss, dX, dY, _ = _run_adapter(mi_b200, dev, Xb, Yb, None, list(range(B)), 1.0, "dv", "strict")
+    assert _loss_rel(loss.sum().item(), ref["loss"]) < 1e-4
+    assert _rel(dX, ref["dX"]) < 1e-3 and _rel(dY, ref["dY"]) < 1e-3
 
 
 def test_sharded_autograd_loss_world1(env):
