@@ -327,7 +327,7 @@ def run_ours(a):
 
     pk = peaks()
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # written from the latest ncu --set full capture
     if os.path.isfile(tpath):
         tj = json.load(open(tpath))
         c = tj["config"]
@@ -339,11 +339,13 @@ def run_ours(a):
     strict = a.precision == "strict"
     # executed tensor flops: statistics pass(es) 2 B^2 D each, one score recompute 2 B^2 D, two dS x operand
     # contractions 2 B^2 D each; strict mode adds the hi/lo segments of T and of the dS panel
+    # (the single-pass path — every estimator but the symmetric one — computes the scores once: no statistics pass)
+    n_stats = 2 if sym else 0
     if strict:
         s_mult = 2.0 if bilinear else 1.0
-        f_exec = ((2 + (2 if sym else 0)) * s_mult + 2 * s_mult + 2 * 2 + 2 * (3 if bilinear else 2)) * float(B) * B * D
+        f_exec = (n_stats * s_mult + 2 * s_mult + 2 * 2 + 2 * (3 if (bilinear or not sym) else 2)) * float(B) * B * D
     else:
-        f_exec = ((2 + (2 if sym else 0)) + 2 + 4) * float(B) * B * D
+        f_exec = (n_stats + 2 + 4) * float(B) * B * D
     f_exec += (6.0 * B * D * D if bilinear else 0.0)
     ach = f_alg / (ms_per_step * 1e-3) / 1e12 / world           # per GPU
     kinds = ["score_stats", "ds_panel", "gemm"]

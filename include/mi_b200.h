@@ -172,6 +172,8 @@ int mi_profile_read(double* ms /*[3]*/, int64_t* launches /*[3]*/);
 void mi_set_cta_group(int group);
 void mi_set_debug(int value);          /* experiments only */
 void mi_set_single_pass(int on);       /* 0: mi_critic_loss_fwd_bwd always takes the two-pass path */
+void mi_set_mn_operands(int on);       /* 0: transpose row-major [K,N] operands into K-major copies instead of reading
+                                          them in place through MN-major UMMA descriptors (default 1) */
 int mi_get_cta_group(void);
 
 #ifdef __cplusplus

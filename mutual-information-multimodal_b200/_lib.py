@@ -21,6 +21,7 @@ PROTOTYPES = {
     "mi_set_cta_group": (None, [c_int]),
     "mi_set_debug": (None, [c_int]),
     "mi_set_single_pass": (None, [c_int]),
+    "mi_set_mn_operands": (None, [c_int]),
     "mi_get_cta_group": (c_int, []),
     "mi_gemm_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_i64,
                              c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),

@@ -63,6 +63,7 @@ struct Sched {
   int a_seg[4];
   int b_seg[4];
   int a_moff[4];  // MN-major A only: M-coordinate offset of the segment (e.g. the lo half of a [hi | lo] panel)
+  int b_noff[4];  // MN-major B only: N-coordinate offset of the segment
 };
 
 struct Unit { int m, s, ks, nt0, nt1, kb0, kb1; };
@@ -90,7 +91,8 @@ __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
 // of a row-major [K, M] matrix).  Its 128(M) x kBK(K) tile is fetched as 64(K) x 64(M) boxes — for each
 // 64-wide M half the K rows are contiguous — and described to the MMA with the MN-major SWIZZLE_128B
 // canonical layout (LBO = bytes between the M halves, SBO = 1 KB between 8-row K groups).
-template <int kCG, class Epi, bool kAMN>
+// kBMN: the same for the B operand (B[n,k] at base[k*ld + n]): per 64-wide N group the K rows are contiguous.
+template <int kCG, class Epi, bool kAMN, bool kBMN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const Sched sc, const typename Epi::Params ep) {
@@ -151,6 +153,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         int seg = un.kb0 / sc.seg_len, w = un.kb0 - seg * sc.seg_len;
         int a_k = (sel4(sc.a_seg, seg) + w) * C::kBK, b_k = (sel4(sc.b_seg, seg) + w) * C::kBK;
         int a_m = a_row + sel4(sc.a_moff, seg);
+        int b_n = b_row + sel4(sc.b_noff, seg);
         for (int kb = un.kb0; kb < un.kb1; ++kb) {
           ptx::mbar_wait_addr(empty0 + stage * 8u, phase ^ 1u, 1);
           if (lane == 0) {
@@ -167,7 +170,13 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               } else {
                 ptx::tma_load_2d_addr<kCG>(sa + t * C::kAAtomBytes, ta, bar, a_k + t * ATOM_K, a_row);
               }
-              ptx::tma_load_2d_addr<kCG>(sb + t * C::kBAtomBytes, tb, bar, b_k + t * ATOM_K, b_row);
+              if constexpr (kBMN) {
+#pragma unroll
+                for (int h = 0; h < C::kBRows / 64; ++h)
+                  ptx::tma_load_2d_addr<kCG>(sb + h * (C::kBK * 128) + t * (ATOM_K * 128), tb, bar, b_n + 64 * h, b_k + t * ATOM_K);
+              } else {
+                ptx::tma_load_2d_addr<kCG>(sb + t * C::kBAtomBytes, tb, bar, b_k + t * ATOM_K, b_row);
+              }
             }
           }
           __syncwarp();
@@ -175,6 +184,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (++w == sc.seg_len) {
             w = 0; ++seg;
             a_k = sel4(sc.a_seg, seg) * C::kBK; b_k = sel4(sc.b_seg, seg) * C::kBK; a_m = a_row + sel4(sc.a_moff, seg);
+            b_n = b_row + sel4(sc.b_noff, seg);
           }
           if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -183,12 +193,12 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (leader) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * kCG, TILE_N) | (kAMN ? (1u << 15) : 0u);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * kCG, TILE_N) | (kAMN ? (1u << 15) : 0u) | (kBMN ? (1u << 16) : 0u);
       const uint32_t tfull0 = ptx::smem_u32(&tmem_full_bar[0]);
       const uint32_t tempty0 = ptx::smem_u32(&tmem_empty_bar[0]);
       // descriptor templates (everything but the 14-bit start address)
       const uint64_t da_hi = kAMN ? ptx::make_smem_desc_mn128(0, C::kABytes / 2) : ptx::make_smem_desc_k128(0);
-      const uint64_t db_hi = ptx::make_smem_desc_k128(0);
+      const uint64_t db_hi = kBMN ? ptx::make_smem_desc_mn128(0, C::kBK * 128) : ptx::make_smem_desc_k128(0);
       uint32_t stage = 0, phase = 0, tile_cnt = 0;
       for (int u = pair_id; u < n_units; u += n_pairs) {
         const Unit un = decode_unit(sc, u);
@@ -211,7 +221,8 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 // MN-major: 16 K rows = two 1 KB swizzle atoms (+128)
                 const uint32_t a_adv = kAMN ? (uint32_t)(128 * k)
                                             : (uint32_t)((k / 4) * (C::kAAtomBytes >> 4) + (k % 4) * 2);
-                const uint32_t b_adv = (uint32_t)((k / 4) * (C::kBAtomBytes >> 4) + (k % 4) * 2);
+                const uint32_t b_adv = kBMN ? (uint32_t)(128 * k)
+                                            : (uint32_t)((k / 4) * (C::kBAtomBytes >> 4) + (k % 4) * 2);
                 ptx::umma_bf16<kCG>(d_tmem, da + a_adv, db + b_adv, idesc, (k == 0) ? acc : 1u);
               }
               ptx::umma_commit_addr<kCG>(empty0 + stage * 8u, 0x3);   // smem slot reusable once these MMAs retire

@@ -2,6 +2,7 @@
 // include/mi_b200.h.  The tensor-core work is in engine.cuh (tcgen05 / TMEM / TMA, sm_100a only).
 // There is no CPU path: every entry point fails with MI_ERR_NO_DEVICE / MI_ERR_CUDA when no
 // Blackwell device is available.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <mutex>
@@ -22,6 +23,7 @@ thread_local char g_cuda_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_debug = 0;
 int g_cta_group = -1;   // resolved lazily: env MI_CTA_GROUP or 2
+bool g_mn_operands = true;   // read row-major [K, N] / [K, M] operands in place (MN-major descriptors) instead of transposing them
 
 // optional per-launch CUDA-event timing of the tile-engine kernels (bench.py's roofline breakdown)
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
@@ -131,15 +133,16 @@ struct MapSpec {          // a 2-D bf16 tensor map: `rows` x `k_extent` elements
   const void* ptr; long long rows, k_extent, ld;
 };
 
-template <int kCG, class Epi, bool kAMN>
+template <int kCG, class Epi, bool kAMN, bool kBMN>
 int launch_engine_cg(const MapSpec& a, const MapSpec& b, const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
   using C = mi::Cfg<kCG>;
   CUtensorMap ta, tb;
   // MN-major A: the map's contiguous dimension is M, its rows are K; fetched as 64 x 64 boxes
   if (kAMN) MI_TRY(make_tmap(&ta, a.ptr, a.rows, a.k_extent, a.ld, 64));
   else MI_TRY(make_tmap(&ta, a.ptr, a.rows, a.k_extent, a.ld, mi::BLOCK_M));
-  MI_TRY(make_tmap(&tb, b.ptr, b.rows, b.k_extent, b.ld, C::kBRows));
-  auto kern = mi::tile_engine_kernel<kCG, Epi, kAMN>;
+  if (kBMN) MI_TRY(make_tmap(&tb, b.ptr, b.rows, b.k_extent, b.ld, 64));
+  else MI_TRY(make_tmap(&tb, b.ptr, b.rows, b.k_extent, b.ld, C::kBRows));
+  auto kern = mi::tile_engine_kernel<kCG, Epi, kAMN, kBMN>;
   constexpr int smem = C::template smem_bytes<Epi>();
   static bool attr_set = false;
   if (!attr_set) {
@@ -180,10 +183,10 @@ template <> struct EpiKind<mi::EpiStats> { static constexpr int value = 0; };
 template <> struct EpiKind<mi::EpiPStore> { static constexpr int value = 1; };
 template <> struct EpiKind<mi::EpiStore> { static constexpr int value = 2; };
 
-template <class Epi, bool kAMN = false>
+template <class Epi, bool kAMN = false, bool kBMN = false>
 int launch_engine(const MapSpec& a, const MapSpec& b, const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
-  if (cta_group() == 1) return launch_engine_cg<1, Epi, kAMN>(a, b, sc, ep, stream);
-  return launch_engine_cg<2, Epi, kAMN>(a, b, sc, ep, stream);
+  if (cta_group() == 1) return launch_engine_cg<1, Epi, kAMN, kBMN>(a, b, sc, ep, stream);
+  return launch_engine_cg<2, Epi, kAMN, kBMN>(a, b, sc, ep, stream);
 }
 
 inline int rows_per_mblk() { return mi::BLOCK_M * cta_group(); }
@@ -208,7 +211,7 @@ int choose_split(int n_mblk, int n_ntile, int U) {
 
 void single_segment(Sched& sc) {
   sc.seg_len = sc.k_blocks;
-  for (int i = 0; i < 4; ++i) { sc.a_seg[i] = 0; sc.b_seg[i] = 0; sc.a_moff[i] = 0; }
+  for (int i = 0; i < 4; ++i) { sc.a_seg[i] = 0; sc.b_seg[i] = 0; sc.a_moff[i] = 0; sc.b_noff[i] = 0; }
 }
 
 // ------------------------------------------------------------------------------------ aux kernels
@@ -406,6 +409,27 @@ __global__ void transpose_scale_kernel(const __nv_bfloat16* __restrict__ in, lon
     }
   }
 }
+// out[r, c] = bf16(w[r] * in[r, c]) (+ residual half at out_lo), row-major: the MN-major B operand of P~^T (w Q)
+__global__ void scale_rows_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, int in_split, long long Dp,
+                                  const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo,
+                                  long long ld_out, long long R, long long C) {
+  const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2;
+  if (idx >= R * C) return;
+  const long long r = idx / C, c = idx - r * C;         // C is even (D % 8 == 0)
+  float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + r * ld_in + c));
+  if (in_split == 2) {
+    const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + r * ld_in + Dp + c));
+    v.x += l.x; v.y += l.y;
+  }
+  const float wr = w[r];
+  v.x *= wr; v.y *= wr;
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<__nv_bfloat162*>(out + r * ld_out + c) = h;
+  if (out_lo) {
+    const float2 hf = __bfloat1622float2(h);
+    *reinterpret_cast<__nv_bfloat162*>(out_lo + r * ld_out + c) = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
+  }
+}
 // Oq[i,:] = alpha (c_i Oraw[i,:] - gamma Kdiag[i,:]),  c_i = e^{rho_i - LSE} (DV) or wrow_i (row InfoNCE)
 __global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, long long rows, const float* __restrict__ rho,
                                   const float* __restrict__ wrow, const float* __restrict__ lse, int dv_like,
@@ -560,10 +584,11 @@ int score_segments(Sched& sc, const Opnd& q, const Opnd& k, long long D) {
 struct GemmArgs {
   MapSpec a, b;
   bool a_mn = false;          // A stored M-contiguous (transposed view of a row-major [K, M] matrix)
+  bool b_mn = false;          // B stored N-contiguous (a row-major [K, N] matrix used as it is)
   long long M = 0, N = 0;
   int k_blocks = 0;           // total K blocks (all segments)
   int seg_len = 0;            // 0: one segment
-  int a_seg[4] = {0, 0, 0, 0}, b_seg[4] = {0, 0, 0, 0}, a_moff[4] = {0, 0, 0, 0};
+  int a_seg[4] = {0, 0, 0, 0}, b_seg[4] = {0, 0, 0, 0}, a_moff[4] = {0, 0, 0, 0}, b_noff[4] = {0, 0, 0, 0};
   int ksplit = 1;
   float alpha = 1.f, gamma = 0.f;
   const __nv_bfloat16* sub = nullptr; const __nv_bfloat16* sub_lo = nullptr; long long ld_sub = 0;
@@ -585,7 +610,7 @@ int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
   single_segment(sc);
   if (g.seg_len > 0) {
     sc.seg_len = g.seg_len;
-    for (int i = 0; i < 4; ++i) { sc.a_seg[i] = g.a_seg[i]; sc.b_seg[i] = g.b_seg[i]; sc.a_moff[i] = g.a_moff[i]; }
+    for (int i = 0; i < 4; ++i) { sc.a_seg[i] = g.a_seg[i]; sc.b_seg[i] = g.b_seg[i]; sc.a_moff[i] = g.a_moff[i]; sc.b_noff[i] = g.b_noff[i]; }
   }
   float* partial = nullptr;
   if (sc.n_ksplit > 1) partial = ws.take<float>(static_cast<size_t>(sc.n_ksplit) * g.M * g.ld_out);
@@ -604,8 +629,10 @@ int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
   ep.sub_row0 = static_cast<int>(g.sub_row0); ep.sub_rows = static_cast<int>(g.sub_rows < 0 ? g.M : g.sub_rows);
   ep.ksplit_stride = static_cast<long long>(g.M) * g.ld_out;
   ep.accumulate = (!sk && g.accumulate) ? 1 : 0;
-  if (g.a_mn) MI_TRY((launch_engine<mi::EpiStore, true>(g.a, g.b, sc, ep, stream)));
-  else MI_TRY((launch_engine<mi::EpiStore, false>(g.a, g.b, sc, ep, stream)));
+  if (g.a_mn && g.b_mn) MI_TRY((launch_engine<mi::EpiStore, true, true>(g.a, g.b, sc, ep, stream)));
+  else if (g.a_mn) MI_TRY((launch_engine<mi::EpiStore, true, false>(g.a, g.b, sc, ep, stream)));
+  else if (g.b_mn) MI_TRY((launch_engine<mi::EpiStore, false, true>(g.a, g.b, sc, ep, stream)));
+  else MI_TRY((launch_engine<mi::EpiStore, false, false>(g.a, g.b, sc, ep, stream)));
   if (sk) {
     if (!g.out_f32 || g.sub || g.accumulate) return MI_ERR_BAD_ARG;
     const long long n = static_cast<long long>(g.M) * g.ld_out;
@@ -755,8 +782,9 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   const long long panel_rows = mb_panel * rows_per_mblk();
   const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
   float* refk2 = ws.take<float>(k_pad);
-  bf* Kt = ws.take<bf>(static_cast<size_t>(D) * ld_kt);
-  bf* Qt = ok ? ws.take<bf>(static_cast<size_t>(D) * ld_qt) : nullptr;
+  const bool mn = g_mn_operands;     // K and Q are read in place as MN-major B operands: no transposed copies
+  bf* Kt = (mn && !ws.dry) ? nullptr : ws.take<bf>(static_cast<size_t>(D) * ld_kt);
+  bf* Qt = (ok && !(mn && !ws.dry)) ? ws.take<bf>(static_cast<size_t>(D) * ld_qt) : nullptr;
   bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
@@ -770,13 +798,15 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     MI_LAUNCH_CHECK("make_refk2_kernel");
   }
   // V^T for the P K product (K-major B operand): [D, k_pad] (+ the lo half next to it in strict mode)
-  if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
-  MI_TRY(transpose_impl(K.p, K.ld, Kt, ld_kt, Bk, D, stream));
-  if (k_hl) MI_TRY(transpose_impl(K.p + Dp, K.ld, Kt + k_pad, ld_kt, Bk, D, stream));
-  if (ok) {
-    if (q_hl) MI_CUDA(cudaMemsetAsync(Qt, 0, static_cast<size_t>(D) * ld_qt * sizeof(bf), stream));
-    MI_TRY(transpose_impl(Q.p, Q.ld, Qt, ld_qt, Bq, D, stream));
-    if (q_hl) MI_TRY(transpose_impl(Q.p + Dp, Q.ld, Qt + q_pad, ld_qt, Bq, D, stream));
+  if (!mn) {
+    if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
+    MI_TRY(transpose_impl(K.p, K.ld, Kt, ld_kt, Bk, D, stream));
+    if (k_hl) MI_TRY(transpose_impl(K.p + Dp, K.ld, Kt + k_pad, ld_kt, Bk, D, stream));
+    if (ok) {
+      if (q_hl) MI_CUDA(cudaMemsetAsync(Qt, 0, static_cast<size_t>(D) * ld_qt * sizeof(bf), stream));
+      MI_TRY(transpose_impl(Q.p, Q.ld, Qt, ld_qt, Bq, D, stream));
+      if (q_hl) MI_TRY(transpose_impl(Q.p + Dp, Q.ld, Qt + q_pad, ld_qt, Bq, D, stream));
+    }
   }
   const Opnd Qe{Q.p, Q.ld, strict ? Q.split : 1}, Ke{K.p, K.ld, strict ? K.split : 1};
 
@@ -806,12 +836,16 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
       const int kr = static_cast<int>(cdiv(rows, bk()));
       g.a_mn = true;
       g.a = MapSpec{P, rows, pitch, pitch};            // map rows = K (panel rows), contiguous = M (columns of S)
-      g.b = MapSpec{Qt + r0, D, q_hl ? q_pad + (Bq - r0) : (Bq - r0), ld_qt};
+      if (mn) { g.b_mn = true; g.b = MapSpec{Q.p + r0 * Q.ld, rows, q_hl ? Dp + D : D, Q.ld}; }
+      else g.b = MapSpec{Qt + r0, D, q_hl ? q_pad + (Bq - r0) : (Bq - r0), ld_qt};
       g.M = Bk; g.N = D; g.seg_len = kr; g.k_blocks = kr;
       const int q_lo_blk = static_cast<int>(q_pad / bk());
       if (strict) {                                  // P_hi^T Q_hi + P_lo^T Q_hi (+ P_hi^T Q_lo)
         g.k_blocks = 2 * kr; g.a_moff[1] = static_cast<int>(k_pad);
-        if (q_hl) { g.k_blocks = 3 * kr; g.b_seg[2] = q_lo_blk; }
+        if (q_hl) {
+          g.k_blocks = 3 * kr;
+          if (mn) g.b_noff[2] = static_cast<int>(Dp); else g.b_seg[2] = q_lo_blk;
+        }
       }
       g.alpha = alpha; g.gamma = gamma;
       g.accumulate = r0 > 0;
@@ -829,11 +863,15 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     if (oq.f32 || oq.bf16) {
       GemmArgs g;
       g.a = MapSpec{P, rows, pitch, pitch};
-      g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
+      if (mn) { g.b_mn = true; g.b = MapSpec{K.p, Bk, k_hl ? Dp + D : D, K.ld}; }
+      else g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
       g.M = rows; g.N = D; g.seg_len = kp; g.k_blocks = kp;
       if (strict) {                                  // P_hi V_hi + P_lo V_hi (+ P_hi V_lo)
         g.k_blocks = 2 * kp; g.a_seg[1] = kp;
-        if (k_hl) { g.k_blocks = 3 * kp; g.b_seg[2] = kp; }
+        if (k_hl) {
+          g.k_blocks = 3 * kp;
+          if (mn) g.b_noff[2] = static_cast<int>(Dp); else g.b_seg[2] = kp;
+        }
       }
       g.alpha = alpha; g.gamma = gamma;
       if (gamma != 0.f) {                            // - gamma K[q_offset + q]
@@ -881,8 +919,11 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   const long long ld_qt = r_pad * (strict ? 2 : 1);
   const int max_split = n_ntile;
   const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
-  bf* Kt = ws.take<bf>(static_cast<size_t>(D) * ld_kt);
-  bf* Qt = ok_raw || ws.dry ? ws.take<bf>(static_cast<size_t>(D) * ld_qt) : nullptr;
+  const bool mn = g_mn_operands;     // K and w Q are read as row-major MN-major B operands: no transposed copies
+  const long long ld_qs = strict ? 2 * Dp : D;               // w Q [panel_rows, hi | lo]
+  bf* Kt = (mn && !ws.dry) ? nullptr : ws.take<bf>(static_cast<size_t>(D) * ld_kt);
+  const size_t qt_elems = std::max(static_cast<size_t>(D) * ld_qt, static_cast<size_t>(panel_rows) * ld_qs);   // either layout
+  bf* Qt = ok_raw || ws.dry ? ws.take<bf>(qt_elems) : nullptr;
   bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
   float* part = ws.take<float>(static_cast<size_t>(max_split > 64 ? 64 : max_split) * mi::kColQuarters * panel_rows);
   float* qnorm = ws.take<float>(Bq);
@@ -913,10 +954,12 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split, q_offset, Bq, D, Dp, scale, diag);
   MI_LAUNCH_CHECK("diag_kernel");
   // V^T for the P K product
-  if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
-  MI_TRY(transpose_impl(K.p, K.ld, Kt, ld_kt, Bk, D, stream));
-  if (k_hl) MI_TRY(transpose_impl(K.p + Dp, K.ld, Kt + k_pad, ld_kt, Bk, D, stream));
-  if (Qt && strict) MI_CUDA(cudaMemsetAsync(Qt, 0, static_cast<size_t>(D) * ld_qt * sizeof(bf), stream));
+  if (!mn) {
+    if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
+    MI_TRY(transpose_impl(K.p, K.ld, Kt, ld_kt, Bk, D, stream));
+    if (k_hl) MI_TRY(transpose_impl(K.p + Dp, K.ld, Kt + k_pad, ld_kt, Bk, D, stream));
+    if (Qt && strict) MI_CUDA(cudaMemsetAsync(Qt, 0, static_cast<size_t>(D) * ld_qt * sizeof(bf), stream));
+  }
 
   for (long long r0 = 0; r0 < Bq; r0 += panel_rows) {
     const long long rows = (Bq - r0 < panel_rows) ? (Bq - r0) : panel_rows;
@@ -947,18 +990,26 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
     Bump none(nullptr, 0, false);
     // (2) Ok_raw += P~^T (w Q)[panel]: contraction over the panel rows, P~ read MN-major
     if (ok_raw) {
-      dim3 tg(static_cast<unsigned>(cdiv(D, 64)), static_cast<unsigned>(cdiv(rows, 64)));
-      transpose_scale_kernel<<<tg, 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qt, strict ? Qt + r_pad : nullptr,
-                                                     ld_qt, rows, D);
-      MI_LAUNCH_CHECK("transpose_scale_kernel");
+      if (mn) {
+        scale_rows_kernel<<<blocks_for(rows * D / 2, 256), 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qt,
+                                                                            strict ? Qt + Dp : nullptr, ld_qs, rows, D);
+        MI_LAUNCH_CHECK("scale_rows_kernel");
+      } else {
+        dim3 tg(static_cast<unsigned>(cdiv(D, 64)), static_cast<unsigned>(cdiv(rows, 64)));
+        transpose_scale_kernel<<<tg, 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qt, strict ? Qt + r_pad : nullptr,
+                                                       ld_qt, rows, D);
+        MI_LAUNCH_CHECK("transpose_scale_kernel");
+      }
       GemmArgs g;
       const int kr = static_cast<int>(cdiv(rows, bk()));
       g.a_mn = true;
       g.a = MapSpec{P, rows, pitch, pitch};
-      g.b = MapSpec{Qt, D, strict ? r_pad + rows : rows, ld_qt};
+      if (mn) { g.b_mn = true; g.b = MapSpec{Qt, rows, strict ? Dp + D : D, ld_qs}; }
+      else g.b = MapSpec{Qt, D, strict ? r_pad + rows : rows, ld_qt};
       g.M = Bk; g.N = D; g.seg_len = kr; g.k_blocks = kr;
       if (strict) {                                  // P_hi^T Q_hi + P_lo^T Q_hi + P_hi^T Q_lo
-        g.k_blocks = 3 * kr; g.a_moff[1] = static_cast<int>(k_pad); g.b_seg[2] = static_cast<int>(r_pad / bk());
+        g.k_blocks = 3 * kr; g.a_moff[1] = static_cast<int>(k_pad);
+        if (mn) g.b_noff[2] = static_cast<int>(Dp); else g.b_seg[2] = static_cast<int>(r_pad / bk());
       }
       g.accumulate = r0 > 0;
       g.out_f32 = ok_raw; g.ld_out = D;
@@ -969,11 +1020,15 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
     {
       GemmArgs g;
       g.a = MapSpec{P, rows, pitch, pitch};
-      g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
+      if (mn) { g.b_mn = true; g.b = MapSpec{K.p, Bk, k_hl ? Dp + D : D, K.ld}; }
+      else g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
       g.M = rows; g.N = D; g.seg_len = kp; g.k_blocks = kp;
       if (strict) {
         g.k_blocks = 2 * kp; g.a_seg[1] = kp;
-        if (k_hl) { g.k_blocks = 3 * kp; g.b_seg[2] = kp; }
+        if (k_hl) {
+          g.k_blocks = 3 * kp;
+          if (mn) g.b_noff[2] = static_cast<int>(Dp); else g.b_seg[2] = kp;
+        }
       }
       g.out_f32 = oq_raw + r0 * D; g.ld_out = D;
       MI_TRY(run_gemm(g, none, stream));
@@ -1009,7 +1064,8 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   const long long Dp = round_up(D, kSplitAlign);
   const long long ldT = tsplit == 2 ? 2 * Dp : D;
   const long long b_pad = round_up(B, kSplitAlign);
-  bf* Wt = bilinear ? ws.take<bf>(static_cast<size_t>(D) * D) : nullptr;
+  const bool mn = g_mn_operands && !ws.dry;   // W, X and dT are read in place (MN-major descriptors); planning covers both
+  bf* Wt = (bilinear && !mn) ? ws.take<bf>(static_cast<size_t>(D) * D) : nullptr;
   bf* T = bilinear ? ws.take<bf>(static_cast<size_t>(B) * ldT) : nullptr;
   float* rows_r = ws.take<float>(static_cast<size_t>(B) * 4);
   float* rows_c = sym ? ws.take<float>(static_cast<size_t>(B) * 4) : nullptr;
@@ -1019,8 +1075,8 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   float* ref_r = ws.take<float>(B);
   float* ref_c = sym ? ws.take<float>(B) : nullptr;
   bf* dT16 = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(B) * ldT) : nullptr;
-  bf* Xt = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(D) * b_pad) : nullptr;
-  bf* dTt = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(D) * b_pad * tsplit) : nullptr;
+  bf* Xt = (bilinear && plan && !mn) ? ws.take<bf>(static_cast<size_t>(D) * b_pad) : nullptr;
+  bf* dTt = (bilinear && plan && !mn) ? ws.take<bf>(static_cast<size_t>(D) * b_pad * tsplit) : nullptr;
   float* sp_rho = single ? ws.take<float>(B) : nullptr;
   float* sp_wrow = single ? ws.take<float>(B) : nullptr;
   float* sp_lambda = single ? ws.take<float>(1) : nullptr;
@@ -1035,11 +1091,20 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   size_t mk = ws.mark();
   if (bilinear) {
     if (!ws.dry) {
-      MI_TRY(transpose_impl(W, D, Wt, D, D, D, stream));
+      if (!mn) MI_TRY(transpose_impl(W, D, Wt, D, D, D, stream));
       if (tsplit == 2) MI_CUDA(cudaMemsetAsync(T, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
     }
-    // T = X W  (B operand of the engine is [N, K] = W^T)
-    MI_TRY(gemm_impl(Xo, Opnd{Wt, D, 1}, B, D, D, 1.f, 0.f, nullptr, 0, nullptr, 0, T, ldT, tsplit, 1, ws, stream));
+    // T = X W  (B operand of the engine is [N, K] = W^T: W itself read MN-major, or the transposed copy)
+    if (mn) {
+      GemmArgs g;
+      g.a = MapSpec{X, B, D, D};
+      g.b_mn = true; g.b = MapSpec{W, D, D, D};
+      g.M = B; g.N = D; g.k_blocks = static_cast<int>(cdiv(D, bk()));
+      g.out_bf16 = T; g.ld_out16 = ldT; g.out_bf16_lo = tsplit == 2 ? T + Dp : nullptr;
+      MI_TRY(run_gemm(g, ws, stream));
+    } else {
+      MI_TRY(gemm_impl(Xo, Opnd{Wt, D, 1}, B, D, D, 1.f, 0.f, nullptr, 0, nullptr, 0, T, ldT, tsplit, 1, ws, stream));
+    }
     ws.release(mk);
   }
   if (single) {
@@ -1123,7 +1188,7 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     }
     // dW = X^T dT : A = X^T [D, B], B operand = dT^T [D, B] (hi | lo halves side by side), split-K over the batch
     if (dW || ws.dry) {
-      if (!ws.dry) {
+      if (!ws.dry && !mn) {
         MI_TRY(transpose_impl(X, D, Xt, b_pad, B, D, stream));
         if (tsplit == 2) MI_CUDA(cudaMemsetAsync(dTt, 0, static_cast<size_t>(D) * b_pad * tsplit * sizeof(bf), stream));
         MI_TRY(transpose_impl(dT16, ldT, dTt, b_pad * tsplit, B, D, stream));
@@ -1131,10 +1196,18 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
       }
       GemmArgs g;
       const int kb = static_cast<int>(b_pad / bk());
-      g.a = MapSpec{Xt, D, B, b_pad};
-      g.b = MapSpec{dTt, D, tsplit == 2 ? b_pad + B : B, b_pad * tsplit};
+      if (mn) {        // both operands are row-major [B, D] matrices contracted over their rows
+        g.a_mn = true; g.a = MapSpec{X, B, D, D};
+        g.b_mn = true; g.b = MapSpec{dT16, B, tsplit == 2 ? Dp + D : D, ldT};
+      } else {
+        g.a = MapSpec{Xt, D, B, b_pad};
+        g.b = MapSpec{dTt, D, tsplit == 2 ? b_pad + B : B, b_pad * tsplit};
+      }
       g.M = D; g.N = D; g.seg_len = kb; g.k_blocks = kb;
-      if (tsplit == 2) { g.k_blocks = 2 * kb; g.b_seg[1] = kb; }
+      if (tsplit == 2) {
+        g.k_blocks = 2 * kb;
+        if (mn) g.b_noff[1] = static_cast<int>(Dp); else g.b_seg[1] = kb;
+      }
       const long long tiles = cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N);
       long long ks = cdiv(num_pairs(), tiles);
       if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
@@ -1193,6 +1266,7 @@ int mi_profile_read(double* ms, int64_t* launches) {
 }
 void mi_set_debug(int v) { g_debug = v; }
 void mi_set_single_pass(int on) { g_single_pass = on != 0; }
+void mi_set_mn_operands(int on) { g_mn_operands = on != 0; }
 void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
 int mi_get_cta_group(void) { return cta_group(); }
 
