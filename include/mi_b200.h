@@ -159,6 +159,25 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
                                 double* loss_out_host, float* dX_host, float* dY_host, float* dW_host,
                                 void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream);
 
+/* ---- the reference's own critic: make_mlp(2D, [H1, H2]) on every pair ---------------- */
+
+/* Replaces, for the critic the reference ships (main_utils.py:77: mi_discriminator = make_mlp(1536, [1024, 512]),
+ * model.py:18-32), the sequence  create_mi_pairs -> mi_discriminator -> dv/infonce_bound_loss -> backward
+ * (main_utils.py:220-226) without building the [B + N_neg, 2D] pair tensor.  All tensors fp32, row-major, on the
+ * device, in nn.Linear layout:  W1 [H1, 2D] (columns [0,D) act on the image embedding, [D,2D) on the text
+ * embedding), b1 [H1], W2 [H2, H1], b2 [H2], W3 [1, H2], b3 [1].   D, H1, H2 multiples of 8, H2 <= 512.
+ * estimator: MI_EST_DV, MI_EST_INFONCE_REF or MI_EST_INFONCE_ROW.  precision: MI_PREC_BF16_FAST (bf16 operands of
+ * the tensor-core contractions, fp32 accumulate) or MI_PREC_BF16_STRICT (hi/lo bf16 pairs, 16 significant bits).
+ * loss_out (fp64[8]) as mi_critic_loss_fwd_bwd.  S_out (optional, [B, B]) receives the logit of EVERY pair
+ * (S[i,j] = mlp([x_i ; y_j]); the reference's logits are its diagonal followed by its negatives in gap-major
+ * order).  Every gradient pointer may be NULL; all NULL = forward only. */
+size_t mi_mlp_critic_workspace_bytes(int64_t B, int64_t D, int64_t H1, int64_t H2, int precision);
+int mi_mlp_critic_loss_fwd_bwd(const float* X, const float* Y, const float* W1, const float* b1, const float* W2, const float* b2,
+                               const float* W3, const float* b3, const int32_t* sid,
+                               int64_t B, int64_t D, int64_t H1, int64_t H2, int estimator, int precision,
+                               double* loss_out, float* S_out, float* dX, float* dY, float* dW1, float* db1, float* dW2, float* db2,
+                               float* dW3, float* db3, void* workspace, size_t workspace_bytes, mi_stream_t stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t mi_launch_count(void);
 
@@ -170,6 +189,7 @@ int mi_profile_read(double* ms /*[3]*/, int64_t* launches /*[3]*/);
 /* bring-up / A-B knob: 2 (default) = CTA pairs, cta_group::2 MMAs with M = 256; 1 = single-CTA M = 128.
  * Also settable through the environment variable MI_CTA_GROUP before the first call. */
 void mi_set_cta_group(int group);
+void mi_set_mlp_panel_pairs(int64_t pairs); /* pairs per row panel of the MLP-critic path (default 2^19; tests use small values) */
 void mi_set_debug(int value);          /* experiments only */
 void mi_set_single_pass(int on);       /* 0: mi_critic_loss_fwd_bwd always takes the two-pass path */
 void mi_set_mn_operands(int on);       /* 0: transpose row-major [K,N] operands into K-major copies instead of reading

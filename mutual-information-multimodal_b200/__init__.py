@@ -15,12 +15,12 @@ device is missing.
 """
 from . import _lib  # noqa: F401
 from .critic import (  # noqa: F401
-    FusedCritic, PairBatch, ScoreHandle, create_mi_pairs, create_mi_pairs_tensor, dv_bound_loss, infonce_bound_loss,
+    FusedCritic, FusedMLPCritic, PairBatch, ScoreHandle, create_mi_pairs, create_mi_pairs_tensor, dv_bound_loss, infonce_bound_loss,
     mi_estimator_loss, select_estimator, sharded_mi_loss,
 )
 from .ops import MIError  # noqa: F401
 
 __all__ = [
-    "FusedCritic", "PairBatch", "ScoreHandle", "create_mi_pairs", "create_mi_pairs_tensor", "dv_bound_loss",
+    "FusedCritic", "FusedMLPCritic", "PairBatch", "ScoreHandle", "create_mi_pairs", "create_mi_pairs_tensor", "dv_bound_loss",
     "infonce_bound_loss", "mi_estimator_loss", "select_estimator", "sharded_mi_loss", "MIError",
 ]

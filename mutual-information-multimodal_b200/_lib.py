@@ -22,6 +22,7 @@ PROTOTYPES = {
     "mi_set_debug": (None, [c_int]),
     "mi_set_single_pass": (None, [c_int]),
     "mi_set_mn_operands": (None, [c_int]),
+    "mi_set_mlp_panel_pairs": (None, [c_i64]),
     "mi_get_cta_group": (c_int, []),
     "mi_gemm_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_i64,
                              c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
@@ -45,6 +46,8 @@ PROTOTYPES = {
     "mi_critic_workspace_bytes": (c_sz, [c_i64, c_i64, c_int, c_int, c_int, c_int]),
     "mi_critic_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "mi_mlp_critic_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_i64, c_int]),
+    "mi_mlp_critic_loss_fwd_bwd": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_i64, c_int, c_int] + [c_vp] * 10 + [c_vp, c_sz, c_vp]),
     "mi_critic_host_scratch_bytes": (c_sz, [c_i64, c_i64, c_int, c_int, c_int, c_int]),
     "mi_critic_loss_fwd_bwd_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32,
                                             c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -97,7 +97,7 @@ def create_mi_pairs_tensor(embedding_img: torch.Tensor, embedding_txt: torch.Ten
 class ScoreHandle:
     """Lazy stand-in for the ``[N, 1]`` logits tensor (``mi_output``, main_utils.py:222)."""
 
-    def __init__(self, pairs: PairBatch, critic: "FusedCritic"):
+    def __init__(self, pairs: PairBatch, critic):
         self.pairs = pairs
         self.critic = critic
 
@@ -216,8 +216,64 @@ class FusedCritic(nn.Module):
         return (t * rows[:, D:]).sum(1, keepdim=True) * self.inv_tau
 
 
+class _FusedMLPCriticLoss(torch.autograd.Function):
+    """loss = estimator(S), S[i,j] = make_mlp(2D,[H1,H2])([x_i ; y_j]) for every pair — one library call
+    produces the loss and the gradients of both embeddings and all six MLP tensors."""
+
+    @staticmethod
+    def forward(ctx, X, Y, W1, b1, W2, b2, W3, b3, sid, estimator, precision, check_negatives):
+        tensors = (X, Y, W1, b1, W2, b2, W3, b3)
+        need = any(t.requires_grad for t in tensors)
+        out, _, grads = ops.mlp_critic_loss_fwd_bwd(X, Y, (W1, b1, W2, b2, W3, b3), sid, estimator, precision, need_grads=need)
+        if check_negatives and float(out.cpu()[3]) == 0.0:
+            raise ops.MIError("no negative pairs in the batch (every study_id is equal): the reference "
+                              "returns nan (dv) / -inf (infonce) here; the fused path refuses instead")
+        ctx.grads = grads
+        ctx.dtypes = tuple(t.dtype for t in tensors)
+        ctx.stats = out
+        return out[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = grad_out.to(torch.float32)
+        if ctx.grads is None:
+            return (None,) * 12
+        names = ("dX", "dY", "dW1", "db1", "dW2", "db2", "dW3", "db3")
+        outs = tuple((ctx.grads[n] * g).to(dt) for n, dt in zip(names, ctx.dtypes))
+        return outs + (None, None, None, None)
+
+
+class FusedMLPCritic(nn.Sequential):
+    """The reference's own critic, ``make_mlp(2 * dim, hidden_dims)`` (model.py:18-32; main_utils.py:77 builds
+    ``make_mlp(1536, [1024, 512])``), as a drop-in for the ``mi_discriminator`` slot: the SAME ``nn.Sequential``
+    (``Linear, ReLU, Linear, ReLU, Linear`` — identical parameter names ``0.weight … 4.bias``, identical default
+    initialisation, so a reference checkpoint loads with ``load_state_dict``).
+
+    Called with the explicit ``[N, 2D]`` pair tensor it IS the reference module (torch ops).  Called with a
+    ``PairBatch`` (what this package's ``create_mi_pairs`` returns) it yields a ``ScoreHandle`` and the loss
+    functions run the fused CUDA path: layer 1 is evaluated once per image and once per text
+    (``W1 [x;y] = W1x x + W1y y``), layers 2-3 on tensor cores for all B^2 pairs, the pair tensor is never built."""
+
+    def __init__(self, dim: int = 768, hidden_dims=(1024, 512), precision: str = "strict", check_negatives: bool = True):
+        if len(hidden_dims) != 2:
+            raise ValueError("the fused path implements the reference's two-hidden-layer critic")
+        h1, h2 = int(hidden_dims[0]), int(hidden_dims[1])
+        super().__init__(nn.Linear(2 * dim, h1), nn.ReLU(), nn.Linear(h1, h2), nn.ReLU(), nn.Linear(h2, 1))
+        self.dim = dim
+        self.precision = precision
+        self.check_negatives = check_negatives
+
+    def forward(self, mi_input):
+        if isinstance(mi_input, PairBatch):
+            return ScoreHandle(mi_input, self)
+        return super().forward(mi_input)
+
+
 def mi_estimator_loss(handle: ScoreHandle, estimator: str) -> torch.Tensor:
     p, c = handle.pairs, handle.critic
+    if isinstance(c, FusedMLPCritic):
+        return _FusedMLPCriticLoss.apply(p.embedding_img, p.embedding_txt, c[0].weight, c[0].bias, c[2].weight, c[2].bias,
+                                         c[4].weight, c[4].bias, p.sid, estimator, c.precision, c.check_negatives)
     return _FusedCriticLoss.apply(p.embedding_img, p.embedding_txt, c.W, p.sid, estimator, c.precision,
                                   c.inv_tau, c.check_negatives)
 

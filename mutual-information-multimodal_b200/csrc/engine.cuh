@@ -243,6 +243,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t colq = (warp - kEpiWarp0) >> 2;        // 64-column quarter of the 256-column tile
     uint32_t tile_cnt = 0;
     typename Epi::State st;
+    Epi::init(ep, st);
     st.stage_smem = epi_smem + (warp - kEpiWarp0) * (Epi::kEpiSmemBytes / kNumEpiWarps);
     for (int u = pair_id; u < n_units; u += n_pairs) {
       const Unit un = decode_unit(sc, u);
@@ -271,6 +272,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
       Epi::unit_end(ep, st, un, row, (int)colq);
     }
+    Epi::finish(ep, st, (int)colq);
   }
 
   // ---------------------------------------------------------------- teardown
@@ -349,6 +351,8 @@ struct EpiStats {
   };
   struct State { uint8_t* stage_smem; MaskState ms; float m, s; };
 
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
   static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
     st.m = neg_inf(); st.s = 0.f;
     mask_begin(p.mask, st.ms, row, p.q_rows);
@@ -414,6 +418,8 @@ struct EpiPStore {
   };
   struct State { uint8_t* stage_smem; MaskState ms; float rq2; float s; };
 
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
   static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
     st.s = 0.f;
     mask_begin(p.mask, st.ms, row, p.q_rows);
@@ -529,8 +535,13 @@ struct EpiStore {
     int sub_row0, sub_rows;    // SUB row r applies to output row sub_row0 + r, r in [0, sub_rows)
     long long ksplit_stride;   // elements between split-K partial outputs (fp32 only)
     int accumulate;            // out_f32 += result (panel-by-panel accumulation)
+    const float* bias;         // optional [cols]: C = alpha * (ACC - gamma SUB) + bias   (nn.Linear bias)
+    const __nv_bfloat16* relu_mask;  // optional [rows, ld_mask]: C = 0 where relu_mask <= 0  (backward of a ReLU whose
+    long long ld_mask;               //                          output is relu_mask)
   };
   struct State { uint8_t* stage_smem; };
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
   static __device__ __forceinline__ void unit_begin(const Params&, State&, const Unit&, int, int) {}
   static __device__ __forceinline__ void chunk(const Params& p, State&, const Unit& un, int row, int col0,
                                                uint32_t (&v)[32]) {
@@ -564,6 +575,36 @@ struct EpiStore {
     }
 #pragma unroll
     for (int c = 0; c < 32; ++c) o[c] *= p.alpha;
+    if (p.bias != nullptr) {
+      if (full) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b = __ldg(b4 + g);
+          o[4 * g] += b.x; o[4 * g + 1] += b.y; o[4 * g + 2] += b.z; o[4 * g + 3] += b.w;
+        }
+      } else {
+        for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) o[c] += p.bias[col0 + c];
+      }
+    }
+    if (p.relu_mask != nullptr) {
+      const __nv_bfloat16* m = p.relu_mask + (size_t)row * p.ld_mask + col0;
+      if (full) {
+        const uint4* m4 = reinterpret_cast<const uint4*>(m);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 q = __ldg(m4 + g);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {       // bf16 > 0  <=>  sign clear and magnitude non-zero
+            if (!(__uint_as_float(w[j] << 16) > 0.f)) o[g * 8 + 2 * j] = 0.f;
+            if (!(__uint_as_float(w[j] & 0xffff0000u) > 0.f)) o[g * 8 + 2 * j + 1] = 0.f;
+          }
+        }
+      } else {
+        for (int c = 0; c < 32; ++c) if (col0 + c < p.cols && !(__bfloat162float(m[c]) > 0.f)) o[c] = 0.f;
+      }
+    }
     if (p.out_f32 != nullptr) {
       float* d = p.out_f32 + (size_t)un.ks * p.ksplit_stride + (size_t)row * p.ld_out + col0;
       if (full) {
@@ -613,6 +654,161 @@ struct EpiStore {
     }
   }
   static __device__ __forceinline__ void unit_end(const Params&, State&, const Unit&, int, int) {}
+};
+
+// =====================================================================================
+// Concat-MLP critic (the reference's make_mlp(2D, [H1, H2]), model.py:18-32): the accumulator tile is
+// Z2[pair, n] = sum_k H1act[pair, k] W2[n, k]; rows are (image i, text j) pairs, columns the H2 hidden units.
+// =====================================================================================
+// column sums over the 32 lanes (rows) of a warp: in: v[c] = this row's value of column c; out: lane l holds
+// sum over rows of column l.  Butterfly that halves the live values per step: 31 shuffles instead of 160.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int c = 0; c < s; ++c) {
+      // lanes with bit s keep the upper half [s, 2s), the others the lower half [0, s)
+      const float send = up ? v[c] : v[c + s];
+      const float keep = up ? v[c + s] : v[c];
+      v[c] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];      // column index = lane (bit s of the lane selected the half at every step)
+}
+
+// ---- forward: logit[pair] = b3 + sum_n w3[n] relu(Z2[pair, n] + b2[n]); each epilogue warp owns a 64-column
+//      quarter of every 256-column tile, so it writes one partial per (pair, column quarter)
+struct EpiMlpFwd {
+  static constexpr int kEpiSmemBytes = 0;
+  struct Params {
+    const float* b2;       // [n_ntile * 256] zero padded
+    const float* w3;       // [n_ntile * 256] zero padded
+    float* part;           // [kColQuarters][rows_padded]
+    int rows_padded;
+  };
+  struct State { uint8_t* stage_smem; float acc; };
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+  static __device__ __forceinline__ void unit_begin(const Params&, State& st, const Unit&, int, int) { st.acc = 0.f; }
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int, int col0, uint32_t (&v)[32]) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col0);
+    const float4* w4 = reinterpret_cast<const float4*>(p.w3 + col0);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = __ldg(b4 + g), w = __ldg(w4 + g);
+      a0 = fmaf(w.x, fmaxf(__uint_as_float(v[4 * g]) + b.x, 0.f), a0);
+      a1 = fmaf(w.y, fmaxf(__uint_as_float(v[4 * g + 1]) + b.y, 0.f), a1);
+      a2 = fmaf(w.z, fmaxf(__uint_as_float(v[4 * g + 2]) + b.z, 0.f), a2);
+      a3 = fmaf(w.w, fmaxf(__uint_as_float(v[4 * g + 3]) + b.w, 0.f), a3);
+    }
+    st.acc += (a0 + a1) + (a2 + a3);
+  }
+  static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit&, int row, int colq) {
+    p.part[(size_t)colq * p.rows_padded + row] = st.acc;
+  }
+};
+
+// ---- backward through layer 3 / ReLU 2:  dZ2[pair, n] = g[pair] w3[n] [Z2 + b2 > 0]  (bf16 hi [+ lo]) for the
+//      dW2 / dH1 contractions;  dw3[n] += sum_pairs g relu(Z2 + b2),  db2[n] += sum_pairs dZ2  (column sums over
+//      the warp's rows, kept per lane across the whole launch, one atomicAdd per column at the end).
+struct EpiMlpDz {
+  static constexpr int kEpiSmemBytes = 0;
+  static constexpr int kMaxTiles = 2;       // H2 <= 512
+  struct Params {
+    const float* b2;       // [n_ntile * 256] zero padded
+    const float* w3;       // [n_ntile * 256] zero padded
+    const float* g;        // [rows] dL/dlogit of the pair
+    int rows, cols;
+    __nv_bfloat16* dz;     // [rows, pitch]
+    __nv_bfloat16* dz_lo;  // residual half (strict) or nullptr
+    long long pitch;
+    float* dw3;            // [n_ntile * 256] accumulators (atomicAdd)
+    float* db2;
+  };
+  struct State { uint8_t* stage_smem; float g; float sw[kMaxTiles][2]; float sb[kMaxTiles][2]; };
+  static __device__ __forceinline__ void init(const Params&, State& st) {
+#pragma unroll
+    for (int t = 0; t < kMaxTiles; ++t) { st.sw[t][0] = st.sw[t][1] = 0.f; st.sb[t][0] = st.sb[t][1] = 0.f; }
+  }
+  static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
+    st.g = row < p.rows ? __ldg(p.g + row) : 0.f;
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0, uint32_t (&v)[32]) {
+    const int lane = (int)(threadIdx.x & 31);
+    const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col0);
+    const float4* w4 = reinterpret_cast<const float4*>(p.w3 + col0);
+    float dz[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = __ldg(b4 + g), w = __ldg(w4 + g);
+      const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = __uint_as_float(v[4 * g + j]) + bb[j];
+        dz[4 * g + j] = z > 0.f ? st.g * ww[j] : 0.f;                       // padded columns: w3 = 0
+        v[4 * g + j] = __float_as_uint(z > 0.f ? st.g * z : 0.f);             // g relu(z2): the dw3 summand
+      }
+    }
+    if (row < p.rows && col0 < p.cols) {
+      uint32_t hi[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(dz[2 * c], dz[2 * c + 1]);
+      const bool full = col0 + 32 <= p.cols;
+      __nv_bfloat16* d = p.dz + (size_t)row * p.pitch + col0;
+      if (full) {
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) d4[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+      } else {
+        for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) d[c] = __float2bfloat16(dz[c]);
+      }
+      if (p.dz_lo != nullptr) {
+        __nv_bfloat16* dl = p.dz_lo + (size_t)row * p.pitch + col0;
+        uint32_t lo[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float h0 = __uint_as_float(hi[c] << 16), h1 = __uint_as_float(hi[c] & 0xffff0000u);
+          lo[c] = ptx::pack_bf16(dz[2 * c] - h0, dz[2 * c + 1] - h1);
+        }
+        if (full) {
+          uint4* d4 = reinterpret_cast<uint4*>(dl);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) d4[g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+        } else {
+          for (int c = 0; c < 32; ++c)
+            if (col0 + c < p.cols) dl[c] = __float2bfloat16(dz[c] - __bfloat162float(__float2bfloat16(dz[c])));
+        }
+      }
+    }
+    // column sums over this warp's 32 pairs (rows beyond p.rows carry g = 0)
+    const float cb = warp_column_sums(dz, lane);
+    float hw[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) hw[c] = __uint_as_float(v[c]);
+    const float cw = warp_column_sums(hw, lane);
+    const int t = col0 >> 8, h = (col0 >> 5) & 1;
+#pragma unroll
+    for (int tt = 0; tt < kMaxTiles; ++tt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+        if (tt == t && hh == h) { st.sb[tt][hh] += cb; st.sw[tt][hh] += cw; }
+  }
+  static __device__ __forceinline__ void unit_end(const Params&, State&, const Unit&, int, int) {}
+  static __device__ __forceinline__ void finish(const Params& p, State& st, int colq) {
+    const int lane = (int)(threadIdx.x & 31);
+#pragma unroll
+    for (int t = 0; t < kMaxTiles; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = t * TILE_N + colq * 64 + h * 32 + lane;
+        if (col < p.cols && (st.sb[t][h] != 0.f || st.sw[t][h] != 0.f)) {
+          atomicAdd(p.db2 + col, st.sb[t][h]);
+          atomicAdd(p.dw3 + col, st.sw[t][h]);
+        }
+      }
+  }
 };
 
 }  // namespace mi

@@ -182,6 +182,8 @@ int launch_engine_cg(const MapSpec& a, const MapSpec& b, const Sched& sc, const 
 template <> struct EpiKind<mi::EpiStats> { static constexpr int value = 0; };
 template <> struct EpiKind<mi::EpiPStore> { static constexpr int value = 1; };
 template <> struct EpiKind<mi::EpiStore> { static constexpr int value = 2; };
+template <> struct EpiKind<mi::EpiMlpFwd> { static constexpr int value = 0; };   // (profiling buckets: score-like / panel-like)
+template <> struct EpiKind<mi::EpiMlpDz> { static constexpr int value = 1; };
 
 template <class Epi, bool kAMN = false, bool kBMN = false>
 int launch_engine(const MapSpec& a, const MapSpec& b, const Sched& sc, const typename Epi::Params& ep, cudaStream_t stream) {
@@ -552,12 +554,15 @@ __global__ void make_ref_kernel(float* __restrict__ dst, const float4* __restric
   dst[i] = col == 0 ? v.x : col == 1 ? v.y : col == 2 ? v.z : v.w;
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int n_part, long long stride, float* __restrict__ out, long long n) {
+// out[r, c] (pitch ld_out) (+)= sum_p part[p][r, c] (compact partials, pitch ldp): split-K reduction
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int n_part, long long stride, long long ldp,
+                                       float* __restrict__ out, long long ld_out, long long rows, long long cols, int accumulate) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float a = 0.f;
-  for (int p = 0; p < n_part; ++p) a += part[(size_t)p * stride + i];
-  out[i] = a;
+  if (i >= rows * cols) return;
+  const long long r = i / cols, c = i - r * cols;
+  float a = accumulate ? out[r * ld_out + c] : 0.f;
+  for (int p = 0; p < n_part; ++p) a += part[(size_t)p * stride + r * ldp + c];
+  out[r * ld_out + c] = a;
 }
 
 inline unsigned blocks_for(long long n, int t) { return static_cast<unsigned>(cdiv(n, t)); }
@@ -596,6 +601,8 @@ struct GemmArgs {
   float* out_f32 = nullptr; long long ld_out = 0;
   __nv_bfloat16* out_bf16 = nullptr; __nv_bfloat16* out_bf16_lo = nullptr; long long ld_out16 = 0;
   bool accumulate = false;
+  const float* bias = nullptr;                                   // [N] added after alpha (nn.Linear bias)
+  const __nv_bfloat16* relu_mask = nullptr; long long ld_mask = 0;   // zero the result where relu_mask <= 0
 };
 
 int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
@@ -613,7 +620,8 @@ int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
     for (int i = 0; i < 4; ++i) { sc.a_seg[i] = g.a_seg[i]; sc.b_seg[i] = g.b_seg[i]; sc.a_moff[i] = g.a_moff[i]; sc.b_noff[i] = g.b_noff[i]; }
   }
   float* partial = nullptr;
-  if (sc.n_ksplit > 1) partial = ws.take<float>(static_cast<size_t>(sc.n_ksplit) * g.M * g.ld_out);
+  const long long ldp = round_up(g.N, 4);      // split-K partials are compact [M, ldp] blocks
+  if (sc.n_ksplit > 1) partial = ws.take<float>(static_cast<size_t>(sc.n_ksplit) * g.M * ldp);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
   if (!g.a.ptr || !g.b.ptr || (!g.out_f32 && !g.out_bf16)) return MI_ERR_BAD_ARG;
@@ -622,21 +630,23 @@ int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
   ep.out_f32 = sk ? partial : g.out_f32;
   ep.out_bf16 = sk ? nullptr : g.out_bf16;
   ep.out_bf16_lo = sk ? nullptr : g.out_bf16_lo;
-  ep.ld_out = g.ld_out; ep.ld_out16 = g.ld_out16;
+  ep.ld_out = sk ? ldp : g.ld_out; ep.ld_out16 = g.ld_out16;
+  ep.bias = sk ? nullptr : g.bias; ep.relu_mask = sk ? nullptr : g.relu_mask; ep.ld_mask = g.ld_mask;
   ep.rows = static_cast<int>(g.M); ep.cols = static_cast<int>(g.N);
   ep.alpha = g.alpha; ep.gamma = g.gamma;
   ep.sub = sk ? nullptr : g.sub; ep.sub_lo = sk ? nullptr : g.sub_lo; ep.ld_sub = g.ld_sub;
   ep.sub_row0 = static_cast<int>(g.sub_row0); ep.sub_rows = static_cast<int>(g.sub_rows < 0 ? g.M : g.sub_rows);
-  ep.ksplit_stride = static_cast<long long>(g.M) * g.ld_out;
+  ep.ksplit_stride = static_cast<long long>(g.M) * ldp;
   ep.accumulate = (!sk && g.accumulate) ? 1 : 0;
   if (g.a_mn && g.b_mn) MI_TRY((launch_engine<mi::EpiStore, true, true>(g.a, g.b, sc, ep, stream)));
   else if (g.a_mn) MI_TRY((launch_engine<mi::EpiStore, true, false>(g.a, g.b, sc, ep, stream)));
   else if (g.b_mn) MI_TRY((launch_engine<mi::EpiStore, false, true>(g.a, g.b, sc, ep, stream)));
   else MI_TRY((launch_engine<mi::EpiStore, false, false>(g.a, g.b, sc, ep, stream)));
   if (sk) {
-    if (!g.out_f32 || g.sub || g.accumulate) return MI_ERR_BAD_ARG;
-    const long long n = static_cast<long long>(g.M) * g.ld_out;
-    reduce_partials_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(partial, sc.n_ksplit, n, g.out_f32, n);
+    if (!g.out_f32 || g.sub || g.bias || g.relu_mask || g.alpha != 1.f) return MI_ERR_BAD_ARG;
+    const long long n = static_cast<long long>(g.M) * g.N;
+    reduce_partials_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(partial, sc.n_ksplit, static_cast<long long>(g.M) * ldp, ldp,
+                                                                   g.out_f32, g.ld_out, g.M, g.N, g.accumulate ? 1 : 0);
     MI_LAUNCH_CHECK("reduce_partials_kernel");
   }
   return MI_OK;
@@ -1221,6 +1231,399 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   return MI_OK;
 }
 
+
+// ============================================================================================
+// Concat-MLP critic — the reference's own mi_discriminator = make_mlp(1536, [1024, 512])
+// (main_utils.py:77, model.py:18-32) on every (image i, text j) pair, without the pair tensor.
+//
+//   layer 1 is separable:  W1 [x_i ; y_j] + b1 = (W1x x_i + b1) + W1y y_j = A_i + C_j     (two [B, H1] GEMMs)
+//   per pair (i, j):       h1 = relu(A_i + C_j);  z2 = W2 h1 + b2;  S_ij = w3 . relu(z2) + b3
+//
+// Pairs are processed in row panels (rows i in [r0, r0 + R), all columns j; pair index p = (i - r0) B + j):
+//   forward   H[p,:] = bf16 h1  ->  tile engine  Z2 = H W2^T  with the EpiMlpFwd epilogue  ->  S (fp32 [B, B])
+//   loss      row statistics of S over the negatives mask -> DV / InfoNCE exactly as for the separable critics; G = dL/dS
+//   backward  recompute Z2 with the EpiMlpDz epilogue -> dZ2 panel (bf16), dw3, db2;
+//             dW2 += dZ2^T H          (both operands read MN-major, contraction over the pairs, split-K)
+//             dZ1  = (dZ2 W2) . [H > 0]  (W2 read MN-major; ReLU mask in the epilogue), reduced over j -> dA_i, over i -> dC_j
+//             dX = dA W1x, dY = dC W1y, dW1 = [dA^T X | dC^T Y], db1 = sum_i dA_i
+// Strict ("fp32-accumulate") mode keeps every bf16 operand as a hi/lo pair and adds the cross terms as K segments.
+// ============================================================================================
+// fp32 [R, C] (pitch ld_in) -> bf16 [R, pitch]: hi in columns [0, C), lo (split == 2) in [Cp, Cp + C), zeros elsewhere
+__global__ void split_f32_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out, long long pitch,
+                                 int split, long long Cp, long long R, long long C) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= R * pitch) return;
+  const long long r = idx / pitch, c = idx - r * pitch;
+  float v = 0.f;
+  if (c < C) v = __bfloat162float(__float2bfloat16(in[r * ld_in + c]));
+  else if (split == 2 && c >= Cp && c < Cp + C) {
+    const float x = in[r * ld_in + (c - Cp)];
+    v = x - __bfloat162float(__float2bfloat16(x));
+  }
+  out[idx] = __float2bfloat16(v);
+}
+__global__ void pad_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, long long n_pad) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = (i < n) ? src[i] : 0.f;
+}
+// H[p, k] = relu(A[r0 + p / Bk, k] + C[p % Bk, k]) as bf16 hi (+ lo at column Hp), 8 columns per thread
+__global__ void mlp_gen_kernel(const float* __restrict__ A, const float* __restrict__ Cm, long long H1, long long Bk, long long r0,
+                               long long P, __nv_bfloat16* __restrict__ H, long long pitch, long long Hp, int split) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long h8 = H1 >> 3;
+  if (idx >= P * h8) return;
+  const long long p = idx / h8, k = (idx - p * h8) << 3;
+  const long long i = r0 + p / Bk, j = p % Bk;
+  const float4* a4 = reinterpret_cast<const float4*>(A + i * H1 + k);
+  const float4* c4 = reinterpret_cast<const float4*>(Cm + j * H1 + k);
+  const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), c0 = __ldg(c4), c1 = __ldg(c4 + 1);
+  const float v[8] = {fmaxf(a0.x + c0.x, 0.f), fmaxf(a0.y + c0.y, 0.f), fmaxf(a0.z + c0.z, 0.f), fmaxf(a0.w + c0.w, 0.f),
+                      fmaxf(a1.x + c1.x, 0.f), fmaxf(a1.y + c1.y, 0.f), fmaxf(a1.z + c1.z, 0.f), fmaxf(a1.w + c1.w, 0.f)};
+  uint32_t hi[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) hi[t] = ptx::pack_bf16(v[2 * t], v[2 * t + 1]);
+  *reinterpret_cast<uint4*>(H + p * pitch + k) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (split == 2) {
+    uint32_t lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      lo[t] = ptx::pack_bf16(v[2 * t] - __uint_as_float(hi[t] << 16), v[2 * t + 1] - __uint_as_float(hi[t] & 0xffff0000u));
+    *reinterpret_cast<uint4*>(H + p * pitch + Hp + k) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+// S[r0 * Bk + p] = b3 + sum of the column-quarter partials
+__global__ void mlp_logit_merge_kernel(const float* __restrict__ part, int rows_padded, long long P, const float* __restrict__ b3,
+                                       float* __restrict__ S) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float a = b3[0];
+#pragma unroll
+  for (int q = 0; q < mi::kColQuarters; ++q) a += part[(size_t)q * rows_padded + p];
+  S[p] = a;
+}
+// one warp per row of S: {lse over the negatives, #negatives, S_ii, lse over negatives and the positive}
+__global__ void mlp_row_stats_kernel(const float* __restrict__ S, const int* __restrict__ sid, long long B, float4* __restrict__ row_out) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int my = sid[row];
+  float m = mi::neg_inf(), s = 0.f, cnt = 0.f;
+  for (long long j = lane; j < B; j += 32) {
+    if (sid[j] != my) {                                   // main_utils.py:105 (the diagonal has equal ids)
+      const float v = S[row * B + j];
+      const float mn = fmaxf(m, v);
+      s = s * expf(m - mn) + expf(v - mn); m = mn; cnt += 1.f;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const float mn = fmaxf(m, m2);
+    if (mn > mi::neg_inf()) s = s * expf(m - mn) + s2 * expf(m2 - mn);
+    m = mn;
+  }
+  if (lane == 0) {
+    const float diag = S[row * B + row];
+    const float lse_neg = (cnt > 0.f && s > 0.f) ? m + logf(s) : mi::neg_inf();
+    const float hi = fmaxf(lse_neg, diag), lo = fminf(lse_neg, diag);
+    row_out[row] = make_float4(lse_neg, cnt, diag, hi + log1pf(expf(lo - hi)));
+  }
+}
+// G = dL/dS.  dv / infonce (mi_critics.py:3-23): softmax over ALL negatives, -1/B on the diagonal;
+// row InfoNCE: (1/B) softmax over {positive} u negatives of the row, minus 1/B on the diagonal.
+__global__ void mlp_g_kernel(const float* __restrict__ S, const int* __restrict__ sid, long long B, int dv_like,
+                             const float* __restrict__ lse, const float4* __restrict__ rows, float* __restrict__ G) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= B * B) return;
+  const long long i = idx / B, j = idx - i * B;
+  const float inv_b = 1.f / static_cast<float>(B);
+  const bool neg = sid[i] != sid[j];
+  float g = 0.f;
+  if (dv_like) g = neg ? expf(S[idx] - lse[0]) : (i == j ? -inv_b : 0.f);
+  else if (neg || i == j) g = inv_b * expf(S[idx] - rows[i].w) - (i == j ? inv_b : 0.f);
+  G[idx] = g;
+}
+// dA[r0 + il, k..k+3] = sum_j DZ1[il * Bk + j, k..k+3]
+__global__ void mlp_reduce_rows_kernel(const float* __restrict__ dz1, long long H1, long long Bk, long long R, long long r0,
+                                       float* __restrict__ dA) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long h4 = H1 >> 2;
+  if (idx >= R * h4) return;
+  const long long il = idx / h4, k = (idx - il * h4) << 2;
+  const float* src = dz1 + il * Bk * H1 + k;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long j = 0; j < Bk; ++j) {
+    const float4 v = *reinterpret_cast<const float4*>(src + j * H1);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dA + (r0 + il) * H1 + k) = a;
+}
+// dC[j, k..k+3] += sum_il DZ1[il * Bk + j, k..k+3]
+__global__ void mlp_reduce_cols_kernel(const float* __restrict__ dz1, long long H1, long long Bk, long long R, float* __restrict__ dC) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long h4 = H1 >> 2;
+  if (idx >= Bk * h4) return;
+  const long long j = idx / h4, k = (idx - j * h4) << 2;
+  const float* src = dz1 + j * H1 + k;
+  float4 a = *reinterpret_cast<const float4*>(dC + j * H1 + k);
+  for (long long il = 0; il < R; ++il) {
+    const float4 v = *reinterpret_cast<const float4*>(src + il * Bk * H1);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dC + j * H1 + k) = a;
+}
+// out[c] = sum_r in[r, c]  (one thread per column; rows are few thousand at most)
+__global__ void colsum_kernel(const float* __restrict__ in, long long R, long long C, float* __restrict__ out) {
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (long long r = 0; r < R; ++r) a += in[r * C + c];
+  out[c] = a;
+}
+// one block: out[0] = sum in[0..n)
+__global__ void sum_reduce_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) a += in[i];
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i]; out[0] = static_cast<float>(t); }
+}
+__global__ void copy_f32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+struct MlpDims { long long B, D, H1, H2; };
+struct MlpParams { const float *W1, *b1, *W2, *b2, *W3, *b3; };
+struct MlpGrads { float *dX, *dY, *dW1, *db1, *dW2, *db2, *dW3, *db3; };
+
+long long g_mlp_max_pairs = 1LL << 19;                    // bounds the panel buffers (H, dZ2, dZ1) to a few GB
+inline long long mlp_panel_rows(long long B) {
+  const long long max_pairs = g_mlp_max_pairs;
+  long long R = max_pairs / B;
+  if (R < 1) R = 1;
+  if (R > B) R = B;
+  return R;
+}
+
+// hi*hi (+ lo*hi + hi*lo) K segments of a K-major x K-major product whose operands are [hi | lo] pairs
+void kk_segments(GemmArgs& g, int sp, long long K) {
+  const int kb = static_cast<int>(sp == 2 ? round_up(K, kSplitAlign) / bk() : cdiv(K, bk()));
+  g.k_blocks = kb; g.seg_len = kb;
+  if (sp == 2) { g.k_blocks = 3 * kb; g.a_seg[1] = kb; g.b_seg[2] = kb; }
+}
+
+int mlp_impl(const float* X, const float* Y, const MlpParams& prm, const int* sid, const MlpDims& d, int estimator, int precision,
+             double* loss_out, float* S_out, const MlpGrads& gr, Bump& ws, cudaStream_t stream) {
+  const long long B = d.B, D = d.D, H1 = d.H1, H2 = d.H2;
+  if (B <= 0 || D <= 0 || H1 <= 0 || H2 <= 0 || (D % 8) != 0 || (H1 % 8) != 0 || (H2 % 8) != 0) return MI_ERR_BAD_ARG;
+  if (H2 > mi::EpiMlpDz::kMaxTiles * mi::TILE_N) return MI_ERR_BAD_ARG;
+  if (estimator != MI_EST_DV && estimator != MI_EST_INFONCE_REF && estimator != MI_EST_INFONCE_ROW) return MI_ERR_BAD_ARG;
+  typedef __nv_bfloat16 bf;
+  const int sp = (precision & 1) == MI_PREC_BF16_STRICT ? 2 : 1;
+  const bool grads = gr.dX || gr.dY || gr.dW1 || gr.db1 || gr.dW2 || gr.db2 || gr.dW3 || gr.db3;
+  const bool plan = grads || ws.dry;
+  const long long Dp = round_up(D, kSplitAlign), Hp = round_up(H1, kSplitAlign), H2p = round_up(H2, kSplitAlign);
+  const long long pX = sp == 2 ? 2 * Dp : D, pH = sp == 2 ? 2 * Hp : H1, pZ = sp == 2 ? 2 * H2p : H2;
+  const long long eX = sp == 2 ? Dp + D : D, eH = sp == 2 ? Hp + H1 : H1, eZ = sp == 2 ? H2p + H2 : H2;   // TMA extents
+  const long long R = mlp_panel_rows(B), Pmax = R * B;
+  const int nt2 = static_cast<int>(cdiv(H2, mi::TILE_N));
+  const long long h2_pad = static_cast<long long>(nt2) * mi::TILE_N;
+  const long long rows_padded_max = cdiv(Pmax, rows_per_mblk()) * rows_per_mblk();
+
+  bf* X16 = ws.take<bf>(B * pX); bf* Y16 = ws.take<bf>(B * pX);
+  bf* W1x = ws.take<bf>(H1 * pX); bf* W1y = ws.take<bf>(H1 * pX);
+  bf* W2h = ws.take<bf>(H2 * pH);
+  float* A32 = ws.take<float>(B * H1); float* C32 = ws.take<float>(B * H1);
+  float* b2p = ws.take<float>(h2_pad); float* w3p = ws.take<float>(h2_pad);
+  float* S = S_out ? S_out : ws.take<float>(B * B);
+  float* rows_r = ws.take<float>(B * 4);
+  double* scal = ws.take<double>(8);
+  float* lse_f = ws.take<float>(1);
+  bf* Hpan = ws.take<bf>(Pmax * pH);
+  float* part = ws.take<float>(mi::kColQuarters * rows_padded_max);
+  float* G = plan ? ws.take<float>(B * B) : nullptr;
+  bf* DZ2 = plan ? ws.take<bf>(Pmax * pZ) : nullptr;
+  float* DZ1 = plan ? ws.take<float>(Pmax * H1) : nullptr;
+  float* dA32 = plan ? ws.take<float>(B * H1) : nullptr; float* dC32 = plan ? ws.take<float>(B * H1) : nullptr;
+  bf* dA16 = plan ? ws.take<bf>(B * pH) : nullptr; bf* dC16 = plan ? ws.take<bf>(B * pH) : nullptr;
+  float* acc_w3 = plan ? ws.take<float>(h2_pad) : nullptr; float* acc_b2 = plan ? ws.take<float>(h2_pad) : nullptr;
+  float* dW2_tmp = (plan && !gr.dW2) ? ws.take<float>(H2 * H1) : nullptr;
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  const size_t mk = ws.mark();
+  const bool dry = ws.dry;
+  if (!dry && (!X || !Y || !sid || !loss_out || !prm.W1 || !prm.b1 || !prm.W2 || !prm.b2 || !prm.W3 || !prm.b3)) return MI_ERR_BAD_ARG;
+
+  auto split = [&](const float* in, long long ld_in, bf* out, long long pitch, long long Cp, long long Rr, long long Cc) -> int {
+    split_f32_kernel<<<blocks_for(Rr * pitch, 256), 256, 0, stream>>>(in, ld_in, out, pitch, sp, Cp, Rr, Cc);
+    MI_LAUNCH_CHECK("split_f32_kernel");
+    return MI_OK;
+  };
+  if (!dry) {
+    MI_TRY(split(X, D, X16, pX, Dp, B, D));
+    MI_TRY(split(Y, D, Y16, pX, Dp, B, D));
+    MI_TRY(split(prm.W1, 2 * D, W1x, pX, Dp, H1, D));            // W1 = [W1x | W1y]  (nn.Linear weight [H1, 2D])
+    MI_TRY(split(prm.W1 + D, 2 * D, W1y, pX, Dp, H1, D));
+    MI_TRY(split(prm.W2, H1, W2h, pH, Hp, H2, H1));
+    pad_f32_kernel<<<blocks_for(h2_pad, 256), 256, 0, stream>>>(prm.b2, b2p, H2, h2_pad);
+    MI_LAUNCH_CHECK("pad_f32_kernel");
+    pad_f32_kernel<<<blocks_for(h2_pad, 256), 256, 0, stream>>>(prm.W3, w3p, H2, h2_pad);
+    MI_LAUNCH_CHECK("pad_f32_kernel");
+    if (sp == 2 || (H1 % bk()) != 0) MI_CUDA(cudaMemsetAsync(Hpan, 0, static_cast<size_t>(Pmax) * pH * sizeof(bf), stream));
+    if (DZ2 && (sp == 2 || (H2 % bk()) != 0)) MI_CUDA(cudaMemsetAsync(DZ2, 0, static_cast<size_t>(Pmax) * pZ * sizeof(bf), stream));
+  }
+  // ---- layer 1: A = X W1x^T + b1, C = Y W1y^T  (fp32 out)
+  for (int side = 0; side < 2; ++side) {
+    GemmArgs g;
+    g.a = MapSpec{side == 0 ? X16 : Y16, B, eX, pX};
+    g.b = MapSpec{side == 0 ? W1x : W1y, H1, eX, pX};
+    g.M = B; g.N = H1; kk_segments(g, sp, D);
+    g.out_f32 = side == 0 ? A32 : C32; g.ld_out = H1;
+    g.bias = side == 0 ? prm.b1 : nullptr;
+    MI_TRY(run_gemm(g, ws, stream));
+    ws.release(mk);
+  }
+  // Z2 = H W2^T over one panel, handed to an epilogue policy
+  auto z2_sched = [&](long long P, Sched& sc) {
+    sc.n_mblk = static_cast<int>(cdiv(P, rows_per_mblk()));
+    sc.n_ntile = nt2; sc.n_split = 1; sc.n_ksplit = 1; sc.order = 0;
+    single_segment(sc);
+    const int kb = static_cast<int>(sp == 2 ? Hp / bk() : cdiv(H1, bk()));
+    sc.k_blocks = kb; sc.seg_len = kb;
+    if (sp == 2) { sc.k_blocks = 3 * kb; sc.a_seg[1] = kb; sc.b_seg[2] = kb; }
+  };
+  auto gen_panel = [&](long long r0, long long P) -> int {
+    mlp_gen_kernel<<<blocks_for(P * (H1 >> 3), 256), 256, 0, stream>>>(A32, C32, H1, B, r0, P, Hpan, pH, Hp, sp);
+    MI_LAUNCH_CHECK("mlp_gen_kernel");
+    return MI_OK;
+  };
+  const long long n_panels = cdiv(B, R);
+  if (!dry) {
+    // ---- forward: logits of every pair
+    for (long long r0 = 0; r0 < B; r0 += R) {
+      const long long rr = (B - r0 < R) ? (B - r0) : R, P = rr * B;
+      MI_TRY(gen_panel(r0, P));
+      Sched sc; z2_sched(P, sc);
+      mi::EpiMlpFwd::Params ep;
+      ep.b2 = b2p; ep.w3 = w3p; ep.part = part; ep.rows_padded = sc.n_mblk * rows_per_mblk();
+      MI_TRY(launch_engine<mi::EpiMlpFwd>(MapSpec{Hpan, P, eH, pH}, MapSpec{W2h, H2, eH, pH}, sc, ep, stream));
+      mlp_logit_merge_kernel<<<blocks_for(P, 256), 256, 0, stream>>>(part, ep.rows_padded, P, prm.b3, S + r0 * B);
+      MI_LAUNCH_CHECK("mlp_logit_merge_kernel");
+    }
+    // ---- estimator on S (same reductions and fp64 finalisation as the separable critics)
+    mlp_row_stats_kernel<<<blocks_for(B * 32, 256), 256, 0, stream>>>(S, sid, B, reinterpret_cast<float4*>(rows_r));
+    MI_LAUNCH_CHECK("mlp_row_stats_kernel");
+    stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(rows_r), static_cast<int>(B), scal);
+    MI_LAUNCH_CHECK("stats_reduce_kernel");
+    loss_finalize_kernel<<<1, 32, 0, stream>>>(scal, nullptr, B, estimator, loss_out, lse_f);
+    MI_LAUNCH_CHECK("loss_finalize_kernel");
+  }
+  if (!plan) return MI_OK;
+  float* dW2 = gr.dW2 ? gr.dW2 : dW2_tmp;
+  if (!dry) {
+    const int dv_like = (estimator == MI_EST_DV || estimator == MI_EST_INFONCE_REF) ? 1 : 0;
+    mlp_g_kernel<<<blocks_for(B * B, 256), 256, 0, stream>>>(S, sid, B, dv_like, lse_f, reinterpret_cast<const float4*>(rows_r), G);
+    MI_LAUNCH_CHECK("mlp_g_kernel");
+    MI_CUDA(cudaMemsetAsync(dC32, 0, static_cast<size_t>(B) * H1 * sizeof(float), stream));
+    MI_CUDA(cudaMemsetAsync(acc_w3, 0, static_cast<size_t>(h2_pad) * sizeof(float), stream));
+    MI_CUDA(cudaMemsetAsync(acc_b2, 0, static_cast<size_t>(h2_pad) * sizeof(float), stream));
+  }
+  // ---- backward, panel by panel
+  for (long long r0 = 0; r0 < B; r0 += R) {
+    const long long rr = (B - r0 < R) ? (B - r0) : R, P = rr * B;
+    if (!dry) {
+      if (n_panels > 1) MI_TRY(gen_panel(r0, P));                 // a single panel is still resident from the forward
+      Sched sc; z2_sched(P, sc);
+      mi::EpiMlpDz::Params ep;
+      ep.b2 = b2p; ep.w3 = w3p; ep.g = G + r0 * B; ep.rows = static_cast<int>(P); ep.cols = static_cast<int>(H2);
+      ep.dz = DZ2; ep.dz_lo = sp == 2 ? DZ2 + H2p : nullptr; ep.pitch = pZ; ep.dw3 = acc_w3; ep.db2 = acc_b2;
+      MI_TRY(launch_engine<mi::EpiMlpDz>(MapSpec{Hpan, P, eH, pH}, MapSpec{W2h, H2, eH, pH}, sc, ep, stream));
+    }
+    {   // dW2 += dZ2^T H : contraction over the panel's pairs, both operands MN-major
+      GemmArgs g;
+      const int kb = static_cast<int>(cdiv(P, bk()));
+      g.a_mn = true; g.a = MapSpec{DZ2, P, eZ, pZ};
+      g.b_mn = true; g.b = MapSpec{Hpan, P, eH, pH};
+      g.M = H2; g.N = H1; g.k_blocks = kb; g.seg_len = kb;
+      if (sp == 2) { g.k_blocks = 3 * kb; g.a_moff[1] = static_cast<int>(H2p); g.b_noff[2] = static_cast<int>(Hp); }
+      const long long tiles = cdiv(H2, rows_per_mblk()) * cdiv(H1, mi::TILE_N);
+      long long ks = cdiv(num_pairs(), tiles);
+      if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
+      if (ks < 1) ks = 1;
+      g.ksplit = static_cast<int>(ks);
+      g.out_f32 = dW2; g.ld_out = H1; g.accumulate = r0 > 0;
+      MI_TRY(run_gemm(g, ws, stream));
+      ws.release(mk);
+    }
+    {   // dZ1 = (dZ2 W2) . [H > 0] : W2 [H2, H1] read in place as the MN-major B operand
+      GemmArgs g;
+      g.a = MapSpec{DZ2, P, eZ, pZ};
+      g.b_mn = true; g.b = MapSpec{W2h, H2, eH, pH};
+      g.M = P; g.N = H1;
+      const int kb = static_cast<int>(sp == 2 ? H2p / bk() : cdiv(H2, bk()));
+      g.k_blocks = kb; g.seg_len = kb;
+      if (sp == 2) { g.k_blocks = 3 * kb; g.a_seg[1] = kb; g.b_noff[2] = static_cast<int>(Hp); }
+      g.out_f32 = DZ1; g.ld_out = H1; g.relu_mask = Hpan; g.ld_mask = pH;
+      MI_TRY(run_gemm(g, ws, stream));
+      ws.release(mk);
+    }
+    if (!dry) {
+      mlp_reduce_rows_kernel<<<blocks_for(rr * (H1 >> 2), 128), 128, 0, stream>>>(DZ1, H1, B, rr, r0, dA32);
+      MI_LAUNCH_CHECK("mlp_reduce_rows_kernel");
+      mlp_reduce_cols_kernel<<<blocks_for(B * (H1 >> 2), 128), 128, 0, stream>>>(DZ1, H1, B, rr, dC32);
+      MI_LAUNCH_CHECK("mlp_reduce_cols_kernel");
+    }
+  }
+  if (!dry) {
+    if (gr.dW3) { copy_f32_kernel<<<blocks_for(H2, 256), 256, 0, stream>>>(acc_w3, gr.dW3, H2); MI_LAUNCH_CHECK("copy_f32_kernel"); }
+    if (gr.db2) { copy_f32_kernel<<<blocks_for(H2, 256), 256, 0, stream>>>(acc_b2, gr.db2, H2); MI_LAUNCH_CHECK("copy_f32_kernel"); }
+    if (gr.db3) { sum_reduce_kernel<<<1, 1024, 0, stream>>>(G, B * B, gr.db3); MI_LAUNCH_CHECK("sum_reduce_kernel"); }
+    if (gr.db1) { colsum_kernel<<<blocks_for(H1, 128), 128, 0, stream>>>(dA32, B, H1, gr.db1); MI_LAUNCH_CHECK("colsum_kernel"); }
+    MI_TRY(split(dA32, H1, dA16, pH, Hp, B, H1));
+    MI_TRY(split(dC32, H1, dC16, pH, Hp, B, H1));
+  }
+  // ---- layer 1 backward
+  for (int side = 0; side < 2; ++side) {
+    float* dIn = side == 0 ? gr.dX : gr.dY;
+    bf* dAc = side == 0 ? dA16 : dC16;
+    bf* Wside = side == 0 ? W1x : W1y;
+    bf* In16 = side == 0 ? X16 : Y16;
+    if (dIn || dry) {   // dX = dA W1x : W1x [H1, D] read in place as the MN-major B operand
+      GemmArgs g;
+      g.a = MapSpec{dAc, B, eH, pH};
+      g.b_mn = true; g.b = MapSpec{Wside, H1, eX, pX};
+      g.M = B; g.N = D;
+      const int kb = static_cast<int>(sp == 2 ? Hp / bk() : cdiv(H1, bk()));
+      g.k_blocks = kb; g.seg_len = kb;
+      if (sp == 2) { g.k_blocks = 3 * kb; g.a_seg[1] = kb; g.b_noff[2] = static_cast<int>(Dp); }
+      g.out_f32 = dIn; g.ld_out = D;
+      if (dry) { g.out_f32 = reinterpret_cast<float*>(16); }
+      MI_TRY(run_gemm(g, ws, stream));
+      ws.release(mk);
+    }
+    if (gr.dW1 || dry) {   // dW1[:, side] = dA^T X : contraction over the batch, both operands MN-major
+      GemmArgs g;
+      const int kb = static_cast<int>(cdiv(B, bk()));
+      g.a_mn = true; g.a = MapSpec{dAc, B, eH, pH};
+      g.b_mn = true; g.b = MapSpec{In16, B, eX, pX};
+      g.M = H1; g.N = D; g.k_blocks = kb; g.seg_len = kb;
+      if (sp == 2) { g.k_blocks = 3 * kb; g.a_moff[1] = static_cast<int>(Hp); g.b_noff[2] = static_cast<int>(Dp); }
+      const long long tiles = cdiv(H1, rows_per_mblk()) * cdiv(D, mi::TILE_N);
+      long long ks = cdiv(num_pairs(), tiles);
+      if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
+      if (ks < 1) ks = 1;
+      g.ksplit = static_cast<int>(ks);
+      g.out_f32 = gr.dW1 ? gr.dW1 + side * D : nullptr; g.ld_out = 2 * D;
+      if (dry) { g.out_f32 = reinterpret_cast<float*>(16); }
+      MI_TRY(run_gemm(g, ws, stream));
+      ws.release(mk);
+    }
+  }
+  return MI_OK;
+}
+
 int device_check() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return MI_ERR_NO_DEVICE; }
@@ -1267,6 +1670,7 @@ int mi_profile_read(double* ms, int64_t* launches) {
 void mi_set_debug(int v) { g_debug = v; }
 void mi_set_single_pass(int on) { g_single_pass = on != 0; }
 void mi_set_mn_operands(int on) { g_mn_operands = on != 0; }
+void mi_set_mlp_panel_pairs(int64_t pairs) { g_mlp_max_pairs = pairs > 0 ? pairs : (1LL << 19); }
 void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
 int mi_get_cta_group(void) { return cta_group(); }
 
@@ -1475,6 +1879,24 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
   if (dW_host && bilinear) MI_CUDA(cudaMemcpyAsync(dW_host, dW, nDD * 4, cudaMemcpyDeviceToHost, stream));
   MI_CUDA(cudaStreamSynchronize(stream));
   return MI_OK;
+}
+
+size_t mi_mlp_critic_workspace_bytes(int64_t B, int64_t D, int64_t H1, int64_t H2, int precision) {
+  Bump ws(nullptr, 0, true);
+  MlpParams prm{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  MlpGrads gr{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (mlp_impl(nullptr, nullptr, prm, nullptr, MlpDims{B, D, H1, H2}, MI_EST_DV, precision, nullptr, nullptr, gr, ws, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_mlp_critic_loss_fwd_bwd(const float* X, const float* Y, const float* W1, const float* b1, const float* W2, const float* b2,
+                               const float* W3, const float* b3, const int32_t* sid,
+                               int64_t B, int64_t D, int64_t H1, int64_t H2, int estimator, int precision,
+                               double* loss_out, float* S_out, float* dX, float* dY, float* dW1, float* db1, float* dW2, float* db2,
+                               float* dW3, float* db3, void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+  MI_TRY(device_check());
+  Bump ws(workspace, workspace_bytes, false);
+  return mlp_impl(X, Y, MlpParams{W1, b1, W2, b2, W3, b3}, sid, MlpDims{B, D, H1, H2}, estimator, precision, loss_out, S_out,
+                  MlpGrads{dX, dY, dW1, db1, dW2, db2, dW3, db3}, ws, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

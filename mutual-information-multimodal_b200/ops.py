@@ -332,5 +332,47 @@ def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tens
     return loss, dX, dY, dW
 
 
+MLP_PARAMS = ("W1", "b1", "W2", "b2", "W3", "b3")
+
+
+def mlp_critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, params, sid: torch.Tensor, estimator: str = "dv",
+                            precision: str = "fast", need_grads: bool = True, want_scores: bool = False):
+    """The reference's own critic make_mlp(2D, [H1, H2]) (model.py:18-32) on every pair + estimator, fwd+bwd
+    (mi_mlp_critic_loss_fwd_bwd).  ``params`` = (W1 [H1,2D], b1, W2 [H2,H1], b2, W3 [1,H2], b3) fp32.
+    Returns (loss_out fp64[8], S or None, grads dict with keys dX, dY, dW1 ... db3 (or None))."""
+    _need_cuda(X, Y, sid, *params)
+    lib = _lib.load()
+    f32 = lambda t: t.detach().to(torch.float32).contiguous()
+    X, Y = f32(X), f32(Y)
+    W1, b1, W2, b2, W3, b3 = (f32(t) for t in params)
+    B, D = X.shape
+    H1, H2 = W1.shape[0], W2.shape[0]
+    if W1.shape != (H1, 2 * D) or W2.shape != (H2, H1) or W3.numel() != H2 or b1.numel() != H1 or b2.numel() != H2 or b3.numel() != 1:
+        raise MIError("MLP critic parameters do not have the make_mlp(2D, [H1, H2]) shapes")
+    if estimator not in ("dv", "infonce", "infonce_ref", "infonce_row"):
+        raise MIError("the MLP critic supports the dv, infonce and infonce_row estimators")
+    sid = sid.to(torch.int32).contiguous()
+    est, prec = ESTIMATOR[estimator], PRECISION[precision]
+    dev = X.device
+    loss = torch.empty(8, dtype=torch.float64, device=dev)
+    S = torch.empty((B, B), dtype=torch.float32, device=dev) if want_scores else None
+    grads = None
+    if need_grads:
+        shapes = {"dX": (B, D), "dY": (B, D), "dW1": (H1, 2 * D), "db1": (H1,), "dW2": (H2, H1), "db2": (H2,),
+                  "dW3": (1, H2), "db3": (1,)}
+        grads = {k: torch.empty(v, dtype=torch.float32, device=dev) for k, v in shapes.items()}
+    g = grads or {}
+    nbytes = lib.mi_mlp_critic_workspace_bytes(B, D, H1, H2, prec)
+    if nbytes == 0:
+        raise MIError("mi_mlp_critic_workspace_bytes: unsupported shape (D, H1, H2 multiples of 8, H2 <= 512)")
+    ws = workspace(nbytes, dev)
+    _check(lib.mi_mlp_critic_loss_fwd_bwd(_ptr(X), _ptr(Y), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), _ptr(W3), _ptr(b3), _ptr(sid),
+                                          B, D, H1, H2, est, prec, _ptr(loss), _ptr(S),
+                                          _ptr(g.get("dX")), _ptr(g.get("dY")), _ptr(g.get("dW1")), _ptr(g.get("db1")),
+                                          _ptr(g.get("dW2")), _ptr(g.get("db2")), _ptr(g.get("dW3")), _ptr(g.get("db3")),
+                                          _ptr(ws), ws.numel(), _stream()), "mi_mlp_critic_loss_fwd_bwd")
+    return loss, S, grads
+
+
 def launch_count() -> int:
     return int(_lib.load().mi_launch_count())
