@@ -73,6 +73,15 @@ int mi_gemm_bf16(const void* A, int64_t lda, int a_split, const void* B, int64_t
                  float* out_f32, int64_t ld_out, void* out_bf16, int64_t ld_out16, int out_split,
                  mi_stream_t stream);
 
+/* C[M,N] = sum_k A(m,k) B(n,k) where an operand with *_mn = 1 is given as the row-major [K, rows] matrix
+ * (A(m,k) = A[k*lda + m]) and read IN PLACE through MN-major UMMA shared-memory descriptors — X^T dT, X W and
+ * dA W1 need no transposed copies.  *_split = 2: hi/lo pair, lo at column round_up(K,128) (K-major) or
+ * round_up(rows,128) (MN-major).  fp32 outputs of few tiles and long K use split-K (partials in `workspace`). */
+size_t mi_gemm_bf16_mn_workspace_bytes(int64_t M, int64_t N, int64_t K, int a_split, int a_mn, int b_split, int b_mn);
+int mi_gemm_bf16_mn(const void* A, int64_t lda, int a_split, int a_mn, const void* B, int64_t ldb, int b_split, int b_mn,
+                    int64_t M, int64_t N, int64_t K, float* out_f32, int64_t ld_out, void* out_bf16, int64_t ld_out16, int out_split,
+                    void* workspace, size_t workspace_bytes, mi_stream_t stream);
+
 /* out[C,R] = in[R,C]^T (bf16) */
 int mi_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, mi_stream_t stream);
 /* out = bf16(in), n elements */
@@ -190,6 +199,10 @@ int mi_profile_read(double* ms /*[3]*/, int64_t* launches /*[3]*/);
  * Also settable through the environment variable MI_CTA_GROUP before the first call. */
 void mi_set_cta_group(int group);
 void mi_set_mlp_panel_pairs(int64_t pairs); /* pairs per row panel of the MLP-critic path (default 2^19; tests use small values) */
+/* Multi-GPU overlap: the tile-engine launches that follow `event_after_outk` inside mi_score_single_pass / mi_score_grad
+ * use (SM count - n) SMs, so the collective the caller starts at that event (reduce-scatter of the dY contributions)
+ * finds free SMs instead of queueing behind a persistent 148-CTA grid.  0 (default) = use every SM. */
+void mi_set_overlap_reserve_sms(int n);
 void mi_set_debug(int value);          /* experiments only */
 void mi_set_single_pass(int on);       /* 0: mi_critic_loss_fwd_bwd always takes the two-pass path */
 void mi_set_mn_operands(int on);       /* 0: transpose row-major [K,N] operands into K-major copies instead of reading

@@ -22,10 +22,14 @@ PROTOTYPES = {
     "mi_set_debug": (None, [c_int]),
     "mi_set_single_pass": (None, [c_int]),
     "mi_set_mn_operands": (None, [c_int]),
+    "mi_set_overlap_reserve_sms": (None, [c_int]),
     "mi_set_mlp_panel_pairs": (None, [c_i64]),
     "mi_get_cta_group": (c_int, []),
     "mi_gemm_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_i64,
                              c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
+    "mi_gemm_bf16_mn_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int]),
+    "mi_gemm_bf16_mn": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_i64,
+                                c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
     "mi_transpose_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "mi_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "mi_score_stats_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),

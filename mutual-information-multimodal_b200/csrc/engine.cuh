@@ -260,13 +260,17 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           uint32_t v[32];
           ptx::tmem_ld_32x32(taddr, v);
           ptx::tmem_ld_wait();
+          if (c == 1) {
+            // this warp's last read of the accumulator stage is in registers: hand the stage back to the MMA
+            // issuer BEFORE the chunk is processed, so the MMAs of tile t+2 never wait for epilogue math / stores
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCG == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
+              else ptx::mbar_arrive_remote(&tmem_empty_bar[as], 0);
+            }
+          }
           Epi::chunk(ep, st, un, row, nt * TILE_N + (int)col_in_tile, v);
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (kCG == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
-          else ptx::mbar_arrive_remote(&tmem_empty_bar[as], 0);
         }
         ++tile_cnt;
       }

@@ -23,6 +23,8 @@ thread_local char g_cuda_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_debug = 0;
 int g_cta_group = -1;   // resolved lazily: env MI_CTA_GROUP or 2
+int g_overlap_reserve_sms = 0;  // SMs left free for a concurrent collective by the engine launches that follow event_after_outk
+thread_local int t_reserve_sms = 0;   // applied to the next engine launches of this thread
 bool g_mn_operands = true;   // read row-major [K, N] / [K, M] operands in place (MN-major descriptors) instead of transposing them
 
 // optional per-launch CUDA-event timing of the tile-engine kernels (bench.py's roofline breakdown)
@@ -150,7 +152,7 @@ int launch_engine_cg(const MapSpec& a, const MapSpec& b, const Sched& sc, const 
     attr_set = true;
   }
   const int units = sc.n_mblk * sc.n_split * sc.n_ksplit;
-  int pairs = num_sms() / kCG;
+  int pairs = (num_sms() - t_reserve_sms) / kCG;
   if (pairs > units) pairs = units;
   if (pairs < 1) pairs = 1;
   cudaLaunchConfig_t cfg;
@@ -676,6 +678,39 @@ int gemm_impl(const Opnd& A, const Opnd& B, long long M, long long N, long long 
   return run_gemm(g, ws, stream);
 }
 
+// C = A B^T with either operand stored K-major ([rows, K]) or MN-major (row-major [K, rows], read in place through
+// MN-major UMMA descriptors — no transposed copy); hi/lo operands add the cross terms as K segments.
+// ksplit = 0: split-K chosen from the tile count (fp32 output only).
+int gemm_mn_impl(const Opnd& A, bool a_mn, const Opnd& B, bool b_mn, long long M, long long N, long long K,
+                 float* out_f32, long long ld_out, void* out_bf16, long long ld_out16, int out_split, int ksplit,
+                 Bump& ws, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return MI_ERR_BAD_ARG;
+  GemmArgs g;
+  const bool a_sp = A.split == 2, b_sp = B.split == 2;
+  const bool k_pad = (a_sp && !a_mn) || (b_sp && !b_mn);          // a K-major hi/lo pair fixes the lo offset at round_up(K, 128)
+  const int kb = static_cast<int>(k_pad ? round_up(K, kSplitAlign) / bk() : cdiv(K, bk()));
+  const long long Mp = round_up(M, kSplitAlign), Np = round_up(N, kSplitAlign);
+  g.a_mn = a_mn; g.b_mn = b_mn;
+  g.a = a_mn ? MapSpec{A.p, K, a_sp ? Mp + M : M, A.ld} : MapSpec{A.p, M, opnd_k_extent(A, K), A.ld};
+  g.b = b_mn ? MapSpec{B.p, K, b_sp ? Np + N : N, B.ld} : MapSpec{B.p, N, opnd_k_extent(B, K), B.ld};
+  g.M = M; g.N = N; g.seg_len = kb;
+  int seg = 1;
+  if (a_sp) { if (a_mn) g.a_moff[seg] = static_cast<int>(Mp); else g.a_seg[seg] = kb; ++seg; }      // A_lo B_hi
+  if (b_sp) { if (b_mn) g.b_noff[seg] = static_cast<int>(Np); else g.b_seg[seg] = kb; ++seg; }      // A_hi B_lo
+  g.k_blocks = seg * kb;
+  if (ksplit == 0) {
+    const long long tiles = cdiv(M, rows_per_mblk()) * cdiv(N, mi::TILE_N);
+    long long ks = (out_f32 && !out_bf16) ? cdiv(num_pairs(), tiles) : 1;
+    if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
+    ksplit = static_cast<int>(ks < 1 ? 1 : ks);
+  }
+  g.ksplit = ksplit;
+  g.out_f32 = out_f32; g.ld_out = ld_out;
+  g.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); g.ld_out16 = ld_out16;
+  g.out_bf16_lo = (out_split == 2 && out_bf16) ? g.out_bf16 + Np : nullptr;
+  return run_gemm(g, ws, stream);
+}
+
 int transpose_impl(const void* in, long long ld_in, void* out, long long ld_out, long long R, long long C, cudaStream_t stream) {
   if (!in || !out || R <= 0 || C <= 0) return MI_ERR_BAD_ARG;
   dim3 grid(static_cast<unsigned>(cdiv(C, 64)), static_cast<unsigned>(cdiv(R, 64)));
@@ -867,7 +902,10 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
       g.out_f32 = ok->f32; g.ld_out = ok->ld;
       MI_TRY(run_gemm(g, none, stream));
       // the K-side output is complete after the last panel: let the caller start its reduce-scatter here
-      if (ev_after_k != nullptr && r0 + panel_rows >= Bq) MI_CUDA(cudaEventRecord(ev_after_k, stream));
+      if (ev_after_k != nullptr && r0 + panel_rows >= Bq) {
+        MI_CUDA(cudaEventRecord(ev_after_k, stream));
+        t_reserve_sms = g_overlap_reserve_sms;
+      }
     }
     // (3) Oq[panel] = alpha (P V - gamma SUB), contraction over the Bk columns
     if (oq.f32 || oq.bf16) {
@@ -891,7 +929,9 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
       g.out_f32 = oq.f32 ? oq.f32 + r0 * oq.ld : nullptr; g.ld_out = oq.ld;
       g.out_bf16 = oq.bf16 ? oq.bf16 + r0 * oq.ld16 : nullptr; g.ld_out16 = oq.ld16;
       g.out_bf16_lo = (oq.bf16 && oq.split == 2) ? g.out_bf16 + Dp : nullptr;
-      MI_TRY(run_gemm(g, none, stream));
+      const int st = run_gemm(g, none, stream);
+      t_reserve_sms = 0;
+      MI_TRY(st);
     }
   }
   return MI_OK;
@@ -1024,7 +1064,10 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
       g.accumulate = r0 > 0;
       g.out_f32 = ok_raw; g.ld_out = D;
       MI_TRY(run_gemm(g, none, stream));
-      if (ev_after_k != nullptr && r0 + panel_rows >= Bq) MI_CUDA(cudaEventRecord(ev_after_k, stream));
+      if (ev_after_k != nullptr && r0 + panel_rows >= Bq) {
+        MI_CUDA(cudaEventRecord(ev_after_k, stream));
+        t_reserve_sms = g_overlap_reserve_sms;      // the caller's collective starts here: leave it some SMs
+      }
     }
     // (3) Oq_raw[panel] = P~ K
     {
@@ -1041,7 +1084,9 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
         }
       }
       g.out_f32 = oq_raw + r0 * D; g.ld_out = D;
-      MI_TRY(run_gemm(g, none, stream));
+      const int st = run_gemm(g, none, stream);
+      t_reserve_sms = 0;
+      MI_TRY(st);
     }
   }
   return MI_OK;
@@ -1670,6 +1715,7 @@ int mi_profile_read(double* ms, int64_t* launches) {
 void mi_set_debug(int v) { g_debug = v; }
 void mi_set_single_pass(int on) { g_single_pass = on != 0; }
 void mi_set_mn_operands(int on) { g_mn_operands = on != 0; }
+void mi_set_overlap_reserve_sms(int n) { g_overlap_reserve_sms = (n > 0 && n < 128) ? (n & ~1) : 0; }
 void mi_set_mlp_panel_pairs(int64_t pairs) { g_mlp_max_pairs = pairs > 0 ? pairs : (1LL << 19); }
 void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
 int mi_get_cta_group(void) { return cta_group(); }
@@ -1683,6 +1729,22 @@ int mi_gemm_bf16(const void* A, int64_t lda, int a_split, const void* B, int64_t
   return gemm_impl(Opnd{static_cast<const __nv_bfloat16*>(A), lda, a_split == 2 ? 2 : 1},
                    Opnd{static_cast<const __nv_bfloat16*>(B), ldb, b_split == 2 ? 2 : 1}, M, N, K, alpha, gamma, sub, ld_sub,
                    out_f32, ld_out, out_bf16, ld_out16, out_split, 1, ws, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t mi_gemm_bf16_mn_workspace_bytes(int64_t M, int64_t N, int64_t K, int a_split, int a_mn, int b_split, int b_mn) {
+  Bump ws(nullptr, 0, true);
+  if (gemm_mn_impl(Opnd{nullptr, 8, a_split == 2 ? 2 : 1}, a_mn != 0, Opnd{nullptr, 8, b_split == 2 ? 2 : 1}, b_mn != 0, M, N, K,
+                   reinterpret_cast<float*>(16), N, nullptr, 0, 1, 0, ws, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_gemm_bf16_mn(const void* A, int64_t lda, int a_split, int a_mn, const void* B, int64_t ldb, int b_split, int b_mn,
+                    int64_t M, int64_t N, int64_t K, float* out_f32, int64_t ld_out, void* out_bf16, int64_t ld_out16, int out_split,
+                    void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+  MI_TRY(device_check());
+  Bump ws(workspace, workspace_bytes, false);
+  return gemm_mn_impl(Opnd{static_cast<const __nv_bfloat16*>(A), lda, a_split == 2 ? 2 : 1}, a_mn != 0,
+                      Opnd{static_cast<const __nv_bfloat16*>(B), ldb, b_split == 2 ? 2 : 1}, b_mn != 0, M, N, K,
+                      out_f32, ld_out, out_bf16, ld_out16, out_split, 0, ws, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mi_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, mi_stream_t stream) {

@@ -20,6 +20,7 @@ gloo tests inject an emulation to exercise the sharding / collective logic witho
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -139,7 +140,7 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
     dX, dW = dT32, None
     if bilinear:
         dX = backend.gemm(dT16, Wb)
-        dW = backend.gemm(backend.transpose(Xb), backend.transpose(dT16))
+        dW = backend.gemm(Xb, dT16, a_t=True, b_t=True)          # X^T dT, both operands read in place
         if world > 1:
             dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group)
     if rs_work is not None:
@@ -173,7 +174,7 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     if world > 1:
         Y_all = torch.empty((Bg, D), dtype=Yb.dtype, device=Yb.device)
         y_work = dist.all_gather_into_tensor(Y_all, Yb, group=group, async_op=True)
-    T_local = backend.gemm(Xb, backend.transpose(Wb), out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb
+    T_local = backend.gemm(Xb, Wb, b_t=True, out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb   # X W, W in place
     single = need_grads and not sym and not two_pass
     qmax = None
     if single:                                        # largest |T_i| over ALL ranks: the global constant of the bound
@@ -190,6 +191,10 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     sid_loc = sid_all[off:off + Bl].contiguous()
 
     nccl = world > 1 and dist.get_backend(group) != "gloo"
+    if nccl and hasattr(backend, "set_overlap_reserve_sms"):
+        # the reduce-scatter of the dY contributions starts from an in-pass event; NCCL's CTAs cannot co-reside with
+        # the engine's (one CTA per SM, all of its shared memory), so the launches after that event leave SMs free
+        backend.set_overlap_reserve_sms(int(os.environ.get("MI_RS_RESERVE_SMS", "16")))
     if single:
         return _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
                                  precision, qmax, world, group, nccl)
@@ -257,7 +262,7 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     dX, dW = dT32, None
     if bilinear:
         dX = backend.gemm(dT16, Wb)                                               # dT W^T
-        dW = backend.gemm(backend.transpose(Xb), backend.transpose(dT16))         # X^T dT (local rows)
+        dW = backend.gemm(Xb, dT16, a_t=True, b_t=True)                           # X^T dT (local rows), operands in place
         if world > 1:
             dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group)
     if rs_work is not None:

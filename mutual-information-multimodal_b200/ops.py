@@ -117,11 +117,40 @@ def as_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _gemm_mn(A: Mat, B: Mat, a_t: bool, b_t: bool, out_dtype, out_split: bool):
+    At, lda, asp, wa = _opnd(A)
+    Bt, ldb, bsp, wb = _opnd(B)
+    K = At.shape[0] if a_t else wa
+    assert K == (Bt.shape[0] if b_t else wb), "inner dimensions differ"
+    M = wa if a_t else At.shape[0]
+    N = wb if b_t else Bt.shape[0]
+    of = ob = None
+    ld16 = 0
+    if out_split:
+        res = new_split(M, N, At.device)
+        ob, ld16 = res.data, res.data.stride(0)
+    elif out_dtype == torch.bfloat16:
+        res = torch.empty((M, N), dtype=torch.bfloat16, device=At.device)
+        ob, ld16 = res, N
+    else:
+        res = torch.empty((M, N), dtype=torch.float32, device=At.device)
+        of = res
+    lib = _lib.load()
+    ws = workspace(lib.mi_gemm_bf16_mn_workspace_bytes(M, N, K, asp, int(a_t), bsp, int(b_t)), At.device)
+    _check(lib.mi_gemm_bf16_mn(_ptr(At), lda, asp, int(a_t), _ptr(Bt), ldb, bsp, int(b_t), M, N, K, _ptr(of), N, _ptr(ob), ld16,
+                               2 if out_split else 1, _ptr(ws), ws.numel(), _stream()), "mi_gemm_bf16_mn")
+    return res
+
+
 def gemm(A: Mat, B: Mat, alpha: float = 1.0, gamma: float = 0.0, sub: Optional[torch.Tensor] = None,
-         out_dtype=torch.float32, out_split: bool = False):
+         out_dtype=torch.float32, out_split: bool = False, a_t: bool = False, b_t: bool = False):
     """C = alpha * (A @ B.T - gamma * sub); A [M,K], B [N,K] bf16 (plain or hi/lo).  ``out_split``
-    returns a SplitBF16."""
+    returns a SplitBF16.  ``a_t`` / ``b_t``: the operand is given as the row-major [K, M] / [K, N] matrix and is
+    read in place (MN-major descriptors) — ``gemm(X, dT, a_t=True, b_t=True)`` is X^T dT without transposes."""
     _need_cuda(A, B, sub)
+    if a_t or b_t:
+        assert alpha == 1.0 and gamma == 0.0 and sub is None
+        return _gemm_mn(A, B, a_t, b_t, out_dtype, out_split)
     At, lda, asp, K = _opnd(A)
     Bt, ldb, bsp, Kb = _opnd(B)
     assert K == Kb, "inner dimensions differ"
@@ -372,6 +401,11 @@ def mlp_critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, params, sid: torch
                                           _ptr(g.get("dW2")), _ptr(g.get("db2")), _ptr(g.get("dW3")), _ptr(g.get("db3")),
                                           _ptr(ws), ws.numel(), _stream()), "mi_mlp_critic_loss_fwd_bwd")
     return loss, S, grads
+
+
+def set_overlap_reserve_sms(n: int) -> None:
+    """SMs the engine leaves free after the dY contributions are complete (mi_set_overlap_reserve_sms)."""
+    _lib.load().mi_set_overlap_reserve_sms(int(n))
 
 
 def launch_count() -> int:

@@ -8,8 +8,9 @@ def as_bf16(x):
     return x.detach().double().contiguous()      # exact arithmetic: isolates the collective logic
 
 
-def gemm(A, B, alpha=1.0, gamma=0.0, sub=None, out_dtype=torch.float32, out_split=False):
-    C = A.double() @ B.double().t()
+def gemm(A, B, alpha=1.0, gamma=0.0, sub=None, out_dtype=torch.float32, out_split=False, a_t=False, b_t=False):
+    A, B = A.double(), B.double()
+    C = (A.t() if a_t else A) @ (B if b_t else B.t())
     if sub is not None:
         C = C - gamma * sub.double()
     return alpha * C                           # no rounding, whatever out_dtype / out_split ask for
