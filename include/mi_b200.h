@@ -140,7 +140,15 @@ int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K,
                          const float* qnorm_max_in, float* row_out /*[Bq,4]*/, double* scal_out /*[8]*/,
                          float* oq_raw /*[Bq,D]*/, float* ok_raw /*[Bk,D] or NULL*/,
                          float* rho /*[Bq]*/, float* wrow /*[Bq]*/, float* lambda_out /*[1]*/, int32_t* flag_out /*[1]*/,
-                         void* event_after_outk, void* workspace, size_t workspace_bytes, mi_stream_t stream);
+                         void* event_after_outk,
+                         void* event_after_scal /* cudaEvent_t or NULL: recorded once row_out / scal_out are final, i.e. BEFORE the
+                                                   last panel's two contractions — exchange the loss scalars under them */,
+                         void* workspace, size_t workspace_bytes, mi_stream_t stream);
+/* Multi-GPU glue: the ranks' scal_out rows [world][8] (all-gathered) -> loss_out (fp64[8], layout of mi_critic_loss_fwd_bwd,
+ * global batch B_global, estimators DV / INFONCE_REF / INFONCE_ROW) and the global log-sum-exp as a float (lse_out[1]).
+ * Two tiny kernels instead of a chain of framework ops.  scratch8: 8 doubles of device scratch. */
+int mi_merge_scalars(const double* scal_all, int world, int64_t B_global, int estimator, double* loss_out, float* lse_out,
+                     double* scratch8, mi_stream_t stream);
 int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const float* rho, const float* wrow, const float* lse,
                          int dv_like, float alpha, float gamma, const void* kdiag, int64_t ldk, int k_split,
                          float* out_f32, void* out_bf16, int64_t ld16, int out_split, mi_stream_t stream);

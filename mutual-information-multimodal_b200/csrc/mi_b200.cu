@@ -526,6 +526,20 @@ __global__ void stats_reduce_kernel(const float4* __restrict__ row_out, int q_ro
   }
 }
 
+// ranks' reduced scalars [world][8] -> one row of the same layout (global max / rescaled sum-exp, plain sums)
+__global__ void merge_scal_kernel(const double* __restrict__ scal_all, int world, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double gm = -INFINITY;
+  for (int r = 0; r < world; ++r) gm = fmax(gm, scal_all[r * 8]);
+  double s = 0, t[4] = {0, 0, 0, 0};
+  for (int r = 0; r < world; ++r) {
+    const double* v = scal_all + r * 8;
+    if (isfinite(v[0])) s += v[1] * exp(v[0] - gm);
+    for (int k = 0; k < 4; ++k) t[k] += v[2 + k];
+  }
+  out[0] = gm; out[1] = s; out[2] = t[0]; out[3] = t[1]; out[4] = t[2]; out[5] = t[3]; out[6] = 0; out[7] = 0;
+}
+
 // fused single-GPU glue: loss from the reduced scalars (fp64), and the scalar references as floats
 // loss_out = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, rows w/o negatives, 0 }
 __global__ void loss_finalize_kernel(const double* __restrict__ scal_row, const double* __restrict__ scal_col,
@@ -952,7 +966,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                      int include_diag, int precision, float inv_bg, const float* qmax_in,
                      float* row_out, float* oq_raw, float* ok_raw,
                      float* rho, float* wrow, float* lambda_out, int* flag_out, Bump& ws, cudaStream_t stream,
-                     cudaEvent_t ev_after_k = nullptr) {
+                     cudaEvent_t ev_after_k = nullptr, double* scal_out = nullptr, cudaEvent_t ev_after_scal = nullptr) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
   const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
@@ -1037,6 +1051,13 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                                                                 include_diag, inv_bg, reinterpret_cast<float4*>(row_out) + r0,
                                                                 lsum + r0, wrow + r0, flag_out);
     MI_LAUNCH_CHECK("sum_merge_kernel");
+    if (scal_out != nullptr && r0 + panel_rows >= Bq) {
+      // every row's statistics are final once the last panel's sums are merged: reduce them NOW (before the two
+      // contractions of this panel) so a caller can exchange the scalars of the loss while the GEMMs still run
+      stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out);
+      MI_LAUNCH_CHECK("stats_reduce_kernel");
+      if (ev_after_scal != nullptr) MI_CUDA(cudaEventRecord(ev_after_scal, stream));
+    }
     Bump none(nullptr, 0, false);
     // (2) Ok_raw += P~^T (w Q)[panel]: contraction over the panel rows, P~ read MN-major
     if (ok_raw) {
@@ -1168,11 +1189,9 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     float* oq_raw = sp_oq ? sp_oq : dX;
     float* ok_raw = dY ? dY : sp_ok;
     MI_TRY(single_pass_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, precision, gam, nullptr,
-                            rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream));
+                            rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream, nullptr, scal_r));
     ws.release(mk);
     if (!ws.dry) {
-      stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(rows_r), static_cast<int>(B), scal_r);
-      MI_LAUNCH_CHECK("stats_reduce_kernel");
       loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, nullptr, B, estimator, loss_out, lse_f);
       MI_LAUNCH_CHECK("loss_finalize_kernel");
       flag_to_loss_kernel<<<1, 1, 0, stream>>>(sp_flag, loss_out);
@@ -1694,7 +1713,7 @@ const char* mi_status_string(int status) {
   }
 }
 const char* mi_last_cuda_error(void) { return g_cuda_err; }
-int mi_abi_version(void) { return 2; }
+int mi_abi_version(void) { return 3; }
 int mi_device_check(void) { return device_check(); }
 int64_t mi_launch_count(void) { return g_launches.load(); }
 void mi_set_profiling(int on) { g_profiling = on != 0; }
@@ -1834,7 +1853,7 @@ int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K,
                          int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag, int precision, float inv_bg,
                          const float* qnorm_max_in, float* row_out, double* scal_out, float* oq_raw, float* ok_raw,
                          float* rho, float* wrow, float* lambda_out, int32_t* flag_out, void* event_after_outk,
-                         void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
+                         void* event_after_scal, void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
   MI_TRY(device_check());
   if (q_offset < 0 || q_offset + Bq > Bk || !scal_out) return MI_ERR_BAD_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -1843,9 +1862,19 @@ int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K,
                           Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
                           sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, precision, inv_bg, qnorm_max_in,
                           row_out, oq_raw, ok_raw, rho, wrow, lambda_out, flag_out, ws, stream,
-                          reinterpret_cast<cudaEvent_t>(event_after_outk)));
-  stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out);
-  MI_LAUNCH_CHECK("stats_reduce_kernel");
+                          reinterpret_cast<cudaEvent_t>(event_after_outk), scal_out, reinterpret_cast<cudaEvent_t>(event_after_scal)));
+  return MI_OK;
+}
+int mi_merge_scalars(const double* scal_all, int world, int64_t B_global, int estimator, double* loss_out, float* lse_out,
+                     double* scratch8, mi_stream_t stream_) {
+  MI_TRY(device_check());
+  if (!scal_all || world <= 0 || !loss_out || !lse_out || !scratch8 || estimator < MI_EST_DV || estimator > MI_EST_INFONCE_ROW)
+    return MI_ERR_BAD_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  merge_scal_kernel<<<1, 32, 0, stream>>>(scal_all, world, scratch8);
+  MI_LAUNCH_CHECK("merge_scal_kernel");
+  loss_finalize_kernel<<<1, 32, 0, stream>>>(scratch8, nullptr, B_global, estimator, loss_out, lse_out);
+  MI_LAUNCH_CHECK("loss_finalize_kernel");
   return MI_OK;
 }
 int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const float* rho, const float* wrow, const float* lse,

@@ -108,12 +108,30 @@ def _reduce_scatter_rows(part, Bl, off, world, group, nccl, ev):
         return part[off:off + Bl].contiguous(), None
     side = _side_stream(part.device)
     side.wait_event(ev)
+    if os.environ.get("MI_DY_EXCHANGE", "rs") == "a2a":
+        # all-to-all of the per-destination slabs (plain NVLink copies) + a local sum, instead of a ring reduce-scatter
+        recv = torch.empty_like(part)
+        with torch.cuda.stream(side):
+            work = dist.all_to_all_single(recv, part, group=group, async_op=True)
+        part.record_stream(side)
+        recv.record_stream(side)
+        return _A2ASum(recv.view(world, Bl, part.shape[1])), work
     out = torch.empty((Bl, part.shape[1]), dtype=part.dtype, device=part.device)
     with torch.cuda.stream(side):
         work = dist.reduce_scatter_tensor(out, part, op=dist.ReduceOp.SUM, group=group, async_op=True)
     part.record_stream(side)
     out.record_stream(side)
     return out, work
+
+
+class _A2ASum:
+    """The received slabs [world, Bl, D]; summed after the collective has completed."""
+
+    def __init__(self, slabs):
+        self.slabs = slabs
+
+    def resolve(self):
+        return self.slabs.sum(0)
 
 
 def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
@@ -123,18 +141,38 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
     strict = precision == "strict"
     dv_like = estimator != "infonce_row"
     gamma = 1.0 / Bg
-    ev = None
+    ev = ev_s = None
     if nccl:
-        ev = torch.cuda.Event()
-        ev.record()
+        ev, ev_s = torch.cuda.Event(), torch.cuda.Event()
+        ev.record(); ev_s.record()                    # (creates the CUDA events; the library re-records them in the pass)
     sp = backend.score_single_pass(T_local, Y_all, sid_loc, sid_all, off, inv_tau, not dv_like, precision, gamma,
-                                   qmax=qmax, want_k=True, event_after_k=ev)
-    dY, rs_work = _reduce_scatter_rows(sp["ok_raw"], Bl, off, world, group, nccl, ev)
-    g = merge_scalars(_all_gather_rows(sp["scal"].reshape(1, 8), world, group))
-    out = {"pos_mean": g["diag_sum"] / Bg, "lse_neg": g["lse_neg"], "n_neg": g["n_neg"], "loss_row": g["rowloss_sum"] / Bg,
-           "loose_reference_rows": sp["flag"]}
-    out["loss"] = _loss_from(out, estimator)
-    lse32 = out["lse_neg"].to(torch.float32).reshape(1)
+                                   qmax=qmax, want_k=True, event_after_k=ev, **({"event_after_scal": ev_s} if nccl else {}))
+    scal = sp["scal"].reshape(1, 8)
+    if nccl:
+        # the loss scalars are final BEFORE the panel's two contractions: exchange them first, then start the big
+        # reduce-scatter — both from the side stream, so NCCL runs them in this order under the GEMMs and the
+        # finalisation that follows never queues behind the reduce-scatter
+        side = _side_stream(scal.device)
+        scal_all = torch.empty((world, 8), dtype=scal.dtype, device=scal.device)
+        side.wait_event(ev_s)
+        with torch.cuda.stream(side):
+            s_work = dist.all_gather_into_tensor(scal_all, scal, group=group, async_op=True)
+        scal.record_stream(side)
+        scal_all.record_stream(side)
+        dY, rs_work = _reduce_scatter_rows(sp["ok_raw"], Bl, off, world, group, nccl, ev)
+        s_work.wait()
+    else:
+        dY, rs_work = _reduce_scatter_rows(sp["ok_raw"], Bl, off, world, group, nccl, ev)
+        scal_all = _all_gather_rows(scal, world, group)
+    if hasattr(backend, "merge_scalars_loss"):        # two tiny kernels instead of ~25 framework ops
+        out = backend.merge_scalars_loss(scal_all, estimator, Bg)
+        lse32 = out.pop("lse32")
+    else:
+        g = merge_scalars(scal_all)
+        out = {"pos_mean": g["diag_sum"] / Bg, "lse_neg": g["lse_neg"], "n_neg": g["n_neg"], "loss_row": g["rowloss_sum"] / Bg}
+        out["loss"] = _loss_from(out, estimator)
+        lse32 = out["lse_neg"].to(torch.float32).reshape(1)
+    out["loose_reference_rows"] = sp["flag"]
     dT32, dT16 = backend.single_finalize_q(sp["oq_raw"], sp["rho"], sp["wrow"], lse32, dv_like, inv_tau, gamma, Yb,
                                            want_f32=not bilinear, want_bf16=bilinear, out_split=bilinear and strict)
     dX, dW = dT32, None
@@ -145,6 +183,8 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
             dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group)
     if rs_work is not None:
         rs_work.wait()
+    if isinstance(dY, _A2ASum):
+        dY = dY.resolve()
     backend.single_finalize_k(dY, sp["lam"], lse32, dv_like, inv_tau, gamma, T_local)
     return out, dX, dY, dW
 
@@ -194,7 +234,7 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     if nccl and hasattr(backend, "set_overlap_reserve_sms"):
         # the reduce-scatter of the dY contributions starts from an in-pass event; NCCL's CTAs cannot co-reside with
         # the engine's (one CTA per SM, all of its shared memory), so the launches after that event leave SMs free
-        backend.set_overlap_reserve_sms(int(os.environ.get("MI_RS_RESERVE_SMS", "16")))
+        backend.set_overlap_reserve_sms(int(os.environ.get("MI_RS_RESERVE_SMS", "0")))
     if single:
         return _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
                                  precision, qmax, world, group, nccl)

@@ -271,7 +271,8 @@ def row_norm_max(A: Mat) -> Tuple[torch.Tensor, torch.Tensor]:
 
 def score_single_pass(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float, include_diag: bool, precision: str,
                       inv_bg: float, qmax: Optional[torch.Tensor] = None, want_k: bool = True,
-                      event_after_k: Optional["torch.cuda.Event"] = None) -> dict:
+                      event_after_k: Optional["torch.cuda.Event"] = None,
+                      event_after_scal: Optional["torch.cuda.Event"] = None) -> dict:
     """mi_score_single_pass: statistics and raw gradient contractions from ONE score computation."""
     _need_cuda(Q, K, sid_q, sid_k, qmax)
     lib = _lib.load()
@@ -293,8 +294,24 @@ def score_single_pass(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
                                     _ptr(r["oq_raw"]), _ptr(r["ok_raw"]), _ptr(r["rho"]), _ptr(r["wrow"]), _ptr(r["lam"]),
                                     _ptr(r["flag"]),
                                     None if event_after_k is None else C.c_void_p(event_after_k.cuda_event),
+                                    None if event_after_scal is None else C.c_void_p(event_after_scal.cuda_event),
                                     _ptr(ws), ws.numel(), _stream()), "mi_score_single_pass")
     return r
+
+
+def merge_scalars_loss(scal_all: torch.Tensor, estimator: str, b_global: int) -> dict:
+    """Ranks' reduced scalars [world, 8] (fp64) -> the global loss terms as 0-d fp64 views plus the global
+    log-sum-exp as a 1-element fp32 tensor (mi_merge_scalars: two tiny kernels, no host sync)."""
+    _need_cuda(scal_all)
+    scal_all = scal_all.contiguous()
+    dev = scal_all.device
+    out = torch.empty(8, dtype=torch.float64, device=dev)
+    scratch = torch.empty(8, dtype=torch.float64, device=dev)
+    lse32 = torch.empty(1, dtype=torch.float32, device=dev)
+    _check(_lib.load().mi_merge_scalars(_ptr(scal_all), scal_all.shape[0], b_global, ESTIMATOR[estimator], _ptr(out), _ptr(lse32),
+                                        _ptr(scratch), _stream()), "mi_merge_scalars")
+    return {"loss": out[0], "pos_mean": out[1], "lse_neg": out[2], "n_neg": out[3], "loss_row": out[4],
+            "rows_without_negatives": out[6], "lse32": lse32}
 
 
 def single_finalize_q(oq_raw, rho, wrow, lse, dv_like: bool, alpha: float, gamma: float, kdiag: Mat,

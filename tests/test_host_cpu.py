@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/mi_b200.h but not exported"
         assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
     assert set(_lib.PROTOTYPES) == set(names)
-    assert _lib.load().mi_abi_version() == 2
+    assert _lib.load().mi_abi_version() == 3
 
 
 def test_status_strings_and_planning_without_gpu():
