@@ -243,11 +243,17 @@ def run_ours(a):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
+        marks = []
         for _ in range(steps):
             r = fn()
+            if os.environ.get("MI_BENCH_STEPTIMES"):
+                marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
         e1.record()
         sync_all()
         t1 = time.time()
+        if marks and rank == 0:
+            ts = [e0.elapsed_time(m) for m in marks]
+            print("per-step ms:", " ".join(f"{b - a:.2f}" for a, b in zip([0.0] + ts[:-1], ts)), file=sys.stderr, flush=True)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -966,7 +966,8 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                      int include_diag, int precision, float inv_bg, const float* qmax_in,
                      float* row_out, float* oq_raw, float* ok_raw,
                      float* rho, float* wrow, float* lambda_out, int* flag_out, Bump& ws, cudaStream_t stream,
-                     cudaEvent_t ev_after_k = nullptr, double* scal_out = nullptr, cudaEvent_t ev_after_scal = nullptr) {
+                     cudaEvent_t ev_after_k = nullptr, double* scal_out = nullptr, cudaEvent_t ev_after_scal = nullptr,
+                     const float* kmax_in = nullptr, cudaEvent_t ev_k_ready = nullptr) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
   const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
@@ -1006,15 +1007,23 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   // references
   row_norm_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Dp, Bq, D, qnorm);
   MI_LAUNCH_CHECK("row_norm_kernel");
-  row_norm_kernel<<<blocks_for(Bk * 32, 256), 256, 0, stream>>>(Ke.p, Ke.ld, Ke.split, Dp, Bk, D, knorm);
-  MI_LAUNCH_CHECK("row_norm_kernel");
-  max_reduce_kernel<<<1, 1024, 0, stream>>>(knorm, Bk, kmax);
-  MI_LAUNCH_CHECK("max_reduce_kernel");
+  if (kmax_in != nullptr) {
+    kmax = const_cast<float*>(kmax_in);              // max_k |K_k| supplied by the caller (e.g. gathered with the study ids)
+  } else {
+    // the K rows may still be arriving (all-gather): everything above needed the study ids and Q only
+    if (ev_k_ready != nullptr) { MI_CUDA(cudaStreamWaitEvent(stream, ev_k_ready, 0)); ev_k_ready = nullptr; }
+    row_norm_kernel<<<blocks_for(Bk * 32, 256), 256, 0, stream>>>(Ke.p, Ke.ld, Ke.split, Dp, Bk, D, knorm);
+    MI_LAUNCH_CHECK("row_norm_kernel");
+    max_reduce_kernel<<<1, 1024, 0, stream>>>(knorm, Bk, kmax);
+    MI_LAUNCH_CHECK("max_reduce_kernel");
+  }
   rho_kernel<<<blocks_for(Bq, 256), 256, 0, stream>>>(qnorm, kmax, scale, Bq, rho);
   MI_LAUNCH_CHECK("rho_kernel");
   // lambda = the same bound for the largest row norm (of ALL ranks when qmax_in is given): a global constant
   if (qmax_in) { rho_kernel<<<1, 32, 0, stream>>>(qmax_in, kmax, scale, 1, lambda_out); MI_LAUNCH_CHECK("rho_kernel"); }
   else { max_reduce_kernel<<<1, 1024, 0, stream>>>(rho, Bq, lambda_out); MI_LAUNCH_CHECK("max_reduce_kernel"); }
+  // from here on the K rows are read: wait for the caller's "K complete" event (the all-gather of the text embeddings)
+  if (ev_k_ready != nullptr) MI_CUDA(cudaStreamWaitEvent(stream, ev_k_ready, 0));
   diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split, q_offset, Bq, D, Dp, scale, diag);
   MI_LAUNCH_CHECK("diag_kernel");
   // V^T for the P K product
@@ -1853,7 +1862,8 @@ int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K,
                          int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag, int precision, float inv_bg,
                          const float* qnorm_max_in, float* row_out, double* scal_out, float* oq_raw, float* ok_raw,
                          float* rho, float* wrow, float* lambda_out, int32_t* flag_out, void* event_after_outk,
-                         void* event_after_scal, void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
+                         void* event_after_scal, const float* knorm_max_in, void* event_k_ready,
+                         void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
   MI_TRY(device_check());
   if (q_offset < 0 || q_offset + Bq > Bk || !scal_out) return MI_ERR_BAD_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -1862,7 +1872,8 @@ int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K,
                           Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
                           sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, precision, inv_bg, qnorm_max_in,
                           row_out, oq_raw, ok_raw, rho, wrow, lambda_out, flag_out, ws, stream,
-                          reinterpret_cast<cudaEvent_t>(event_after_outk), scal_out, reinterpret_cast<cudaEvent_t>(event_after_scal)));
+                          reinterpret_cast<cudaEvent_t>(event_after_outk), scal_out, reinterpret_cast<cudaEvent_t>(event_after_scal),
+                          knorm_max_in, reinterpret_cast<cudaEvent_t>(event_k_ready)));
   return MI_OK;
 }
 int mi_merge_scalars(const double* scal_all, int world, int64_t B_global, int estimator, double* loss_out, float* lse_out,

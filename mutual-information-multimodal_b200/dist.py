@@ -135,7 +135,7 @@ class _A2ASum:
 
 
 def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
-                      precision, qmax, world, group, nccl):
+                      precision, qmax, world, group, nccl, kmax=None, ev_y=None):
     """dv / infonce / row InfoNCE with ONE score computation per rank (see mi_score_single_pass)."""
     bilinear = Wb is not None
     strict = precision == "strict"
@@ -146,7 +146,8 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
         ev, ev_s = torch.cuda.Event(), torch.cuda.Event()
         ev.record(); ev_s.record()                    # (creates the CUDA events; the library re-records them in the pass)
     sp = backend.score_single_pass(T_local, Y_all, sid_loc, sid_all, off, inv_tau, not dv_like, precision, gamma,
-                                   qmax=qmax, want_k=True, event_after_k=ev, **({"event_after_scal": ev_s} if nccl else {}))
+                                   qmax=qmax, want_k=True, event_after_k=ev,
+                                   **({"event_after_scal": ev_s, "kmax": kmax, "event_k_ready": ev_y} if nccl else {}))
     scal = sp["scal"].reshape(1, 8)
     if nccl:
         # the loss scalars are final BEFORE the panel's two contractions: exchange them first, then start the big
@@ -179,13 +180,16 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
     if bilinear:
         dX = backend.gemm(dT16, Wb)
         dW = backend.gemm(Xb, dT16, a_t=True, b_t=True)          # X^T dT, both operands read in place
-        if world > 1:
-            dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group)
+    dw_work = None
+    if bilinear and world > 1:                                    # runs under the dY finalisation below
+        dw_work = dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group, async_op=True)
     if rs_work is not None:
         rs_work.wait()
     if isinstance(dY, _A2ASum):
         dY = dY.resolve()
     backend.single_finalize_k(dY, sp["lam"], lse32, dv_like, inv_tau, gamma, T_local)
+    if dw_work is not None:
+        dw_work.wait()
     return out, dX, dY, dW
 
 
@@ -209,35 +213,56 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     Xb, Yb = backend.as_bf16(X_local), backend.as_bf16(Y_local)
     Wb = backend.as_bf16(W) if bilinear else None
     # strict mode keeps T = X W as a hi/lo bf16 pair (16 significant bits into the score GEMM)
-    # ---- the exchange step (the all-gather of Y runs on NCCL's stream under the projection GEMM)
-    Y_all, y_work = Yb, None
-    if world > 1:
-        Y_all = torch.empty((Bg, D), dtype=Yb.dtype, device=Yb.device)
-        y_work = dist.all_gather_into_tensor(Y_all, Yb, group=group, async_op=True)
-    T_local = backend.gemm(Xb, Wb, b_t=True, out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb   # X W, W in place
+    # ---- the exchange step
+    nccl = world > 1 and dist.get_backend(group) != "gloo"
     single = need_grads and not sym and not two_pass
-    qmax = None
-    if single:                                        # largest |T_i| over ALL ranks: the global constant of the bound
+    T_local = backend.gemm(Xb, Wb, b_t=True, out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb   # X W, W in place
+    qmax = kmax = None
+    sid_all = None
+    if single and world > 1 and sid_local.dtype == torch.int32:
+        # ONE small all-gather carries the study ids and the two norm maxima of the single-pass score bound
+        # (max_i |T_i|, max_k |Y_k| as raw float bits); it goes first, so the mask pre-pass runs under the big one
+        _, qm = backend.row_norm_max(T_local)
+        _, km = backend.row_norm_max(Yb)
+        bits = lambda v: v.reshape(1).to(torch.float32).view(torch.int32)
+        meta = torch.cat((sid_local.reshape(-1), bits(qm), bits(km)))
+        meta_all = _all_gather_rows(meta.reshape(1, Bl + 2), world, group)
+        sid_all = meta_all[:, :Bl].reshape(-1)
+        qmax = meta_all[:, Bl].contiguous().view(torch.float32).max().reshape(1)
+        kmax = meta_all[:, Bl + 1].contiguous().view(torch.float32).max().reshape(1)
+    elif single:                                      # largest |T_i| over ALL ranks: the global constant of the bound
         _, qmax = backend.row_norm_max(T_local)
         if world > 1:
             dist.all_reduce(qmax, op=dist.ReduceOp.MAX, group=group)
-    if y_work is not None:
-        y_work.wait()
+    Y_all, ev_y = Yb, None
+    if world > 1:
+        Y_all = torch.empty((Bg, D), dtype=Yb.dtype, device=Yb.device)
+        y_work = dist.all_gather_into_tensor(Y_all, Yb, group=group, async_op=True)
+        if nccl and single:
+            # the compute stream does NOT wait here: the library waits for this event right before it first reads
+            # the text embeddings, after the mask pre-pass and the image-side statistics are enqueued
+            side = _side_stream(Yb.device)
+            with torch.cuda.stream(side):
+                y_work.wait()
+                ev_y = torch.cuda.Event()
+                ev_y.record(side)
+            Y_all.record_stream(side)
+        else:
+            y_work.wait()
     T_all = _gather_mat(T_local, world, group) if sym else None
-    if sid_local.dtype == torch.int32:                           # already exact int32 ids: use as they are
-        sid_all = _all_gather_rows(sid_local.contiguous(), world, group)
-    else:                                                        # identical on every rank, no host sync
-        sid_all = dense_labels(_all_gather_rows(sid_local.to(torch.int64), world, group))
+    if sid_all is None:
+        if sid_local.dtype == torch.int32:                       # already exact int32 ids: use as they are
+            sid_all = _all_gather_rows(sid_local.contiguous(), world, group)
+        else:                                                    # identical on every rank, no host sync
+            sid_all = dense_labels(_all_gather_rows(sid_local.to(torch.int64), world, group))
     sid_loc = sid_all[off:off + Bl].contiguous()
 
-    nccl = world > 1 and dist.get_backend(group) != "gloo"
     if nccl and hasattr(backend, "set_overlap_reserve_sms"):
-        # the reduce-scatter of the dY contributions starts from an in-pass event; NCCL's CTAs cannot co-reside with
-        # the engine's (one CTA per SM, all of its shared memory), so the launches after that event leave SMs free
+        # (experiment knob) SMs left free for the overlapped dY exchange; 0 = the engine uses every SM
         backend.set_overlap_reserve_sms(int(os.environ.get("MI_RS_RESERVE_SMS", "0")))
     if single:
         return _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
-                                 precision, qmax, world, group, nccl)
+                                 precision, qmax, world, group, nccl, kmax=kmax, ev_y=ev_y)
 
     # ---- statistics (S never materialised)
     rows_r, scal_r = backend.score_stats(T_local, Y_all, sid_loc, sid_all, off, inv_tau)

@@ -72,11 +72,12 @@ def row_norm_max(A):
 
 
 def score_single_pass(Q, K, sid_q, sid_k, q_offset, scale, include_diag, precision, inv_bg, qmax=None, want_k=True,
-                      event_after_k=None):
+                      event_after_k=None, event_after_scal=None, kmax=None, event_k_ready=None):
     S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
     qn, kn = Q.double().norm(dim=1), K.double().norm(dim=1)
-    rho = scale * qn * kn.max() * 1.001 + 1e-3
-    lam = (scale * (qn.max() if qmax is None else qmax.double().reshape(())) * kn.max() * 1.001 + 1e-3).reshape(1)
+    kmx = kn.max() if kmax is None else kmax.double().reshape(())
+    rho = scale * qn * kmx * 1.001 + 1e-3
+    lam = (scale * (qn.max() if qmax is None else qmax.double().reshape(())) * kmx * 1.001 + 1e-3).reshape(1)
     incl = M.clone()
     if include_diag:
         incl[i, j] = True

@@ -131,7 +131,7 @@ def _free_port():
     return p
 
 
-def _dist_worker(rank, world, port, est, critic, ret):
+def _dist_worker(rank, world, port, est, critic, ret, int32_ids=False):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -145,6 +145,8 @@ def _dist_worker(rank, world, port, est, critic, ret):
         Xb, Yb = X.bfloat16().float(), Y.bfloat16().float()
         Wb = None if W is None else W.bfloat16().float()
         sid_raw = sid * 1000003 + 17                         # arbitrary int64 ids
+        if int32_ids:                                        # exact int32 ids: ids + norm maxima travel in ONE all-gather
+            sid_raw = sid.to(torch.int32)
         Bl = B // world
         sl = slice(rank * Bl, (rank + 1) * Bl)
         out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xb[sl], Yb[sl], Wb, sid_raw[sl], est, "strict", 0.5,
@@ -175,6 +177,17 @@ def test_sharded_path_world2_gloo(est, critic):
         assert errs[0] < 1e-6, (rank, errs)           # fp32 log N_neg and fp32 reference vectors
         assert max(errs[1:-1]) < 1e-6, (rank, errs)
         assert errs[-1] == 0
+
+
+def test_sharded_path_world2_gloo_packed_int32_ids():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dist_worker, args=(2, _free_port(), "dv", "bilinear", ret, True), nprocs=2, join=True)
+    assert len(ret) == 2
+    for rank in range(2):
+        errs = ret[rank]
+        assert errs[0] < 1e-6 and max(errs[1:-1]) < 1e-6 and errs[-1] == 0, (rank, errs)
 
 
 def test_merge_scalars_matches_single_block():
