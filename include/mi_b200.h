@@ -198,6 +198,17 @@ int mi_mlp_critic_loss_fwd_bwd(const float* X, const float* Y, const float* W1, 
                                double* loss_out, float* S_out, float* dX, float* dY, float* dW1, float* db1, float* dW2, float* db2,
                                float* dW3, float* db3, void* workspace, size_t workspace_bytes, mi_stream_t stream);
 
+/* ---- Generalised Discrimination Value (validate.py:16-49, gdv_calculation) ----------------- */
+
+/* pos [Np, D], neg [Nn, D]: fp32 device matrices of the two classes' embeddings (validate.py:118-127).  Each class is
+ * z-scored per feature (StandardScaler semantics incl. its constant-feature rule), then the sums of ALL pairwise
+ * Euclidean distances inside each class and between the classes are formed on the tile engine with a
+ * sqrt(|a|^2 + |b|^2 - 2 a.b) epilogue (no N x N matrix).  out (fp64[4]) = { gdv, intra_pos, intra_neg, inter } with the
+ * reference's normalisers (which count N * D elements, validate.py:25,31-33).  D multiple of 8; Np, Nn >= 2. */
+size_t mi_gdv_workspace_bytes(int64_t Np, int64_t Nn, int64_t D, int precision);
+int mi_gdv(const float* pos, const float* neg, int64_t Np, int64_t Nn, int64_t D, int precision, double* out /*[4]*/,
+           void* workspace, size_t workspace_bytes, mi_stream_t stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t mi_launch_count(void);
 

@@ -8,6 +8,7 @@ hyphen).  Layout:
   ops.py       stage-level wrappers on torch tensors (device memory and streams only)
   critic.py    host-side mirror of the reference API: create_mi_pairs / FusedCritic /
                dv_bound_loss / infonce_bound_loss (mutual_info_img_txt/mi_critics.py, main_utils.py:80-110)
+  validate.py  gdv_calculation (validate.py:16-49) on the same tile engine
   dist.py      batch-sharded multi-GPU path (torch.distributed all-gathers + scalar reductions)
 
 There is no CPU fallback: every compute entry point raises when the CUDA library or a Blackwell
@@ -19,8 +20,9 @@ from .critic import (  # noqa: F401
     mi_estimator_loss, select_estimator, sharded_mi_loss,
 )
 from .ops import MIError  # noqa: F401
+from .validate import gdv_calculation, gdv_terms  # noqa: F401
 
 __all__ = [
     "FusedCritic", "FusedMLPCritic", "PairBatch", "ScoreHandle", "create_mi_pairs", "create_mi_pairs_tensor", "dv_bound_loss",
-    "infonce_bound_loss", "mi_estimator_loss", "select_estimator", "sharded_mi_loss", "MIError",
+    "infonce_bound_loss", "mi_estimator_loss", "select_estimator", "sharded_mi_loss", "MIError", "gdv_calculation", "gdv_terms",
 ]

@@ -53,6 +53,8 @@ PROTOTYPES = {
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mi_mlp_critic_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_i64, c_int]),
     "mi_mlp_critic_loss_fwd_bwd": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_i64, c_int, c_int] + [c_vp] * 10 + [c_vp, c_sz, c_vp]),
+    "mi_gdv_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
+    "mi_gdv": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_sz, c_vp]),
     "mi_critic_host_scratch_bytes": (c_sz, [c_i64, c_i64, c_int, c_int, c_int, c_int]),
     "mi_critic_loss_fwd_bwd_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32,
                                             c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

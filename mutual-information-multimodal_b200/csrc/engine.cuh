@@ -815,4 +815,47 @@ struct EpiMlpDz {
   }
 };
 
+// ---- pairwise Euclidean distance sums (GDV, validate.py:23-34): acc = <a_row, b_col>,
+//      d = sqrt(max(|a|^2 + |b|^2 - 2 acc, 0)); the epilogue keeps one running sum per thread, S is never stored
+struct EpiDist {
+  static constexpr int kEpiSmemBytes = 0;
+  struct Params {
+    const float* na;       // [rows] squared norms of the A rows
+    const float* nb;       // [n_ntile * 256] squared norms of the B rows, zero padded
+    int rows, cols;
+    int same;              // A and B are the same set: the diagonal is exactly 0 (pairwise_distances(X) forces it)
+    float* part;           // [n_split * kColQuarters][rows_padded]
+    int rows_padded;
+  };
+  struct State { uint8_t* stage_smem; float acc; float na; };
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+  static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
+    st.acc = 0.f;
+    st.na = row < p.rows ? __ldg(p.na + row) : 0.f;
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0, uint32_t (&v)[32]) {
+    if (row >= p.rows || col0 >= p.cols) return;
+    const float4* n4 = reinterpret_cast<const float4*>(p.nb + col0);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 nb = __ldg(n4 + g);
+      const float nn[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = col0 + 4 * g + j;
+        const float d2 = fmaf(-2.f, __uint_as_float(v[4 * g + j]), st.na + nn[j]);
+        const bool ok = col < p.cols && !(p.same && col == row);
+        const float d = ok ? sqrtf(fmaxf(d2, 0.f)) : 0.f;
+        if (j & 1) a1 += d; else a0 += d;
+      }
+    }
+    st.acc += a0 + a1;
+  }
+  static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit& un, int row, int colq) {
+    p.part[((size_t)un.s * kColQuarters + colq) * p.rows_padded + row] = st.acc;
+  }
+};
+
 }  // namespace mi

@@ -422,6 +422,23 @@ def mlp_critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, params, sid: torch
     return loss, S, grads
 
 
+def gdv(pos: torch.Tensor, neg: torch.Tensor, precision: str = "strict") -> torch.Tensor:
+    """mi_gdv: fp64[4] = {gdv, intra_pos, intra_neg, inter} of two [N, D] fp32 embedding sets (validate.py:16-49)."""
+    _need_cuda(pos, neg)
+    pos, neg = pos.detach().to(torch.float32).contiguous(), neg.detach().to(torch.float32).contiguous()
+    if pos.dim() != 2 or neg.dim() != 2 or pos.shape[1] != neg.shape[1]:
+        raise MIError("gdv needs two [N, D] matrices with the same D")
+    lib = _lib.load()
+    Np, Nn, D = pos.shape[0], neg.shape[0], pos.shape[1]
+    nbytes = lib.mi_gdv_workspace_bytes(Np, Nn, D, PRECISION[precision])
+    if nbytes == 0:
+        raise MIError("mi_gdv: unsupported shape (D multiple of 8, at least 2 samples per class)")
+    ws = workspace(nbytes, pos.device)
+    out = torch.empty(4, dtype=torch.float64, device=pos.device)
+    _check(lib.mi_gdv(_ptr(pos), _ptr(neg), Np, Nn, D, PRECISION[precision], _ptr(out), _ptr(ws), ws.numel(), _stream()), "mi_gdv")
+    return out
+
+
 def set_overlap_reserve_sms(n: int) -> None:
     """SMs the engine leaves free after the dY contributions are complete (mi_set_overlap_reserve_sms)."""
     _lib.load().mi_set_overlap_reserve_sms(int(n))

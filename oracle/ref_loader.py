@@ -107,3 +107,29 @@ def load():
         ns.import_error = repr(exc)
     _cache["ns"] = ns
     return ns
+
+
+def load_gdv():
+    """The reference's GDV functions (validate.py:16-49: ``z_scored_transform``, ``mean_intra_class_distance``,
+    ``mean_inter_class_distance``, ``gdv_calculation``), verbatim.  ``validate.py`` runs its whole validation at import
+    time (argument parsing, datasets, checkpoints: validate.py:55-171), so only these four function definitions are
+    compiled out of its source — the function bodies are the reference's own, untouched."""
+    if "gdv" in _cache:
+        return _cache["gdv"]
+    import ast
+    import math
+    import numpy as np
+    from sklearn.metrics import pairwise_distances
+    from sklearn.preprocessing import StandardScaler
+    path = os.path.join(REFERENCE_ROOT, "validate.py")
+    if not os.path.isfile(path):
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    tree = ast.parse(open(path).read(), filename=path)
+    wanted = {"z_scored_transform", "mean_intra_class_distance", "mean_inter_class_distance", "gdv_calculation"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    scope = {"math": math, "np": np, "pairwise_distances": pairwise_distances, "StandardScaler": StandardScaler}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), scope)
+    ns = types.SimpleNamespace(**{k: scope[k] for k in wanted})
+    _cache["gdv"] = ns
+    return ns
