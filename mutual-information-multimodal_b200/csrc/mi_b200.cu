@@ -1417,34 +1417,55 @@ __global__ void mlp_g_kernel(const float* __restrict__ S, const int* __restrict_
   else if (neg || i == j) g = inv_b * expf(S[idx] - rows[i].w) - (i == j ? inv_b : 0.f);
   G[idx] = g;
 }
-// dA[r0 + il, k..k+3] = sum_j DZ1[il * Bk + j, k..k+3]
-__global__ void mlp_reduce_rows_kernel(const float* __restrict__ dz1, long long H1, long long Bk, long long R, long long r0,
-                                       float* __restrict__ dA) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long h4 = H1 >> 2;
-  if (idx >= R * h4) return;
-  const long long il = idx / h4, k = (idx - il * h4) << 2;
-  const float* src = dz1 + il * Bk * H1 + k;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long j = 0; j < Bk; ++j) {
-    const float4 v = *reinterpret_cast<const float4*>(src + j * H1);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+// One read of the dZ1 panel gives both reductions.  A block owns a slab [32 rows il] x [all j] x [64 columns]:
+// thread = (column pair, j group); for every j it loads the 32 il values (32 independent loads in flight), adds them into
+// its 32 register accumulators (-> dA[il]) and sends their sum to dC[j] with one atomicAdd per column.
+template <typename T>
+__global__ void __launch_bounds__(256) mlp_reduce_both_kernel(const T* __restrict__ dz1, long long ld, long long H1, long long Bk,
+                                                              long long R, long long r0, float* __restrict__ dA, float* __restrict__ dC) {
+  constexpr int IL = 32, JG = 8;
+  __shared__ float sh[IL][64];
+  const int kk = threadIdx.x & 31, jg = threadIdx.x >> 5;
+  const long long k = blockIdx.x * 64LL + 2 * kk;
+  const long long il0 = blockIdx.y * (long long)IL;
+  const bool kin = k < H1;
+  float ax[IL], ay[IL];
+#pragma unroll
+  for (int i = 0; i < IL; ++i) { ax[i] = 0.f; ay[i] = 0.f; }
+  if (kin) {
+    // blockIdx.z splits the j range so that large batches (few il rows per panel) still fill the machine
+    const long long jchunk = (Bk + gridDim.z - 1) / gridDim.z;
+    const long long j0 = blockIdx.z * jchunk, j1 = (j0 + jchunk < Bk) ? j0 + jchunk : Bk;
+    for (long long j = j0 + jg; j < j1; j += JG) {
+      float sx = 0.f, sy = 0.f;
+#pragma unroll
+      for (int i = 0; i < IL; ++i) {
+        if (il0 + i < R) {
+          const T* src = dz1 + ((il0 + i) * Bk + j) * ld + k;
+          float vx, vy;
+          if constexpr (sizeof(T) == 2) {
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
+            vx = v.x; vy = v.y;
+          } else {
+            const float2 v = *reinterpret_cast<const float2*>(src);
+            vx = v.x; vy = v.y;
+          }
+          ax[i] += vx; ay[i] += vy; sx += vx; sy += vy;
+        }
+      }
+      atomicAdd(dC + j * H1 + k, sx);
+      atomicAdd(dC + j * H1 + k + 1, sy);
+    }
   }
-  *reinterpret_cast<float4*>(dA + (r0 + il) * H1 + k) = a;
-}
-// dC[j, k..k+3] += sum_il DZ1[il * Bk + j, k..k+3]
-__global__ void mlp_reduce_cols_kernel(const float* __restrict__ dz1, long long H1, long long Bk, long long R, float* __restrict__ dC) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long h4 = H1 >> 2;
-  if (idx >= Bk * h4) return;
-  const long long j = idx / h4, k = (idx - j * h4) << 2;
-  const float* src = dz1 + j * H1 + k;
-  float4 a = *reinterpret_cast<const float4*>(dC + j * H1 + k);
-  for (long long il = 0; il < R; ++il) {
-    const float4 v = *reinterpret_cast<const float4*>(src + il * Bk * H1);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  for (int t = threadIdx.x; t < IL * 64; t += 256) sh[t >> 6][t & 63] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < IL; ++i) { atomicAdd(&sh[i][2 * kk], ax[i]); atomicAdd(&sh[i][2 * kk + 1], ay[i]); }   // 8 j groups per cell
+  __syncthreads();
+  for (int t = threadIdx.x; t < IL * 64; t += 256) {
+    const int i = t >> 6, c = t & 63;
+    if (il0 + i < R && blockIdx.x * 64LL + c < H1) atomicAdd(dA + (r0 + il0 + i) * H1 + blockIdx.x * 64LL + c, sh[i][c]);   // dA zeroed by the caller
   }
-  *reinterpret_cast<float4*>(dC + j * H1 + k) = a;
 }
 // out[c] = sum_r in[r, c]  (one thread per column; rows are few thousand at most)
 __global__ void colsum_kernel(const float* __restrict__ in, long long R, long long C, float* __restrict__ out) {
@@ -1520,7 +1541,9 @@ int mlp_impl(const float* X, const float* Y, const MlpParams& prm, const int* si
   float* part = ws.take<float>(mi::kColQuarters * rows_padded_max);
   float* G = plan ? ws.take<float>(B * B) : nullptr;
   bf* DZ2 = plan ? ws.take<bf>(Pmax * pZ) : nullptr;
-  float* DZ1 = plan ? ws.take<float>(Pmax * H1) : nullptr;
+  // dZ1 panel: bf16 in fast mode (half the bytes of the HBM-write-bound masked contraction), fp32 in strict mode
+  float* DZ1 = (plan && sp == 2) ? ws.take<float>(Pmax * H1) : nullptr;
+  bf* DZ1h = (plan && sp == 1) ? ws.take<bf>(Pmax * H1) : nullptr;
   float* dA32 = plan ? ws.take<float>(B * H1) : nullptr; float* dC32 = plan ? ws.take<float>(B * H1) : nullptr;
   bf* dA16 = plan ? ws.take<bf>(B * pH) : nullptr; bf* dC16 = plan ? ws.take<bf>(B * pH) : nullptr;
   float* acc_w3 = plan ? ws.take<float>(h2_pad) : nullptr; float* acc_b2 = plan ? ws.take<float>(h2_pad) : nullptr;
@@ -1601,6 +1624,7 @@ int mlp_impl(const float* X, const float* Y, const MlpParams& prm, const int* si
     mlp_g_kernel<<<blocks_for(B * B, 256), 256, 0, stream>>>(S, sid, B, dv_like, lse_f, reinterpret_cast<const float4*>(rows_r), G);
     MI_LAUNCH_CHECK("mlp_g_kernel");
     MI_CUDA(cudaMemsetAsync(dC32, 0, static_cast<size_t>(B) * H1 * sizeof(float), stream));
+    MI_CUDA(cudaMemsetAsync(dA32, 0, static_cast<size_t>(B) * H1 * sizeof(float), stream));
     MI_CUDA(cudaMemsetAsync(acc_w3, 0, static_cast<size_t>(h2_pad) * sizeof(float), stream));
     MI_CUDA(cudaMemsetAsync(acc_b2, 0, static_cast<size_t>(h2_pad) * sizeof(float), stream));
   }
@@ -1639,15 +1663,20 @@ int mlp_impl(const float* X, const float* Y, const MlpParams& prm, const int* si
       const int kb = static_cast<int>(sp == 2 ? H2p / bk() : cdiv(H2, bk()));
       g.k_blocks = kb; g.seg_len = kb;
       if (sp == 2) { g.k_blocks = 3 * kb; g.a_seg[1] = kb; g.b_noff[2] = static_cast<int>(Hp); }
-      g.out_f32 = DZ1; g.ld_out = H1; g.relu_mask = Hpan; g.ld_mask = pH;
+      g.out_f32 = DZ1; g.ld_out = H1; g.out_bf16 = DZ1h; g.ld_out16 = H1; g.relu_mask = Hpan; g.ld_mask = pH;
+      if (dry) g.out_f32 = reinterpret_cast<float*>(16);
       MI_TRY(run_gemm(g, ws, stream));
       ws.release(mk);
     }
     if (!dry) {
-      mlp_reduce_rows_kernel<<<blocks_for(rr * (H1 >> 2), 128), 128, 0, stream>>>(DZ1, H1, B, rr, r0, dA32);
-      MI_LAUNCH_CHECK("mlp_reduce_rows_kernel");
-      mlp_reduce_cols_kernel<<<blocks_for(B * (H1 >> 2), 128), 128, 0, stream>>>(DZ1, H1, B, rr, dC32);
-      MI_LAUNCH_CHECK("mlp_reduce_cols_kernel");
+      dim3 rg(static_cast<unsigned>(cdiv(H1, 64)), static_cast<unsigned>(cdiv(rr, 32)), 1);
+      const long long blocks = static_cast<long long>(rg.x) * rg.y;
+      long long jz = blocks >= num_sms() ? 1 : cdiv(4LL * num_sms(), blocks);
+      if (jz > B / 64) jz = B / 64;
+      rg.z = static_cast<unsigned>(jz < 1 ? 1 : jz);
+      if (sp == 1) mlp_reduce_both_kernel<bf><<<rg, 256, 0, stream>>>(DZ1h, H1, H1, B, rr, r0, dA32, dC32);
+      else mlp_reduce_both_kernel<float><<<rg, 256, 0, stream>>>(DZ1, H1, H1, B, rr, r0, dA32, dC32);
+      MI_LAUNCH_CHECK("mlp_reduce_both_kernel");
     }
   }
   if (!dry) {
