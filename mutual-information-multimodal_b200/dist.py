@@ -176,13 +176,12 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
     out["loose_reference_rows"] = sp["flag"]
     dT32, dT16 = backend.single_finalize_q(sp["oq_raw"], sp["rho"], sp["wrow"], lse32, dv_like, inv_tau, gamma, Yb,
                                            want_f32=not bilinear, want_bf16=bilinear, out_split=bilinear and strict)
-    dX, dW = dT32, None
+    dX, dW, dw_work = dT32, None, None
     if bilinear:
-        dX = backend.gemm(dT16, Wb)
         dW = backend.gemm(Xb, dT16, a_t=True, b_t=True)          # X^T dT, both operands read in place
-    dw_work = None
-    if bilinear and world > 1:                                    # runs under the dY finalisation below
-        dw_work = dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        if world > 1:                                             # runs under the dX GEMM and the dY finalisation below
+            dw_work = dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        dX = backend.gemm(dT16, Wb)
     if rs_work is not None:
         rs_work.wait()
     if isinstance(dY, _A2ASum):
