@@ -21,7 +21,7 @@ Bl = B // world
 off = rank * Bl
 X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=7, dup_frac=0.05, bilinear=True)
 Xd, Yd, Wd, sd = X.to(dev).bfloat16(), Y.to(dev).bfloat16(), W.to(dev).bfloat16(), sid.to(torch.int32).to(dev)
-worst = 0.0
+worst = {"fast": 0.0, "strict": 0.0}
 for est in ("dv", "infonce_row", "infonce_sym"):
     for prec in ("fast", "strict"):
         out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xd[off:off + Bl], Yd[off:off + Bl], Wd, sd[off:off + Bl], est, prec, 1.0, True)
@@ -29,11 +29,15 @@ for est in ("dv", "infonce_row", "infonce_sym"):
         torch.cuda.synchronize()
         rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
         e = (abs(float(out["loss"]) - float(ref[0])), rel(dX, rX[off:off + Bl]), rel(dY, rY[off:off + Bl]), rel(dW, rW))
-        worst = max(worst, *e[1:])
+        worst[prec] = max(worst[prec], *e[1:])
         if rank == 0:
             print(f"{est} {prec}: loss {float(out['loss']):.8f} vs {float(ref[0]):.8f}  |dloss| {e[0]:.1e}  dX {e[1]:.1e} dY {e[2]:.1e} dW {e[3]:.1e}", flush=True)
-t = torch.tensor([worst], device=dev)
+t = torch.tensor([worst["fast"], worst["strict"]], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("worst relative gradient difference over ranks:", float(t), "OK" if float(t) < 5e-3 else "MISMATCH")
+    # the two paths round the same quantities to bf16 after fp32 sums taken in a different order: in fast mode a 1-ulp
+    # fp32 difference can flip a bf16 rounding of dT (2^-9 of one element), so the bound is the fast-mode tolerance
+    ok = float(t[0]) < 1e-2 and float(t[1]) < 1e-4
+    print(f"worst relative gradient difference over ranks: fast {float(t[0]):.1e} (bound 1e-2), strict {float(t[1]):.1e} (bound 1e-4):",
+          "OK" if ok else "MISMATCH")
 dist.destroy_process_group()
