@@ -539,6 +539,9 @@ struct EpiStore {
     int sub_row0, sub_rows;    // SUB row r applies to output row sub_row0 + r, r in [0, sub_rows)
     long long ksplit_stride;   // elements between split-K partial outputs (fp32 only)
     int accumulate;            // out_f32 += result (panel-by-panel accumulation)
+    int acc_first;             // with `accumulate`: C = alpha * (kappa * (ACC + C_prev) - gamma SUB) — the last panel of an
+    const float* kappa_a;      // accumulation finishes the result; kappa = exp(kappa_a[0] - kappa_b[0]) (device scalars) or 1
+    const float* kappa_b;
     const float* bias;         // optional [cols]: C = alpha * (ACC - gamma SUB) + bias   (nn.Linear bias)
     const __nv_bfloat16* relu_mask;  // optional [rows, ld_mask]: C = 0 where relu_mask <= 0  (backward of a ReLU whose
     long long ld_mask;               //                          output is relu_mask)
@@ -554,6 +557,25 @@ struct EpiStore {
 #pragma unroll
     for (int c = 0; c < 32; ++c) o[c] = __uint_as_float(v[c]);
     const bool full = (col0 + 32 <= p.cols);
+    const bool acc_first = p.acc_first != 0 && p.out_f32 != nullptr;
+    if (acc_first) {
+      const float* d = p.out_f32 + (size_t)un.ks * p.ksplit_stride + (size_t)row * p.ld_out + col0;
+      const float kappa = p.kappa_a != nullptr ? expf(__ldg(p.kappa_a) - __ldg(p.kappa_b)) : 1.f;
+      if (p.accumulate) {
+        if (full) {
+          const float4* d4 = reinterpret_cast<const float4*>(d);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 prev = d4[g];
+            o[4 * g] += prev.x; o[4 * g + 1] += prev.y; o[4 * g + 2] += prev.z; o[4 * g + 3] += prev.w;
+          }
+        } else {
+          for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) o[c] += d[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o[c] *= kappa;
+    }
     const int srow = row - p.sub_row0;
     if (p.sub != nullptr && srow >= 0 && srow < p.sub_rows) {
       const __nv_bfloat16* s = p.sub + (size_t)srow * p.ld_sub + col0;
@@ -613,7 +635,7 @@ struct EpiStore {
       float* d = p.out_f32 + (size_t)un.ks * p.ksplit_stride + (size_t)row * p.ld_out + col0;
       if (full) {
         float4* d4 = reinterpret_cast<float4*>(d);
-        if (p.accumulate) {
+        if (p.accumulate && !acc_first) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 prev = d4[g];
@@ -623,7 +645,7 @@ struct EpiStore {
 #pragma unroll
         for (int g = 0; g < 8; ++g) d4[g] = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
       } else {
-        for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) { if (p.accumulate) o[c] += d[c]; d[c] = o[c]; }
+        for (int c = 0; c < 32; ++c) if (col0 + c < p.cols) { if (p.accumulate && !acc_first) o[c] += d[c]; d[c] = o[c]; }
       }
     }
     if (p.out_bf16 != nullptr) {

@@ -618,6 +618,7 @@ struct GemmArgs {
   float* out_f32 = nullptr; long long ld_out = 0;
   __nv_bfloat16* out_bf16 = nullptr; __nv_bfloat16* out_bf16_lo = nullptr; long long ld_out16 = 0;
   bool accumulate = false;
+  bool acc_first = false; const float* kappa_a = nullptr; const float* kappa_b = nullptr;   // see EpiStore::Params
   const float* bias = nullptr;                                   // [N] added after alpha (nn.Linear bias)
   const __nv_bfloat16* relu_mask = nullptr; long long ld_mask = 0;   // zero the result where relu_mask <= 0
 };
@@ -649,6 +650,7 @@ int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
   ep.out_bf16_lo = sk ? nullptr : g.out_bf16_lo;
   ep.ld_out = sk ? ldp : g.ld_out; ep.ld_out16 = g.ld_out16;
   ep.bias = sk ? nullptr : g.bias; ep.relu_mask = sk ? nullptr : g.relu_mask; ep.ld_mask = g.ld_mask;
+  ep.acc_first = (!sk && g.acc_first) ? 1 : 0; ep.kappa_a = g.kappa_a; ep.kappa_b = g.kappa_b;
   ep.rows = static_cast<int>(g.M); ep.cols = static_cast<int>(g.N);
   ep.alpha = g.alpha; ep.gamma = g.gamma;
   ep.sub = sk ? nullptr : g.sub; ep.sub_lo = sk ? nullptr : g.sub_lo; ep.ld_sub = g.ld_sub;
@@ -660,7 +662,7 @@ int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
   else if (g.b_mn) MI_TRY((launch_engine<mi::EpiStore, false, true>(g.a, g.b, sc, ep, stream)));
   else MI_TRY((launch_engine<mi::EpiStore, false, false>(g.a, g.b, sc, ep, stream)));
   if (sk) {
-    if (!g.out_f32 || g.sub || g.bias || g.relu_mask || g.alpha != 1.f) return MI_ERR_BAD_ARG;
+    if (!g.out_f32 || g.sub || g.bias || g.relu_mask || g.acc_first || g.alpha != 1.f) return MI_ERR_BAD_ARG;
     const long long n = static_cast<long long>(g.M) * g.N;
     reduce_partials_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(partial, sc.n_ksplit, static_cast<long long>(g.M) * ldp, ldp,
                                                                    g.out_f32, g.ld_out, g.M, g.N, g.accumulate ? 1 : 0);
@@ -952,6 +954,14 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   return MI_OK;
 }
 
+// Optional tail of the single pass on ONE GPU: the loss is finalised as soon as the last panel's row sums are merged
+// (the global log-sum-exp is then known on the device), so the last panel's K-side contraction can finish its output
+// in the epilogue — Ok = alpha (kappa (Ok_raw) - gamma Q_diag) — instead of a separate read-modify-write pass over [Bk, D].
+struct SingleFin {
+  double* loss_out; float* lse_f; long long B; int estimator;     // loss_finalize_kernel arguments
+  float alpha, gamma; int dv_like;
+};
+
 // Single-pass variant of the forward statistics + gradient pass (dv / infonce / row InfoNCE).
 // rho[q] = scale |Q_q| max_k |K_k| bounds every score of row q from above (Cauchy-Schwarz), so
 // P~ = incl * e^{S - rho} <= 1 needs no running max and no statistics pass BEFORE the panel is written:
@@ -968,7 +978,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                      float* row_out, float* oq_raw, float* ok_raw,
                      float* rho, float* wrow, float* lambda_out, int* flag_out, Bump& ws, cudaStream_t stream,
                      cudaEvent_t ev_after_k = nullptr, double* scal_out = nullptr, cudaEvent_t ev_after_scal = nullptr,
-                     const float* kmax_in = nullptr, cudaEvent_t ev_k_ready = nullptr) {
+                     const float* kmax_in = nullptr, cudaEvent_t ev_k_ready = nullptr, const struct SingleFin* fin = nullptr) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
   const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
@@ -1067,6 +1077,10 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
       stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out);
       MI_LAUNCH_CHECK("stats_reduce_kernel");
       if (ev_after_scal != nullptr) MI_CUDA(cudaEventRecord(ev_after_scal, stream));
+      if (fin != nullptr) {
+        loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_out, nullptr, fin->B, fin->estimator, fin->loss_out, fin->lse_f);
+        MI_LAUNCH_CHECK("loss_finalize_kernel");
+      }
     }
     Bump none(nullptr, 0, false);
     // (2) Ok_raw += P~^T (w Q)[panel]: contraction over the panel rows, P~ read MN-major
@@ -1094,6 +1108,13 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
       }
       g.accumulate = r0 > 0;
       g.out_f32 = ok_raw; g.ld_out = D;
+      if (fin != nullptr && scal_out != nullptr && r0 + panel_rows >= Bq) {      // last panel: finish the K-side output here
+        g.acc_first = true;
+        if (fin->dv_like) { g.kappa_a = lambda_out; g.kappa_b = fin->lse_f; }
+        g.alpha = fin->alpha; g.gamma = fin->gamma;
+        g.sub = Q.p; g.ld_sub = Q.ld; g.sub_lo = (strict && Q.split == 2) ? Q.p + Dp : nullptr;
+        g.sub_row0 = q_offset; g.sub_rows = Bq;
+      }
       MI_TRY(run_gemm(g, none, stream));
       if (ev_after_k != nullptr && r0 + panel_rows >= Bq) {
         MI_CUDA(cudaEventRecord(ev_after_k, stream));
@@ -1198,12 +1219,18 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     const float gam = 1.f / static_cast<float>(B);
     float* oq_raw = sp_oq ? sp_oq : dX;
     float* ok_raw = dY ? dY : sp_ok;
+    // the loss is finalised inside the pass and, when dY is wanted, the last panel's contraction finishes dY in its epilogue
+    SingleFin fin{loss_out, lse_f, B, estimator, inv_tau, gam, dv_like ? 1 : 0};
+    const bool fused_k = dY != nullptr;
     MI_TRY(single_pass_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, precision, gam, nullptr,
-                            rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream, nullptr, scal_r));
+                            rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream, nullptr, scal_r,
+                            nullptr, nullptr, nullptr, fused_k ? &fin : nullptr));
     ws.release(mk);
     if (!ws.dry) {
-      loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, nullptr, B, estimator, loss_out, lse_f);
-      MI_LAUNCH_CHECK("loss_finalize_kernel");
+      if (!fused_k) {
+        loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, nullptr, B, estimator, loss_out, lse_f);
+        MI_LAUNCH_CHECK("loss_finalize_kernel");
+      }
       flag_to_loss_kernel<<<1, 1, 0, stream>>>(sp_flag, loss_out);
       MI_LAUNCH_CHECK("flag_to_loss_kernel");
       const long long n = B * D;
@@ -1213,11 +1240,7 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
                                                                 Y, D, 1, Dp, bilinear ? nullptr : dX, bilinear ? dT16 : nullptr,
                                                                 (bilinear && tsplit == 2) ? dT16 + Dp : nullptr, ldT);
       MI_LAUNCH_CHECK("finalize_q_kernel");
-      if (dY) {
-        finalize_k_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(dY, D, B, sp_lambda, lse_f, dv_like ? 1 : 0, inv_tau, gam,
-                                                                  To.p, To.ld, To.split, Dp, 0, B);
-        MI_LAUNCH_CHECK("finalize_k_kernel");
-      }
+      // (dY was finished by the last panel's contraction: see SingleFin)
     }
   }
   if (!single || ws.dry) {        // (planning covers both paths)

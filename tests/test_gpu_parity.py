@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {"strict": (1e-4, 1e-3), "fast": (2e-3, 1e-2)}
 GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))
-                if "known_answers" not in p and not os.path.basename(p).startswith("mlp_"))
+                if "known_answers" not in p and not os.path.basename(p).startswith(("mlp_", "gdv_")))
 
 
 @pytest.fixture(scope="module")

@@ -106,7 +106,7 @@ def test_compat_pair_tensor_matches_reference_order(golden_dir):
     import glob
     import mi_b200
     from oracle import matrix_oracle as mo
-    for path in sorted(p for p in glob.glob(os.path.join(golden_dir, "*dups.npz")) if not os.path.basename(p).startswith("mlp_")):
+    for path in sorted(p for p in glob.glob(os.path.join(golden_dir, "*dups.npz")) if not os.path.basename(p).startswith(("mlp_", "gdv_"))):
         z = np.load(path)
         X, Y = torch.from_numpy(z["X"]).requires_grad_(True), torch.from_numpy(z["Y"])
         sid = [str(int(s)) for s in z["sid"]]
