@@ -1153,7 +1153,9 @@ inline bool grads_or_plan_single(int estimator, int precision) {
 
 int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, long long B, long long D,
                 int critic, int estimator, int precision, float inv_tau,
-                double* loss_out, float* dX, float* dY, float* dW, Bump& ws, cudaStream_t stream) {
+                double* loss_out, float* dX, float* dY, float* dW, Bump& ws, cudaStream_t stream,
+                cudaEvent_t ev_dy_final = nullptr, bool* ev_recorded = nullptr) {   // event recorded once dY is final (the
+                                                                                     // dT / dX / dW work follows it)
   if (B <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   if (estimator < MI_EST_DV || estimator > MI_EST_INFONCE_SYM) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
@@ -1223,8 +1225,9 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     SingleFin fin{loss_out, lse_f, B, estimator, inv_tau, gam, dv_like ? 1 : 0};
     const bool fused_k = dY != nullptr;
     MI_TRY(single_pass_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, precision, gam, nullptr,
-                            rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream, nullptr, scal_r,
-                            nullptr, nullptr, nullptr, fused_k ? &fin : nullptr));
+                            rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream,
+                            fused_k ? ev_dy_final : nullptr, scal_r, nullptr, nullptr, nullptr, fused_k ? &fin : nullptr));
+    if (fused_k && ev_dy_final && ev_recorded && !ws.dry) *ev_recorded = true;
     ws.release(mk);
     if (!ws.dry) {
       if (!fused_k) {
@@ -1282,7 +1285,8 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   if (want_q || want_k) {
     if (tsplit == 2 && !ws.dry) MI_CUDA(cudaMemsetAsync(dT16, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
     MI_TRY(grad_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, refq, wq, refk, wk, incl_diag, precision & 1,
-                     inv_tau, gamma, want_q ? oq : oq_none, want_k ? &okk : nullptr, ws, stream));
+                     inv_tau, gamma, want_q ? oq : oq_none, want_k ? &okk : nullptr, ws, stream, want_k ? ev_dy_final : nullptr));
+    if (want_k && ev_dy_final && ev_recorded && !ws.dry) *ev_recorded = true;
     ws.release(mk);
   }
   }   // two-pass path
@@ -1893,6 +1897,24 @@ int device_check() {
   return major == 10 ? MI_OK : MI_ERR_NO_DEVICE;
 }
 
+// second stream + event of the host-buffer entry point (one per device, created on first use)
+struct CopySide { cudaStream_t stream; cudaEvent_t ev; };
+int copy_side(CopySide* out) {
+  static std::mutex mu;
+  static CopySide cache[64];
+  static bool have[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return MI_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(mu);
+  if (!have[dev]) {
+    MI_CUDA(cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking));
+    MI_CUDA(cudaEventCreateWithFlags(&cache[dev].ev, cudaEventDisableTiming));
+    have[dev] = true;
+  }
+  *out = cache[dev];
+  return MI_OK;
+}
+
 }  // namespace
 
 // ======================================================================================== C ABI
@@ -2160,14 +2182,30 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
     MI_CUDA(cudaMemcpyAsync(W32, W_host, nDD * 4, cudaMemcpyHostToDevice, stream));
     MI_TRY(mi_cast_f32_to_bf16(W32, W16, static_cast<int64_t>(nDD), stream_));
   }
-  MI_TRY(mi_critic_loss_fwd_bwd(X16, Y16, bilinear ? W16 : nullptr, sid, B, D, critic, estimator, precision, inv_tau, loss,
-                                dX_host ? dX : nullptr, dY_host ? dY : nullptr, (dW_host && bilinear) ? dW : nullptr,
-                                core, core_bytes, stream_));
+  // dY is final before the dT contraction of the last panel and the dX / dW GEMMs: its copy to the host starts from an
+  // in-pass event on a second stream and runs under that work
+  CopySide side;
+  const bool early = dY_host != nullptr && copy_side(&side) == MI_OK;
+  bool recorded = false;
+  {
+    Bump cws(core, core_bytes, false);
+    MI_TRY(critic_impl(X16, Y16, bilinear ? W16 : nullptr, sid, B, D, critic, estimator, precision, inv_tau, loss,
+                       dX_host ? dX : nullptr, dY_host ? dY : nullptr, (dW_host && bilinear) ? dW : nullptr, cws, stream,
+                       early ? side.ev : nullptr, &recorded));
+  }
+  if (dY_host) {
+    cudaStream_t cs = stream;
+    if (early && recorded) {
+      MI_CUDA(cudaStreamWaitEvent(side.stream, side.ev, 0));
+      cs = side.stream;
+    }
+    MI_CUDA(cudaMemcpyAsync(dY_host, dY, nBD * 4, cudaMemcpyDeviceToHost, cs));
+  }
   MI_CUDA(cudaMemcpyAsync(loss_out_host, loss, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
   if (dX_host) MI_CUDA(cudaMemcpyAsync(dX_host, dX, nBD * 4, cudaMemcpyDeviceToHost, stream));
-  if (dY_host) MI_CUDA(cudaMemcpyAsync(dY_host, dY, nBD * 4, cudaMemcpyDeviceToHost, stream));
   if (dW_host && bilinear) MI_CUDA(cudaMemcpyAsync(dW_host, dW, nDD * 4, cudaMemcpyDeviceToHost, stream));
   MI_CUDA(cudaStreamSynchronize(stream));
+  if (early && recorded) MI_CUDA(cudaStreamSynchronize(side.stream));
   return MI_OK;
 }
 
