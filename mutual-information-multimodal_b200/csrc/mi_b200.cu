@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <functional>
 #include <mutex>
 #include <vector>
 #include <cstdlib>
@@ -382,6 +383,7 @@ __global__ void sum_merge_kernel(const float* __restrict__ part, int n_part, int
     const float hi = fmaxf(lse_neg, diag), lo = fminf(lse_neg, diag);
     lse_all = hi + log1pf(expf(lo - hi));
     wrow[row] = expf(r - lambda[0]);                                 // e^{rho - lambda}; e^{lambda - LSE} is applied at the end
+    if (r - lambda[0] > 60.f) atomicAdd(flag, 1);                    // lambda taken from an earlier panel was far too small
   }
   lsum[row] = l;
   row_out[row] = make_float4(lse_neg, cnt, diag, lse_all);
@@ -962,6 +964,12 @@ struct SingleFin {
   float alpha, gamma; int dv_like;
 };
 
+// The rows of Q may become available panel by panel (host-buffer entry point: the image embeddings are still crossing
+// PCIe while the first panels are processed).  before_panel(r0, rows) enqueues on the stream whatever makes
+// Q[r0, r0 + rows) valid; the per-row statistics of the bound are then taken per panel and lambda — any constant near the
+// largest bound works, it only centres e^{rho - lambda} — is the maximum over the FIRST panel (guarded in sum_merge_kernel).
+struct PanelFeed { std::function<int(long long, long long)> before_panel; };
+
 // Single-pass variant of the forward statistics + gradient pass (dv / infonce / row InfoNCE).
 // rho[q] = scale |Q_q| max_k |K_k| bounds every score of row q from above (Cauchy-Schwarz), so
 // P~ = incl * e^{S - rho} <= 1 needs no running max and no statistics pass BEFORE the panel is written:
@@ -978,7 +986,8 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                      float* row_out, float* oq_raw, float* ok_raw,
                      float* rho, float* wrow, float* lambda_out, int* flag_out, Bump& ws, cudaStream_t stream,
                      cudaEvent_t ev_after_k = nullptr, double* scal_out = nullptr, cudaEvent_t ev_after_scal = nullptr,
-                     const float* kmax_in = nullptr, cudaEvent_t ev_k_ready = nullptr, const struct SingleFin* fin = nullptr) {
+                     const float* kmax_in = nullptr, cudaEvent_t ev_k_ready = nullptr, const struct SingleFin* fin = nullptr,
+                     const struct PanelFeed* feed = nullptr) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
   const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
@@ -1016,8 +1025,10 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   MI_CUDA(cudaMemsetAsync(flag_out, 0, sizeof(int), stream));
   const Opnd Qe{Q.p, Q.ld, strict ? Q.split : 1}, Ke{K.p, K.ld, strict ? K.split : 1};
   // references
-  row_norm_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Dp, Bq, D, qnorm);
-  MI_LAUNCH_CHECK("row_norm_kernel");
+  if (feed == nullptr) {
+    row_norm_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Dp, Bq, D, qnorm);
+    MI_LAUNCH_CHECK("row_norm_kernel");
+  }
   if (kmax_in != nullptr) {
     kmax = const_cast<float*>(kmax_in);              // max_k |K_k| supplied by the caller (e.g. gathered with the study ids)
   } else {
@@ -1028,15 +1039,19 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
     max_reduce_kernel<<<1, 1024, 0, stream>>>(knorm, Bk, kmax);
     MI_LAUNCH_CHECK("max_reduce_kernel");
   }
-  rho_kernel<<<blocks_for(Bq, 256), 256, 0, stream>>>(qnorm, kmax, scale, Bq, rho);
-  MI_LAUNCH_CHECK("rho_kernel");
-  // lambda = the same bound for the largest row norm (of ALL ranks when qmax_in is given): a global constant
-  if (qmax_in) { rho_kernel<<<1, 32, 0, stream>>>(qmax_in, kmax, scale, 1, lambda_out); MI_LAUNCH_CHECK("rho_kernel"); }
-  else { max_reduce_kernel<<<1, 1024, 0, stream>>>(rho, Bq, lambda_out); MI_LAUNCH_CHECK("max_reduce_kernel"); }
+  if (feed == nullptr) {
+    rho_kernel<<<blocks_for(Bq, 256), 256, 0, stream>>>(qnorm, kmax, scale, Bq, rho);
+    MI_LAUNCH_CHECK("rho_kernel");
+    // lambda = the same bound for the largest row norm (of ALL ranks when qmax_in is given): a global constant
+    if (qmax_in) { rho_kernel<<<1, 32, 0, stream>>>(qmax_in, kmax, scale, 1, lambda_out); MI_LAUNCH_CHECK("rho_kernel"); }
+    else { max_reduce_kernel<<<1, 1024, 0, stream>>>(rho, Bq, lambda_out); MI_LAUNCH_CHECK("max_reduce_kernel"); }
+  }
   // from here on the K rows are read: wait for the caller's "K complete" event (the all-gather of the text embeddings)
   if (ev_k_ready != nullptr) MI_CUDA(cudaStreamWaitEvent(stream, ev_k_ready, 0));
-  diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split, q_offset, Bq, D, Dp, scale, diag);
-  MI_LAUNCH_CHECK("diag_kernel");
+  if (feed == nullptr) {
+    diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split, q_offset, Bq, D, Dp, scale, diag);
+    MI_LAUNCH_CHECK("diag_kernel");
+  }
   // V^T for the P K product
   if (!mn) {
     if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
@@ -1047,6 +1062,17 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
 
   for (long long r0 = 0; r0 < Bq; r0 += panel_rows) {
     const long long rows = (Bq - r0 < panel_rows) ? (Bq - r0) : panel_rows;
+    if (feed != nullptr) {        // this panel's Q rows arrive now: their bound, the positive-pair scores, and (once) lambda
+      MI_TRY(feed->before_panel(r0, rows));
+      row_norm_kernel<<<blocks_for(rows * 32, 256), 256, 0, stream>>>(Qe.p + r0 * Qe.ld, Qe.ld, Qe.split, Dp, rows, D, qnorm + r0);
+      MI_LAUNCH_CHECK("row_norm_kernel");
+      rho_kernel<<<blocks_for(rows, 256), 256, 0, stream>>>(qnorm + r0, kmax, scale, rows, rho + r0);
+      MI_LAUNCH_CHECK("rho_kernel");
+      if (r0 == 0) { max_reduce_kernel<<<1, 1024, 0, stream>>>(rho, rows, lambda_out); MI_LAUNCH_CHECK("max_reduce_kernel"); }
+      diag_kernel<<<blocks_for(rows * 32, 256), 256, 0, stream>>>(Qe.p + r0 * Qe.ld, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split,
+                                                                  q_offset + r0, rows, D, Dp, scale, diag + r0);
+      MI_LAUNCH_CHECK("diag_kernel");
+    }
     // (1) score tiles -> P~ panel + row sums
     Sched sc;
     sc.n_mblk = static_cast<int>(cdiv(rows, rows_per_mblk()));
@@ -1154,8 +1180,9 @@ inline bool grads_or_plan_single(int estimator, int precision) {
 int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, long long B, long long D,
                 int critic, int estimator, int precision, float inv_tau,
                 double* loss_out, float* dX, float* dY, float* dW, Bump& ws, cudaStream_t stream,
-                cudaEvent_t ev_dy_final = nullptr, bool* ev_recorded = nullptr) {   // event recorded once dY is final (the
+                cudaEvent_t ev_dy_final = nullptr, bool* ev_recorded = nullptr,     // event recorded once dY is final (the
                                                                                      // dT / dX / dW work follows it)
+                const std::function<int(long long, long long)>* x_ready = nullptr) { // single-pass only: X rows arrive per panel
   if (B <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   if (estimator < MI_EST_DV || estimator > MI_EST_INFONCE_SYM) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
@@ -1204,7 +1231,9 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
       if (tsplit == 2) MI_CUDA(cudaMemsetAsync(T, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
     }
     // T = X W  (B operand of the engine is [N, K] = W^T: W itself read MN-major, or the transposed copy)
-    if (mn) {
+    if (mn && x_ready != nullptr && single) {
+      // projected panel by panel inside the pass (see PanelFeed)
+    } else if (mn) {
       GemmArgs g;
       g.a = MapSpec{X, B, D, D};
       g.b_mn = true; g.b = MapSpec{W, D, D, D};
@@ -1224,9 +1253,27 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     // the loss is finalised inside the pass and, when dY is wanted, the last panel's contraction finishes dY in its epilogue
     SingleFin fin{loss_out, lse_f, B, estimator, inv_tau, gam, dv_like ? 1 : 0};
     const bool fused_k = dY != nullptr;
+    PanelFeed feed;
+    const bool streamed = x_ready != nullptr && mn && !ws.dry;
+    if (streamed) {
+      feed.before_panel = [&](long long r0, long long rows) -> int {
+        MI_TRY((*x_ready)(r0, rows));
+        if (bilinear) {                                  // T[r0 : r0 + rows] = X[r0 : r0 + rows] W
+          GemmArgs g;
+          g.a = MapSpec{X + r0 * D, rows, D, D};
+          g.b_mn = true; g.b = MapSpec{W, D, D, D};
+          g.M = rows; g.N = D; g.k_blocks = static_cast<int>(cdiv(D, bk()));
+          g.out_bf16 = T + r0 * ldT; g.ld_out16 = ldT; g.out_bf16_lo = tsplit == 2 ? T + r0 * ldT + Dp : nullptr;
+          Bump none(nullptr, 0, false);
+          MI_TRY(run_gemm(g, none, stream));
+        }
+        return MI_OK;
+      };
+    }
     MI_TRY(single_pass_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, precision, gam, nullptr,
                             rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream,
-                            fused_k ? ev_dy_final : nullptr, scal_r, nullptr, nullptr, nullptr, fused_k ? &fin : nullptr));
+                            fused_k ? ev_dy_final : nullptr, scal_r, nullptr, nullptr, nullptr, fused_k ? &fin : nullptr,
+                            streamed ? &feed : nullptr));
     if (fused_k && ev_dy_final && ev_recorded && !ws.dry) *ev_recorded = true;
     ws.release(mk);
     if (!ws.dry) {
@@ -1898,7 +1945,8 @@ int device_check() {
 }
 
 // second stream + event of the host-buffer entry point (one per device, created on first use)
-struct CopySide { cudaStream_t stream; cudaEvent_t ev; };
+constexpr int kMaxFeedChunks = 64;
+struct CopySide { cudaStream_t stream; cudaEvent_t ev; cudaEvent_t ev_y; cudaEvent_t ev_x[kMaxFeedChunks]; };
 int copy_side(CopySide* out) {
   static std::mutex mu;
   static CopySide cache[64];
@@ -1909,6 +1957,8 @@ int copy_side(CopySide* out) {
   if (!have[dev]) {
     MI_CUDA(cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking));
     MI_CUDA(cudaEventCreateWithFlags(&cache[dev].ev, cudaEventDisableTiming));
+    MI_CUDA(cudaEventCreateWithFlags(&cache[dev].ev_y, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxFeedChunks; ++i) MI_CUDA(cudaEventCreateWithFlags(&cache[dev].ev_x[i], cudaEventDisableTiming));
     have[dev] = true;
   }
   *out = cache[dev];
@@ -2173,25 +2223,56 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
   ws.off = (ws.off + 255) & ~static_cast<size_t>(255);
   uint8_t* core = ws.base + ws.off;
   const size_t core_bytes = dev_scratch_bytes - ws.off;
-  MI_CUDA(cudaMemcpyAsync(X32, X_host, nBD * 4, cudaMemcpyHostToDevice, stream));
-  MI_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, stream));
+  // Input side: the text embeddings go first; the image embeddings follow in row panels on a second stream, each with
+  // its own event, and the single pass consumes them panel by panel (cast + projection inside the pass) while the rest
+  // is still crossing PCIe.  Output side: dY is final before the last panel's dT contraction and the dX / dW GEMMs, its
+  // copy back starts from an in-pass event on the second stream.
+  CopySide side;
+  const bool have_side = copy_side(&side) == MI_OK;
+  const long long chunk_rows = panel_mblks(B, B, D, precision & 1) * rows_per_mblk();
+  const long long n_chunks = cdiv(B, chunk_rows);
+  const bool want_grads = dX_host || dY_host || (dW_host && bilinear);
+  const bool streamed = have_side && want_grads && g_mn_operands && grads_or_plan_single(estimator, precision) &&
+                        n_chunks <= kMaxFeedChunks;
   MI_CUDA(cudaMemcpyAsync(sid, sid_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, stream));
-  MI_TRY(mi_cast_f32_to_bf16(X32, X16, static_cast<int64_t>(nBD), stream_));
-  MI_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
   if (bilinear) {
     MI_CUDA(cudaMemcpyAsync(W32, W_host, nDD * 4, cudaMemcpyHostToDevice, stream));
     MI_TRY(mi_cast_f32_to_bf16(W32, W16, static_cast<int64_t>(nDD), stream_));
   }
-  // dY is final before the dT contraction of the last panel and the dX / dW GEMMs: its copy to the host starts from an
-  // in-pass event on a second stream and runs under that work
-  CopySide side;
-  const bool early = dY_host != nullptr && copy_side(&side) == MI_OK;
+  std::function<int(long long, long long)> x_ready;
+  if (streamed) {
+    MI_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, side.stream));
+    MI_CUDA(cudaEventRecord(side.ev_y, side.stream));
+    for (long long c = 0; c < n_chunks; ++c) {
+      const long long r0 = c * chunk_rows, rows = (B - r0 < chunk_rows) ? (B - r0) : chunk_rows;
+      MI_CUDA(cudaMemcpyAsync(X32 + r0 * D, X_host + r0 * D, static_cast<size_t>(rows) * D * 4, cudaMemcpyHostToDevice, side.stream));
+      MI_CUDA(cudaEventRecord(side.ev_x[c], side.stream));
+    }
+    MI_CUDA(cudaStreamWaitEvent(stream, side.ev_y, 0));
+    MI_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
+    x_ready = [&](long long r0, long long rows) -> int {
+      if (r0 % chunk_rows != 0) return MI_ERR_BAD_ARG;                // the pass walks the same panels
+      MI_CUDA(cudaStreamWaitEvent(stream, side.ev_x[r0 / chunk_rows], 0));
+      return mi_cast_f32_to_bf16(X32 + r0 * D, X16 + r0 * D, static_cast<int64_t>(rows * D), stream_);
+    };
+  } else {
+    MI_CUDA(cudaMemcpyAsync(X32, X_host, nBD * 4, cudaMemcpyHostToDevice, stream));
+    MI_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, stream));
+    MI_TRY(mi_cast_f32_to_bf16(X32, X16, static_cast<int64_t>(nBD), stream_));
+    MI_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
+  }
+  const bool early = dY_host != nullptr && have_side;
   bool recorded = false;
   {
     Bump cws(core, core_bytes, false);
-    MI_TRY(critic_impl(X16, Y16, bilinear ? W16 : nullptr, sid, B, D, critic, estimator, precision, inv_tau, loss,
-                       dX_host ? dX : nullptr, dY_host ? dY : nullptr, (dW_host && bilinear) ? dW : nullptr, cws, stream,
-                       early ? side.ev : nullptr, &recorded));
+    const int st = critic_impl(X16, Y16, bilinear ? W16 : nullptr, sid, B, D, critic, estimator, precision, inv_tau, loss,
+                               dX_host ? dX : nullptr, dY_host ? dY : nullptr, (dW_host && bilinear) ? dW : nullptr, cws, stream,
+                               early ? side.ev : nullptr, &recorded, streamed ? &x_ready : nullptr);
+    if (st != MI_OK) {                                   // leave no copy in flight into the caller's scratch
+      if (have_side) (void)cudaStreamSynchronize(side.stream);
+      (void)cudaStreamSynchronize(stream);
+      return st;
+    }
   }
   if (dY_host) {
     cudaStream_t cs = stream;

@@ -271,6 +271,42 @@ def test_host_buffer_abi_matches_device_call(env):
 
 
 @pytest.mark.parametrize("critic", ["dot", "bilinear"])
+def test_host_buffer_abi_streams_panels(env, critic):
+    """Several row panels: the host entry point feeds the image embeddings panel by panel from a second stream (cast and
+    projection inside the pass, lambda from the first panel) and copies dY back from an in-pass event — the result must
+    equal the device-pointer call on the same inputs."""
+    mi_b200, ops, mo, dev = env
+    from mi_b200 import _lib
+    lib = _lib.load()
+    B, D = 24576, 64                     # 2 panels of 18944 rows at D = 64
+    bil = critic == "bilinear"
+    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=9, dup_frac=0.05, bilinear=bil)
+    Xh, Yh = X.bfloat16().float().contiguous().pin_memory(), Y.bfloat16().float().contiguous().pin_memory()
+    Wh = W.bfloat16().float().contiguous().pin_memory() if bil else None
+    sh = sid.to(torch.int32).contiguous().pin_memory()
+    inv_tau = 1.0 if bil else 1.0 / math.sqrt(D)
+    for prec_name, prec in (("fast", 0), ("strict", 1)):
+        n = lib.mi_critic_host_scratch_bytes(B, D, int(bil), 0, prec, 1)
+        scratch = torch.empty(n, dtype=torch.uint8, device=dev)
+        loss = torch.zeros(8, dtype=torch.float64).pin_memory()
+        dX, dY = torch.zeros(B, D).pin_memory(), torch.zeros(B, D).pin_memory()
+        dW = torch.zeros(D, D).pin_memory() if bil else None
+        p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        st = lib.mi_critic_loss_fwd_bwd_host(p(Xh), p(Yh), p(Wh), p(sh), B, D, int(bil), 0, prec, inv_tau, p(loss), p(dX), p(dY),
+                                             p(dW), p(scratch), n, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert st == 0, lib.mi_status_string(st)
+        ref, rX, rY, rW = ops.critic_loss_fwd_bwd(Xh.to(dev), Yh.to(dev), None if Wh is None else Wh.to(dev), sh.to(dev), "dv",
+                                                  prec_name, inv_tau, True)
+        torch.cuda.synchronize()
+        assert float(loss[7]) == 0.0 and float(ref[7]) == 0.0
+        assert abs(float(loss[0]) - float(ref[0])) < 1e-6 * max(1.0, abs(float(ref[0])))
+        tol = 1e-4 if prec_name == "strict" else 1e-2        # fast: a 1-ulp fp32 difference may flip a bf16 rounding of dT
+        assert _rel(dX, rX.cpu()) < tol and _rel(dY, rY.cpu()) < tol
+        if bil:
+            assert _rel(dW, rW.cpu()) < tol
+
+
+@pytest.mark.parametrize("critic", ["dot", "bilinear"])
 def test_full_size_properties(env, critic):
     """B = 65536, D = 1024 (the BASELINE metric's size): the CPU oracle cannot form the 4.3e9 pairs,
     so parity is checked through (1) sampled rows / columns recomputed exactly on the CPU in fp64
