@@ -39,6 +39,31 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().mi_abi_version() == 3
 
 
+def test_ctypes_prototypes_match_the_header_signatures():
+    """Every ctypes prototype has exactly as many arguments as the declaration in include/mi_b200.h, pointer arguments are
+    bound as pointers and 64-bit sizes as 64-bit integers (a mismatch would only show up as a crash on the GPU box)."""
+    import ctypes
+    from mi_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "mi_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = dict(re.findall(r"\b(mi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(decls) == set(_lib.PROTOTYPES)
+    for name, params in decls.items():
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
+        _, argtypes = _lib.PROTOTYPES[name]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+        for q, t in zip(plist, argtypes):
+            if "*" in q or q.startswith("mi_stream_t"):
+                assert t is ctypes.c_void_p, (name, q)
+            elif q.startswith(("int64_t", "size_t")):
+                assert ctypes.sizeof(t) == 8 and t is not ctypes.c_void_p, (name, q)
+            elif q.startswith("float"):
+                assert t is ctypes.c_float, (name, q)
+            elif q.startswith("int"):
+                assert t is ctypes.c_int, (name, q)
+
+
 def test_status_strings_and_planning_without_gpu():
     from mi_b200 import _lib
     lib = _lib.load()
