@@ -220,7 +220,7 @@ int mi_profile_read(double* ms /*[3]*/, int64_t* launches /*[3]*/);
 /* bring-up / A-B knob: 2 (default) = CTA pairs, cta_group::2 MMAs with M = 256; 1 = single-CTA M = 128.
  * Also settable through the environment variable MI_CTA_GROUP before the first call. */
 void mi_set_cta_group(int group);
-void mi_set_mlp_panel_pairs(int64_t pairs); /* pairs per row panel of the MLP-critic path (default 2^19; tests use small values) */
+void mi_set_mlp_panel_pairs(int64_t pairs); /* pairs per row panel of the MLP-critic path (default 2^20; tests use small values) */
 /* Multi-GPU overlap: the tile-engine launches that follow `event_after_outk` inside mi_score_single_pass / mi_score_grad
  * use (SM count - n) SMs, so the collective the caller starts at that event (reduce-scatter of the dY contributions)
  * finds free SMs instead of queueing behind a persistent 148-CTA grid.  0 (default) = use every SM. */

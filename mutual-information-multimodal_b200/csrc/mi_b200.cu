@@ -1568,7 +1568,7 @@ struct MlpDims { long long B, D, H1, H2; };
 struct MlpParams { const float *W1, *b1, *W2, *b2, *W3, *b3; };
 struct MlpGrads { float *dX, *dY, *dW1, *db1, *dW2, *db2, *dW3, *db3; };
 
-long long g_mlp_max_pairs = 1LL << 19;                    // bounds the panel buffers (H, dZ2, dZ1) to a few GB
+long long g_mlp_max_pairs = 1LL << 20;                    // bounds the panel buffers (H, dZ2, dZ1): 5 GB fast, 10 GB strict
 inline long long mlp_panel_rows(long long B) {
   const long long max_pairs = g_mlp_max_pairs;
   long long R = max_pairs / B;
@@ -2004,7 +2004,7 @@ void mi_set_debug(int v) { g_debug = v; }
 void mi_set_single_pass(int on) { g_single_pass = on != 0; }
 void mi_set_mn_operands(int on) { g_mn_operands = on != 0; }
 void mi_set_overlap_reserve_sms(int n) { g_overlap_reserve_sms = (n > 0 && n < 128) ? (n & ~1) : 0; }
-void mi_set_mlp_panel_pairs(int64_t pairs) { g_mlp_max_pairs = pairs > 0 ? pairs : (1LL << 19); }
+void mi_set_mlp_panel_pairs(int64_t pairs) { g_mlp_max_pairs = pairs > 0 ? pairs : (1LL << 20); }
 void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
 int mi_get_cta_group(void) { return cta_group(); }
 
