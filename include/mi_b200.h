@@ -146,6 +146,9 @@ int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K,
                          const float* knorm_max_in /* device scalar max_k |K_k| or NULL (computed here from K) */,
                          void* event_k_ready /* cudaEvent_t or NULL: the K rows (an all-gather in flight) are complete once this
                                                 event fires; the mask pre-pass and the Q statistics are enqueued BEFORE the wait */,
+                         int k_local_valid /* 1: rows [q_offset, q_offset + Bq) of K (this rank's own text embeddings) are valid
+                                              already — with knorm_max_in given, the positive-pair scores and the score tiles
+                                              of the own column block also run before the wait */,
                          void* workspace, size_t workspace_bytes, mi_stream_t stream);
 /* Multi-GPU glue: the ranks' scal_out rows [world][8] (all-gathered) -> loss_out (fp64[8], layout of mi_critic_loss_fwd_bwd,
  * global batch B_global, estimators DV / INFONCE_REF / INFONCE_ROW) and the global log-sum-exp as a float (lse_out[1]).

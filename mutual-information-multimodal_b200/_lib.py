@@ -43,7 +43,7 @@ PROTOTYPES = {
     "mi_row_norm_max": (c_int, [c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "mi_score_single_pass": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
                                      c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                     c_vp, c_vp, c_vp, c_sz, c_vp]),
+                                     c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
     "mi_merge_scalars": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "mi_single_finalize_q": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_f32, c_f32, c_vp, c_i64, c_int,
                                      c_vp, c_vp, c_i64, c_int, c_vp]),

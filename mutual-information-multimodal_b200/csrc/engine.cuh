@@ -54,6 +54,7 @@ struct Sched {
   int n_ntile;    // N tiles of 256 columns
   int n_split;    // contiguous N-range splits per M block
   int n_ksplit;   // K splits (split-K GEMM), 1 otherwise
+  int nt_base;    // first N tile of this launch (a launch may cover a sub-range of the columns)
   int order;      // 0: m fastest (concurrent units share the N range), 1: ksplit, split fastest
   int k_blocks;   // number of K blocks (block_k wide) per tile, all segments
   // K segments: block kb belongs to segment kb / seg_len and reads A at K block a_seg[seg] + kb % seg_len,
@@ -80,8 +81,8 @@ __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
     r.ks = u % sc.n_ksplit; int t = u / sc.n_ksplit;
     r.s = t % sc.n_split; r.m = t / sc.n_split;
   }
-  r.nt0 = (int)(((long long)r.s * sc.n_ntile) / sc.n_split);
-  r.nt1 = (int)(((long long)(r.s + 1) * sc.n_ntile) / sc.n_split);
+  r.nt0 = sc.nt_base + (int)(((long long)r.s * sc.n_ntile) / sc.n_split);
+  r.nt1 = sc.nt_base + (int)(((long long)(r.s + 1) * sc.n_ntile) / sc.n_split);
   r.kb0 = (int)(((long long)r.ks * sc.k_blocks) / sc.n_ksplit);
   r.kb1 = (int)(((long long)(r.ks + 1) * sc.k_blocks) / sc.n_ksplit);
   return r;

@@ -216,6 +216,7 @@ int choose_split(int n_mblk, int n_ntile, int U) {
 }
 
 void single_segment(Sched& sc) {
+  sc.nt_base = 0;
   sc.seg_len = sc.k_blocks;
   for (int i = 0; i < 4; ++i) { sc.a_seg[i] = 0; sc.b_seg[i] = 0; sc.a_moff[i] = 0; sc.b_noff[i] = 0; }
 }
@@ -987,7 +988,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                      float* rho, float* wrow, float* lambda_out, int* flag_out, Bump& ws, cudaStream_t stream,
                      cudaEvent_t ev_after_k = nullptr, double* scal_out = nullptr, cudaEvent_t ev_after_scal = nullptr,
                      const float* kmax_in = nullptr, cudaEvent_t ev_k_ready = nullptr, const struct SingleFin* fin = nullptr,
-                     const struct PanelFeed* feed = nullptr) {
+                     const struct PanelFeed* feed = nullptr, bool k_local_valid = false) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
   const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
@@ -1010,7 +1011,9 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   const size_t qt_elems = std::max(static_cast<size_t>(D) * ld_qt, static_cast<size_t>(panel_rows) * ld_qs);   // either layout
   bf* Qt = ok_raw || ws.dry ? ws.take<bf>(qt_elems) : nullptr;
   bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
-  float* part = ws.take<float>(static_cast<size_t>(max_split > 64 ? 64 : max_split) * mi::kColQuarters * panel_rows);
+  // (x3: the first panel may be written by up to three launches — own columns first, the rest once K has arrived)
+  const size_t part_slices = static_cast<size_t>(max_split > 64 ? 64 : max_split) * mi::kColQuarters;
+  float* part = ws.take<float>(3 * part_slices * panel_rows);
   float* qnorm = ws.take<float>(Bq);
   float* knorm = ws.take<float>(Bk);
   float* kmax = ws.take<float>(1);
@@ -1046,8 +1049,13 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
     if (qmax_in) { rho_kernel<<<1, 32, 0, stream>>>(qmax_in, kmax, scale, 1, lambda_out); MI_LAUNCH_CHECK("rho_kernel"); }
     else { max_reduce_kernel<<<1, 1024, 0, stream>>>(rho, Bq, lambda_out); MI_LAUNCH_CHECK("max_reduce_kernel"); }
   }
-  // from here on the K rows are read: wait for the caller's "K complete" event (the all-gather of the text embeddings)
-  if (ev_k_ready != nullptr) MI_CUDA(cudaStreamWaitEvent(stream, ev_k_ready, 0));
+  // from here on the K rows are read: wait for the caller's "K complete" event (the all-gather of the text embeddings).
+  // When the caller vouches for this rank's own rows (k_local_valid) the wait moves further down: the positive-pair
+  // scores and the score tiles of the own column block need nothing else, so they run under the all-gather.
+  const long long own_t0 = q_offset / mi::TILE_N, own_t1 = (q_offset + Bq) / mi::TILE_N;
+  const bool own_first = ev_k_ready != nullptr && k_local_valid && kmax_in != nullptr && feed == nullptr && mn &&
+                         (q_offset % mi::TILE_N) == 0 && (Bq % mi::TILE_N) == 0 && Bq < Bk;
+  if (ev_k_ready != nullptr && !own_first) MI_CUDA(cudaStreamWaitEvent(stream, ev_k_ready, 0));
   if (feed == nullptr) {
     diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split, q_offset, Bq, D, Dp, scale, diag);
     MI_LAUNCH_CHECK("diag_kernel");
@@ -1073,26 +1081,42 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                                                                   q_offset + r0, rows, D, Dp, scale, diag + r0);
       MI_LAUNCH_CHECK("diag_kernel");
     }
-    // (1) score tiles -> P~ panel + row sums
-    Sched sc;
-    sc.n_mblk = static_cast<int>(cdiv(rows, rows_per_mblk()));
-    sc.n_ntile = n_ntile;
-    sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
-    if (sc.n_split > 64) sc.n_split = 64;
-    sc.n_ksplit = 1; sc.order = 0;
-    MI_TRY(score_segments(sc, Qe, Ke, D));
-    const int rows_padded = sc.n_mblk * rows_per_mblk();
-    mi::EpiPStore::Params ep;
-    ep.mask = mi::MaskInfo{mb.excl + r0, mb.n_same + r0, sid_q + r0, mb.sidk_pad};
-    ep.q_rows = static_cast<int>(rows); ep.k_cols = static_cast<int>(Bk);
-    ep.q_offset = q_offset + r0; ep.scale = scale;
-    ep.refq = rho + r0; ep.ln_wq = 0.f; ep.use_q = 1;
-    ep.refk2 = nullptr; ep.use_k = 0; ep.include_diag = include_diag;
-    ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
-    ep.sum_part = part; ep.rows_padded = rows_padded; ep.dbg = g_debug;
-    MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
-                                        MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
-    sum_merge_kernel<<<blocks_for(rows, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(rows),
+    // (1) score tiles -> P~ panel + row sums; a launch covers the N tiles [t0, t1) and appends its partial row sums
+    const int n_mblk_p = static_cast<int>(cdiv(rows, rows_per_mblk()));
+    const int rows_padded = n_mblk_p * rows_per_mblk();
+    int n_part = 0;
+    auto score_tiles = [&](long long t0, long long t1) -> int {
+      if (t1 <= t0) return MI_OK;
+      Sched sc;
+      sc.n_mblk = n_mblk_p;
+      sc.n_ntile = static_cast<int>(t1 - t0);
+      sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
+      if (sc.n_split > 64) sc.n_split = 64;
+      sc.n_ksplit = 1; sc.order = 0;
+      MI_TRY(score_segments(sc, Qe, Ke, D));
+      sc.nt_base = static_cast<int>(t0);
+      mi::EpiPStore::Params ep;
+      ep.mask = mi::MaskInfo{mb.excl + r0, mb.n_same + r0, sid_q + r0, mb.sidk_pad};
+      ep.q_rows = static_cast<int>(rows); ep.k_cols = static_cast<int>(Bk);
+      ep.q_offset = q_offset + r0; ep.scale = scale;
+      ep.refq = rho + r0; ep.ln_wq = 0.f; ep.use_q = 1;
+      ep.refk2 = nullptr; ep.use_k = 0; ep.include_diag = include_diag;
+      ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
+      ep.sum_part = part + static_cast<size_t>(n_part) * rows_padded; ep.rows_padded = rows_padded; ep.dbg = g_debug;
+      MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
+                                          MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
+      n_part += sc.n_split * mi::kColQuarters;
+      return MI_OK;
+    };
+    if (own_first && r0 == 0) {
+      MI_TRY(score_tiles(own_t0, own_t1));                               // this rank's own columns: K rows already here
+      MI_CUDA(cudaStreamWaitEvent(stream, ev_k_ready, 0));               // the other ranks' text embeddings
+      MI_TRY(score_tiles(0, own_t0));
+      MI_TRY(score_tiles(own_t1, n_ntile));
+    } else {
+      MI_TRY(score_tiles(0, n_ntile));
+    }
+    sum_merge_kernel<<<blocks_for(rows, 128), 128, 0, stream>>>(part, n_part, rows_padded, static_cast<int>(rows),
                                                                 rho + r0, lambda_out, mb.n_same + r0, static_cast<int>(Bk), diag + r0,
                                                                 include_diag, inv_bg, reinterpret_cast<float4*>(row_out) + r0,
                                                                 lsum + r0, wrow + r0, flag_out);
@@ -2122,7 +2146,7 @@ int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K,
                          int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag, int precision, float inv_bg,
                          const float* qnorm_max_in, float* row_out, double* scal_out, float* oq_raw, float* ok_raw,
                          float* rho, float* wrow, float* lambda_out, int32_t* flag_out, void* event_after_outk,
-                         void* event_after_scal, const float* knorm_max_in, void* event_k_ready,
+                         void* event_after_scal, const float* knorm_max_in, void* event_k_ready, int k_local_valid,
                          void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
   MI_TRY(device_check());
   if (q_offset < 0 || q_offset + Bq > Bk || !scal_out) return MI_ERR_BAD_ARG;
@@ -2133,7 +2157,7 @@ int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K,
                           sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, precision, inv_bg, qnorm_max_in,
                           row_out, oq_raw, ok_raw, rho, wrow, lambda_out, flag_out, ws, stream,
                           reinterpret_cast<cudaEvent_t>(event_after_outk), scal_out, reinterpret_cast<cudaEvent_t>(event_after_scal),
-                          knorm_max_in, reinterpret_cast<cudaEvent_t>(event_k_ready)));
+                          knorm_max_in, reinterpret_cast<cudaEvent_t>(event_k_ready), nullptr, nullptr, k_local_valid != 0));
   return MI_OK;
 }
 int mi_merge_scalars(const double* scal_all, int world, int64_t B_global, int estimator, double* loss_out, float* lse_out,

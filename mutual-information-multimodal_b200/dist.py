@@ -135,7 +135,7 @@ class _A2ASum:
 
 
 def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
-                      precision, qmax, world, group, nccl, kmax=None, ev_y=None):
+                      precision, qmax, world, group, nccl, kmax=None, ev_y=None, own_first=False):
     """dv / infonce / row InfoNCE with ONE score computation per rank (see mi_score_single_pass)."""
     bilinear = Wb is not None
     strict = precision == "strict"
@@ -147,7 +147,8 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
         ev.record(); ev_s.record()                    # (creates the CUDA events; the library re-records them in the pass)
     sp = backend.score_single_pass(T_local, Y_all, sid_loc, sid_all, off, inv_tau, not dv_like, precision, gamma,
                                    qmax=qmax, want_k=True, event_after_k=ev,
-                                   **({"event_after_scal": ev_s, "kmax": kmax, "event_k_ready": ev_y} if nccl else {}))
+                                   **({"event_after_scal": ev_s, "kmax": kmax, "event_k_ready": ev_y,
+                                       "k_local_valid": own_first} if nccl else {}))
     scal = sp["scal"].reshape(1, 8)
     if nccl:
         # the loss scalars are final BEFORE the panel's two contractions: exchange them first, then start the big
@@ -234,9 +235,18 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         if world > 1:
             dist.all_reduce(qmax, op=dist.ReduceOp.MAX, group=group)
     Y_all, ev_y = Yb, None
+    # (experiment knob, off by default: correct on NCCL — scripts/dist_check.py — but not yet measured on 8 GPUs; at 2 GPUs
+    #  the all-gather it hides is 1 % of the step and the A/B was within the thermal drift of the box)
+    own_first = nccl and single and kmax is not None and os.environ.get("MI_OWN_COLUMNS_FIRST", "0") == "1"
     if world > 1:
         Y_all = torch.empty((Bg, D), dtype=Yb.dtype, device=Yb.device)
-        y_work = dist.all_gather_into_tensor(Y_all, Yb, group=group, async_op=True)
+        if own_first:
+            # in-place all-gather: this rank's rows are in their slot before the collective starts (NCCL leaves the own
+            # slot alone), so the pass can score its own column block while the other ranks' rows are still arriving
+            Y_all[off:off + Bl].copy_(Yb)
+            y_work = dist.all_gather_into_tensor(Y_all, Y_all[off:off + Bl], group=group, async_op=True)
+        else:
+            y_work = dist.all_gather_into_tensor(Y_all, Yb, group=group, async_op=True)
         if nccl and single:
             # the compute stream does NOT wait here: the library waits for this event right before it first reads
             # the text embeddings, after the mask pre-pass and the image-side statistics are enqueued
@@ -261,7 +271,7 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         backend.set_overlap_reserve_sms(int(os.environ.get("MI_RS_RESERVE_SMS", "0")))
     if single:
         return _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
-                                 precision, qmax, world, group, nccl, kmax=kmax, ev_y=ev_y)
+                                 precision, qmax, world, group, nccl, kmax=kmax, ev_y=ev_y, own_first=own_first)
 
     # ---- statistics (S never materialised)
     rows_r, scal_r = backend.score_stats(T_local, Y_all, sid_loc, sid_all, off, inv_tau)

@@ -273,7 +273,7 @@ def score_single_pass(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
                       inv_bg: float, qmax: Optional[torch.Tensor] = None, want_k: bool = True,
                       event_after_k: Optional["torch.cuda.Event"] = None,
                       event_after_scal: Optional["torch.cuda.Event"] = None, kmax: Optional[torch.Tensor] = None,
-                      event_k_ready: Optional["torch.cuda.Event"] = None) -> dict:
+                      event_k_ready: Optional["torch.cuda.Event"] = None, k_local_valid: bool = False) -> dict:
     """mi_score_single_pass: statistics and raw gradient contractions from ONE score computation."""
     _need_cuda(Q, K, sid_q, sid_k, qmax)
     lib = _lib.load()
@@ -297,7 +297,7 @@ def score_single_pass(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
                                     None if event_after_k is None else C.c_void_p(event_after_k.cuda_event),
                                     None if event_after_scal is None else C.c_void_p(event_after_scal.cuda_event),
                                     _ptr(kmax), None if event_k_ready is None else C.c_void_p(event_k_ready.cuda_event),
-                                    _ptr(ws), ws.numel(), _stream()), "mi_score_single_pass")
+                                    int(k_local_valid), _ptr(ws), ws.numel(), _stream()), "mi_score_single_pass")
     return r
 
 

@@ -72,7 +72,7 @@ def row_norm_max(A):
 
 
 def score_single_pass(Q, K, sid_q, sid_k, q_offset, scale, include_diag, precision, inv_bg, qmax=None, want_k=True,
-                      event_after_k=None, event_after_scal=None, kmax=None, event_k_ready=None):
+                      event_after_k=None, event_after_scal=None, kmax=None, event_k_ready=None, k_local_valid=False):
     S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
     qn, kn = Q.double().norm(dim=1), K.double().norm(dim=1)
     kmx = kn.max() if kmax is None else kmax.double().reshape(())
