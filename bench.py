@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one pass of the hot path (score statistics + both gradient passes + the bilinear
-projections) over one batch of synthetic CXR-shaped embeddings.  N=1: B=65536, D=1024 (the size the
+A "step" is one pass of the hot path (single pass: score tiles -> loss statistics and both gradient
+contractions, plus the bilinear projections and their backward) over one batch of synthetic CXR-shaped embeddings.  N=1: B=65536, D=1024 (the size the
 metric is quoted on).  N>1: the same global batch sharded by rows, strong scaling.
 Prints ONE JSON line on rank 0.
 """
