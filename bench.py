@@ -279,6 +279,7 @@ def run_ours(a):
     ms_per_step = total_ms / a.steps
     value = B * B / (ms_per_step * 1e-3)
     loss_val = float(last[0][0].item()) if world == 1 else float(last[0].item())
+    guard_rows = float(last[0][7].item()) if world == 1 else None
 
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     e2e = None
@@ -363,7 +364,7 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "global_batch": B, "dim": D, "critic": a.critic,
                    "estimator": a.estimator, "precision": a.precision, "parallelism": f"row-sharded x{world}",
                    "l2": "inputs (2 x %d MB bf16 + >1 GB dS panel per pass) exceed the 126 MB L2; no flush needed" % (B * D * 2 >> 20),
-                   "loss": loss_val},
+                   "loss": loss_val, "guard_rows": guard_rows},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
                      "frac": ach / pk["sustained"], "traffic": traffic,
                      "traffic_note": "DRAM bytes per step summed over the step's launches (ncu capture in profiles/), "

@@ -12,7 +12,9 @@
  * ctypes stub).  Conventions: all pointers are DEVICE pointers owned by the caller (except where a
  * name ends in _host); row-major; bf16 operands; fp32 / fp64 results; nothing is allocated or freed
  * inside; work is enqueued on `stream` and the call returns without synchronising; return value is
- * 0 on success or a negative mi_status.  Re-entrant; one call per workspace at a time.
+ * 0 on success or a negative mi_status.  Re-entrant across host threads / streams (per-call state is thread-local;
+ * the mi_set_* knobs are process-wide and meant to be set once, before the first call); one call per workspace at a
+ * time.  Study ids: any int32 value is a legal id (no reserved values).
  *
  * Score block:   S[q,k] = scale * <Q[q,:], K[k,:]>,   q in [0,Bq), k in [0,Bk)
  * Sample of row q is column (q_offset + q)  (the positive pair / diagonal).
@@ -48,9 +50,9 @@ enum mi_estimator { MI_EST_DV = 0, MI_EST_INFONCE_REF = 1, MI_EST_INFONCE_ROW = 
 
 enum mi_precision { MI_PREC_BF16_FAST = 0,   /* dS panel rounded once to bf16 */
                     MI_PREC_BF16_STRICT = 1, /* dS = hi + lo bf16 split (fp32-accumulate mode) */
-                    MI_PREC_TWO_PASS = 2     /* flag (OR it in): statistics pass + gradient pass with the exact
-                                                log-sum-exp references, instead of the single pass that uses a
-                                                Cauchy-Schwarz score bound as reference (mi_critic_loss_fwd_bwd) */ };
+                    MI_PREC_TWO_PASS = 2     /* flag (OR it in): exact softmax references (a statistics pass over EVERY
+                                                column before the gradient pass) instead of sampled ones
+                                                (mi_critic_loss_fwd_bwd) */ };
 
 const char* mi_status_string(int status);
 const char* mi_last_cuda_error(void);
@@ -121,41 +123,59 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
                   void* event_after_outk /* cudaEvent_t or NULL: recorded on `stream` once Ok is complete */,
                   void* workspace, size_t workspace_bytes, mi_stream_t stream);
 
-/* Single-pass form of statistics + gradients for dv / infonce / row InfoNCE (one score computation instead
- * of two).  rho[q] = scale |Q_q| max_k |K_k| bounds the scores of row q (Cauchy-Schwarz), so
- * P~ = incl e^{S - rho} <= 1 is written without a prior statistics pass; the same tiles give the row sums
- * (=> row_out / scal_out exactly as mi_score_stats; for include_diag = 1 the sums include the positive pair) and
+/* Single-pass form of statistics + gradients for dv / infonce / row InfoNCE: ONE score computation instead of two.
+ * The pass writes P~ = incl e^{S - ref[q]} before the exact row statistics exist, so it needs a per-row reference close
+ * enough to the row's log-sum-exp for P~ and its row sum to stay inside the fp32 / bf16 range (+-87 in the exponent).
+ *
+ * mi_score_ref_sample produces it: ref[q] = log-sum-exp of row q over the SAMPLED columns col0 + s * stride (s * stride <
+ * n_cols) of K — the statistics epilogue run on a strided view of K (TMA row pitch = stride * ldk, no gather);
+ * include_diag = 1 adds the positive pair.  stride = 1 samples every column: the references are then the exact row
+ * log-sum-exps and the pass cannot leave the safe window.  stride = 0 picks mi_ref_sample_stride(Bq, n_cols, D) (about
+ * mi_set_ref_sample_columns() columns per row, default 2048, i.e. ~1 % of the step at B = 65536).  Also returned:
+ * diag_out[q] = the positive-pair score S[q, q_offset + q], lambda_out[0] = max_q ref[q] (may be NULL).
+ *
+ * mi_score_single_pass: the same tiles give the row sums (=> row_out / scal_out exactly as mi_score_stats; for
+ * include_diag = 1 the sums include the positive pair) and
  *   oq_raw[q,:] = sum_k P~[q,k] K[k,:]                 ok_raw[k,:] = sum_q P~[q,k] wrow[q] Q[q,:]
- * with wrow = e^{rho - lambda} (include_diag = 0) or inv_bg / rowsum (include_diag = 1); lambda = the bound of the
- * largest row norm (qnorm_max_in: device scalar holding max |Q_q| over ALL ranks, NULL = this call's rows).
- * flag_out counts rows whose bound was > ~60 above all their scores: must be 0, else use the two-pass calls.
+ * with wrow = e^{ref - lambda[0]} (include_diag = 0; lambda = ONE constant near the largest reference, the same on every
+ * rank whose ok_raw is summed) or inv_bg / rowsum (include_diag = 1; lambda unused, may be NULL).
+ * Any reference is mathematically valid.  flag_out (and scal_out[6]) count the rows whose reference left the numerically
+ * safe window (row sum outside [1e-30, 1e30], or ref - lambda > 60): must be 0, else repeat with stride = 1 references.
  * The gradients follow from mi_single_finalize_q / _k once the (global) log-sum-exp is known:
- *   Oq = alpha (c_q oq_raw - gamma Kdiag),  c_q = e^{rho_q - lse} (dv_like) or wrow_q
+ *   Oq = alpha (c_q oq_raw - gamma Kdiag),  c_q = e^{ref_q - lse} (dv_like) or wrow_q
  *   Ok = alpha (kappa ok_raw - gamma Qdiag), kappa = e^{lambda - lse} (dv_like) or 1     (in place) */
+size_t mi_score_ref_sample_workspace_bytes(int64_t Bq, int64_t n_cols, int64_t D, int64_t stride);
+int64_t mi_ref_sample_stride(int64_t Bq, int64_t n_cols, int64_t D);
+int mi_score_ref_sample(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
+                        const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                        int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag,
+                        int64_t col0, int64_t n_cols, int64_t stride,
+                        float* ref_out /*[Bq]*/, float* diag_out /*[Bq]*/, float* lambda_out /*[1] or NULL*/,
+                        void* workspace, size_t workspace_bytes, mi_stream_t stream);
 size_t mi_score_single_pass_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision);
 int mi_row_norm_max(const void* A, int64_t lda, int a_split, int64_t rows, int64_t D, float* norm_out, float* max_out, mi_stream_t stream);
 int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
                          const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
                          int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag, int precision, float inv_bg,
-                         const float* qnorm_max_in, float* row_out /*[Bq,4]*/, double* scal_out /*[8]*/,
+                         const float* ref /*[Bq]*/, const float* lambda /*[1]*/, const float* diag /*[Bq]*/,
+                         float* row_out /*[Bq,4]*/, double* scal_out /*[8]*/,
                          float* oq_raw /*[Bq,D]*/, float* ok_raw /*[Bk,D] or NULL*/,
-                         float* rho /*[Bq]*/, float* wrow /*[Bq]*/, float* lambda_out /*[1]*/, int32_t* flag_out /*[1]*/,
+                         float* wrow /*[Bq]*/, int32_t* flag_out /*[1]*/,
                          void* event_after_outk,
                          void* event_after_scal /* cudaEvent_t or NULL: recorded once row_out / scal_out are final, i.e. BEFORE the
                                                    last panel's two contractions — exchange the loss scalars under them */,
-                         const float* knorm_max_in /* device scalar max_k |K_k| or NULL (computed here from K) */,
                          void* event_k_ready /* cudaEvent_t or NULL: the K rows (an all-gather in flight) are complete once this
-                                                event fires; the mask pre-pass and the Q statistics are enqueued BEFORE the wait */,
+                                                event fires; the mask pre-pass is enqueued BEFORE the wait */,
                          int k_local_valid /* 1: rows [q_offset, q_offset + Bq) of K (this rank's own text embeddings) are valid
-                                              already — with knorm_max_in given, the positive-pair scores and the score tiles
-                                              of the own column block also run before the wait */,
+                                              already — the score tiles of the own column block also run before the wait */,
                          void* workspace, size_t workspace_bytes, mi_stream_t stream);
 /* Multi-GPU glue: the ranks' scal_out rows [world][8] (all-gathered) -> loss_out (fp64[8], layout of mi_critic_loss_fwd_bwd,
  * global batch B_global, estimators DV / INFONCE_REF / INFONCE_ROW) and the global log-sum-exp as a float (lse_out[1]).
+ * loss_out[7] = the ranks' guard counts summed (+1 if e^{lambda - lse} would leave the fp32 range; lambda may be NULL).
  * Two tiny kernels instead of a chain of framework ops.  scratch8: 8 doubles of device scratch. */
-int mi_merge_scalars(const double* scal_all, int world, int64_t B_global, int estimator, double* loss_out, float* lse_out,
-                     double* scratch8, mi_stream_t stream);
-int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const float* rho, const float* wrow, const float* lse,
+int mi_merge_scalars(const double* scal_all, int world, int64_t B_global, int estimator, const float* lambda,
+                     double* loss_out, float* lse_out, double* scratch8, mi_stream_t stream);
+int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const float* ref, const float* wrow, const float* lse,
                          int dv_like, float alpha, float gamma, const void* kdiag, int64_t ldk, int k_split,
                          float* out_f32, void* out_bf16, int64_t ld16, int out_split, mi_stream_t stream);
 int mi_single_finalize_k(float* ok, int64_t rows, int64_t D, const float* lambda, const float* lse, int dv_like,
@@ -163,10 +183,17 @@ int mi_single_finalize_k(float* ok, int64_t rows, int64_t D, const float* lambda
 
 /* ---- the whole path, one GPU ------------------------------------------------------------------- */
 
-/* loss_out (fp64[8]) = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, #rows w/o negatives, #rows whose
- * single-pass reference was too loose (must be 0; otherwise repeat the call with MI_PREC_TWO_PASS) }.
+/* loss_out (fp64[8]) = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, #rows w/o negatives, guard }.
  * X = image embeddings [B,D], Y = text embeddings [B,D], W = [D,D] (NULL for the dot critic),
- * S = inv_tau * X W Y^T.  dX, dY (fp32 [B,D]) and dW (fp32 [D,D]) may all be NULL (forward only). */
+ * S = inv_tau * X W Y^T.  dX, dY (fp32 [B,D]) and dW (fp32 [D,D]) may all be NULL (forward only).
+ *
+ * dv / infonce / row InfoNCE run the single pass with SAMPLED references (mi_score_ref_sample).  If any row's reference
+ * leaves the safe window the library repeats the step itself with exact references: the repeat is enqueued on the same
+ * stream behind a device-side predicate (a handful of empty launches when the guard stayed clear), so the call stays
+ * asynchronous and CUDA-graph capturable, and the results are ALWAYS those of a pass whose guard was clear.
+ * guard (loss_out[7]) = number of rows that tripped the sampled pass: > 0 only says that the exact repeat produced the
+ * results.  MI_PREC_TWO_PASS asks for exact references from the start.  The symmetric estimator always runs the
+ * statistics passes + one gradient pass with exact references. */
 size_t mi_critic_workspace_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads);
 int mi_critic_loss_fwd_bwd(const void* X, const void* Y, const void* W, const int32_t* sid,
                            int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
@@ -174,8 +201,10 @@ int mi_critic_loss_fwd_bwd(const void* X, const void* Y, const void* W, const in
                            void* workspace, size_t workspace_bytes, mi_stream_t stream);
 
 /* Same call with HOST buffers (fp32 embeddings as the encoders produce them): copies X, Y, W, sid
- * to the device, runs mi_critic_loss_fwd_bwd, copies loss and gradients back, synchronises.
- * dev_scratch is a device buffer of mi_critic_host_scratch_bytes(...) bytes. */
+ * to the device, runs the path, copies loss and gradients back, synchronises; a tripped guard is handled on the host
+ * (the step is repeated with exact references before the call returns; loss_out[7] as above).
+ * dev_scratch is a device buffer of mi_critic_host_scratch_bytes(...) bytes.  Uses one internal copy stream per device:
+ * concurrent calls on the same device are serialised inside the library. */
 size_t mi_critic_host_scratch_bytes(int64_t B, int64_t D, int critic, int estimator, int precision, int need_grads);
 int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const float* W_host, const int32_t* sid_host,
                                 int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
@@ -228,10 +257,9 @@ void mi_set_mlp_panel_pairs(int64_t pairs); /* pairs per row panel of the MLP-cr
  * use (SM count - n) SMs, so the collective the caller starts at that event (reduce-scatter of the dY contributions)
  * finds free SMs instead of queueing behind a persistent 148-CTA grid.  0 (default) = use every SM. */
 void mi_set_overlap_reserve_sms(int n);
-void mi_set_debug(int value);          /* experiments only */
-void mi_set_single_pass(int on);       /* 0: mi_critic_loss_fwd_bwd always takes the two-pass path */
-void mi_set_mn_operands(int on);       /* 0: transpose row-major [K,N] operands into K-major copies instead of reading
-                                          them in place through MN-major UMMA descriptors (default 1) */
+/* Columns sampled per row for the single pass's references (default 2048; <= 0: always every column).  Tests use small
+ * values to exercise the sampled path and its guard at small B. */
+void mi_set_ref_sample_columns(int64_t n);
 int mi_get_cta_group(void);
 
 #ifdef __cplusplus

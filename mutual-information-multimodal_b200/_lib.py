@@ -19,9 +19,7 @@ PROTOTYPES = {
     "mi_set_profiling": (None, [c_int]),
     "mi_profile_read": (c_int, [c_vp, c_vp]),
     "mi_set_cta_group": (None, [c_int]),
-    "mi_set_debug": (None, [c_int]),
-    "mi_set_single_pass": (None, [c_int]),
-    "mi_set_mn_operands": (None, [c_int]),
+    "mi_set_ref_sample_columns": (None, [c_i64]),
     "mi_set_overlap_reserve_sms": (None, [c_int]),
     "mi_set_mlp_panel_pairs": (None, [c_i64]),
     "mi_get_cta_group": (c_int, []),
@@ -39,12 +37,16 @@ PROTOTYPES = {
     "mi_score_grad": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
                               c_vp, c_f32, c_vp, c_f32, c_int, c_int, c_f32, c_f32,
                               c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "mi_score_ref_sample_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_i64]),
+    "mi_ref_sample_stride": (c_i64, [c_i64, c_i64, c_i64]),
+    "mi_score_ref_sample": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
+                                    c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mi_score_single_pass_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "mi_row_norm_max": (c_int, [c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "mi_score_single_pass": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
                                      c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                     c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
-    "mi_merge_scalars": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+                                     c_vp, c_int, c_vp, c_sz, c_vp]),
+    "mi_merge_scalars": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mi_single_finalize_q": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_f32, c_f32, c_vp, c_i64, c_int,
                                      c_vp, c_vp, c_i64, c_int, c_vp]),
     "mi_single_finalize_k": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_f32, c_f32, c_vp, c_i64, c_int, c_vp]),

@@ -65,6 +65,9 @@ struct Sched {
   int b_seg[4];
   int a_moff[4];  // MN-major A only: M-coordinate offset of the segment (e.g. the lo half of a [hi | lo] panel)
   int b_noff[4];  // MN-major B only: N-coordinate offset of the segment
+  // Device-side launch predicate: when non-null and *run_if == 0 the whole grid returns at once.  The exact
+  // fallback of the single pass is enqueued behind such a flag, so it costs a few empty launches unless needed.
+  const int* run_if;
 };
 
 struct Unit { int m, s, ks, nt0, nt1, kb0, kb1; };
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const Sched sc, const typename Epi::Params ep) {
   using C = Cfg<kCG>;
+  if (sc.run_if != nullptr && *sc.run_if == 0) return;      // grid-uniform: both CTAs of a pair leave together
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
   __shared__ __align__(8) uint64_t empty_bar[C::kStages];
@@ -419,7 +423,6 @@ struct EpiPStore {
     // row sums of P (fp32, before rounding) are the statistics: sum_part[n_split][4][rows_padded]
     float* sum_part;
     int rows_padded;
-    int dbg;                // experiments: 1 = no global stores, 2 = direct register stores (no smem staging)
   };
   struct State { uint8_t* stage_smem; MaskState ms; float rq2; float s; };
 
@@ -500,15 +503,7 @@ struct EpiPStore {
     for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
     const int row0 = row - lane;                       // first row of this warp
     const int rows_valid = p.q_rows - row0;
-    if (p.dbg == 2) {
-      if (row < p.q_rows) {
-        uint4* dst = reinterpret_cast<uint4*>(p.P + (size_t)row * p.pitch + col0);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) dst[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-      }
-      return;
-    }
-    stage_and_flush(st.stage_smem, lane, hi, p.P + (size_t)row0 * p.pitch + col0, p.pitch, p.dbg == 1 ? 0 : rows_valid);
+    stage_and_flush(st.stage_smem, lane, hi, p.P + (size_t)row0 * p.pitch + col0, p.pitch, rows_valid);
     if (p.P_lo != nullptr) {                           // strict mode: residual panel
 #pragma unroll
       for (int c = 0; c < 16; ++c) {

@@ -22,11 +22,19 @@ using mi::Sched;
 // ------------------------------------------------------------------------------------ errors
 thread_local char g_cuda_err[512] = "";
 std::atomic<long long> g_launches{0};
-int g_debug = 0;
-int g_cta_group = -1;   // resolved lazily: env MI_CTA_GROUP or 2
-int g_overlap_reserve_sms = 0;  // SMs left free for a concurrent collective by the engine launches that follow event_after_outk
-thread_local int t_reserve_sms = 0;   // applied to the next engine launches of this thread
-bool g_mn_operands = true;   // read row-major [K, N] / [K, M] operands in place (MN-major descriptors) instead of transposing them
+// Process-wide knobs (bring-up / A-B experiments; set before the first call, not per call):
+std::atomic<int> g_cta_group{-1};          // resolved lazily: env MI_CTA_GROUP or 2
+std::atomic<int> g_overlap_reserve_sms{0}; // SMs left free for a concurrent collective by the engine launches after event_after_outk
+std::atomic<long long> g_ref_sample_cols{2048};   // columns sampled per row for the single pass's softmax references
+// Per-call state lives in thread-locals, so two host threads driving different streams never share it:
+thread_local int t_reserve_sms = 0;        // applied to the next engine launches of this thread
+thread_local const int* t_run_if = nullptr;   // device predicate of the launches of this thread (see Sched::run_if)
+struct PredGuard {
+  const int* prev;
+  explicit PredGuard(const int* p) : prev(t_run_if) { t_run_if = p; }
+  ~PredGuard() { t_run_if = prev; }
+};
+#define MI_PRED(p) do { if ((p) != nullptr && *(p) == 0) return; } while (0)
 
 // optional per-launch CUDA-event timing of the tile-engine kernels (bench.py's roofline breakdown)
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
@@ -36,11 +44,13 @@ std::mutex g_prof_mu;
 template <class Epi> struct EpiKind;
 
 int cta_group() {
-  if (g_cta_group < 0) {
+  int g = g_cta_group.load(std::memory_order_relaxed);
+  if (g < 0) {
     const char* e = std::getenv("MI_CTA_GROUP");
-    g_cta_group = (e && e[0] == '1') ? 1 : 2;
+    g = (e && e[0] == '1') ? 1 : 2;
+    g_cta_group.store(g, std::memory_order_relaxed);
   }
-  return g_cta_group;
+  return g;
 }
 
 int set_cuda_err(cudaError_t e, const char* where) {
@@ -147,10 +157,13 @@ int launch_engine_cg(const MapSpec& a, const MapSpec& b, const Sched& sc, const 
   else MI_TRY(make_tmap(&tb, b.ptr, b.rows, b.k_extent, b.ld, C::kBRows));
   auto kern = mi::tile_engine_kernel<kCG, Epi, kAMN, kBMN>;
   constexpr int smem = C::template smem_bytes<Epi>();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_devs{0};      // bit d: attribute set on device d (it is per device)
+  int dev = 0;
+  MI_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if ((attr_devs.load(std::memory_order_acquire) & bit) == 0) {
     MI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_devs.fetch_or(bit, std::memory_order_release);
   }
   const int units = sc.n_mblk * sc.n_split * sc.n_ksplit;
   int pairs = (num_sms() - t_reserve_sms) / kCG;
@@ -167,12 +180,14 @@ int launch_engine_cg(const MapSpec& a, const MapSpec& b, const Sched& sc, const 
   attr[0].val.clusterDim.x = kCG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  Sched scp = sc;
+  scp.run_if = t_run_if;
   ProfRec rec; rec.kind = EpiKind<Epi>::value; rec.e0 = nullptr; rec.e1 = nullptr;
   if (g_profiling) {
     MI_CUDA(cudaEventCreate(&rec.e0)); MI_CUDA(cudaEventCreate(&rec.e1));
     MI_CUDA(cudaEventRecord(rec.e0, stream));
   }
-  MI_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, sc, ep));
+  MI_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, scp, ep));
   MI_LAUNCH_CHECK("tile_engine_kernel");
   if (g_profiling) {
     MI_CUDA(cudaEventRecord(rec.e1, stream));
@@ -222,49 +237,67 @@ void single_segment(Sched& sc) {
 }
 
 // ------------------------------------------------------------------------------------ aux kernels
-__global__ void pad_int_kernel(const int* __restrict__ src, int* __restrict__ dst, long long n, long long n_pad, int fill) {
+// Every kernel of the single-pass / statistics paths takes a trailing `run_if` launch predicate (see Sched::run_if).
+__global__ void pad_int_kernel(const int* __restrict__ src, int* __restrict__ dst, long long n, long long n_pad, int fill,
+                               const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n_pad) dst[i] = (i < n) ? src[i] : fill;
 }
+// dst[s] = src[s * stride], s < n: the study ids of a strided column sample
+__global__ void gather_int_kernel(const int* __restrict__ src, long long stride, int* __restrict__ dst, long long n,
+                                  const int* __restrict__ run_if) {
+  MI_PRED(run_if);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i * stride];
+}
 
-// ---- exclusion lists: for every row, the columns that share its study id (hash grouping, O(B))
-constexpr int kEmptyKey = static_cast<int>(0x80000000u);
+// ---- exclusion lists: for every row, the columns that share its study id (hash grouping, O(B)).
+// A slot holds (1 << 32) | (uint32) id; 0 = empty, so EVERY int32 id (INT_MIN included) is a legal key.
 __device__ __forceinline__ uint32_t hash_sid(int key, uint32_t mask) {
   return (static_cast<uint32_t>(key) * 2654435761u >> 7) & mask;
 }
-__global__ void excl_init_kernel(int* __restrict__ keys, int* __restrict__ counts, int* __restrict__ members, long long slots) {
+__device__ __forceinline__ unsigned long long slot_key(int key) { return (1ull << 32) | static_cast<uint32_t>(key); }
+__global__ void excl_init_kernel(unsigned long long* __restrict__ keys, int* __restrict__ counts, int* __restrict__ members,
+                                 long long slots, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < slots) {
-    keys[i] = kEmptyKey; counts[i] = 0;
+    keys[i] = 0ull; counts[i] = 0;
     reinterpret_cast<int4*>(members)[i] = make_int4(-1, -1, -1, -1);
   }
 }
-__global__ void excl_insert_kernel(const int* __restrict__ sid_k, long long Bk, int* keys, int* counts, int* members, uint32_t mask) {
+__global__ void excl_insert_kernel(const int* __restrict__ sid_k, long long Bk, unsigned long long* keys, int* counts, int* members,
+                                   uint32_t mask, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= Bk) return;
   const int key = sid_k[k];
+  const unsigned long long sk = slot_key(key);
   uint32_t h = hash_sid(key, mask);
   while (true) {
-    const int prev = atomicCAS(&keys[h], kEmptyKey, key);
-    if (prev == kEmptyKey || prev == key) break;
+    const unsigned long long prev = atomicCAS(&keys[h], 0ull, sk);
+    if (prev == 0ull || prev == sk) break;
     h = (h + 1) & mask;
   }
   const int t = atomicAdd(&counts[h], 1);
   if (t < mi::kMaxExcl) members[h * mi::kMaxExcl + t] = static_cast<int>(k);
 }
-__global__ void excl_lookup_kernel(const int* __restrict__ sid_q, long long Bq, const int* __restrict__ keys,
+__global__ void excl_lookup_kernel(const int* __restrict__ sid_q, long long Bq, const unsigned long long* __restrict__ keys,
                                    const int* __restrict__ counts, const int* __restrict__ members, uint32_t mask,
-                                   int4* __restrict__ excl, int* __restrict__ n_same) {
+                                   int4* __restrict__ excl, int* __restrict__ n_same, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q >= Bq) return;
   const int key = sid_q[q];
+  const unsigned long long sk = slot_key(key);
   uint32_t h = hash_sid(key, mask);
   int4 e = make_int4(-1, -1, -1, -1);
   int n = 0;
   while (true) {
-    const int kk = keys[h];
-    if (kk == key) { n = counts[h]; if (n <= mi::kMaxExcl) e = reinterpret_cast<const int4*>(members)[h]; break; }
-    if (kk == kEmptyKey) break;
+    const unsigned long long kk = keys[h];
+    if (kk == sk) { n = counts[h]; if (n <= mi::kMaxExcl) e = reinterpret_cast<const int4*>(members)[h]; break; }
+    if (kk == 0ull) break;
     h = (h + 1) & mask;
   }
   excl[q] = e; n_same[q] = n;
@@ -307,7 +340,9 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long
 // diag[q] = scale * <Q[q,:], K[q_offset+q,:]> (the positive pair), one warp per row; hi/lo pairs summed
 __global__ void diag_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq, int q_split,
                             const __nv_bfloat16* __restrict__ K, long long ldk, int k_split,
-                            long long q_offset, long long Bq, long long D, long long Dp, float scale, float* __restrict__ diag) {
+                            long long q_offset, long long Bq, long long D, long long Dp, float scale, float* __restrict__ diag,
+                            const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= Bq) return;
@@ -326,8 +361,8 @@ __global__ void diag_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq, 
   if (lane == 0) diag[row] = acc * scale;
 }
 
-// ---- single-pass ("safe reference") path ------------------------------------------------------------
-// row L2 norms of a bf16 matrix (hi/lo pairs summed), one warp per row
+// ---- single-pass path -------------------------------------------------------------------------------
+// row L2 norms of a bf16 matrix (hi/lo pairs summed), one warp per row (mi_row_norm_max: a stage op kept for callers)
 __global__ void row_norm_kernel(const __nv_bfloat16* __restrict__ A, long long ld, int split, long long Dp,
                                 long long rows, long long D, float* __restrict__ norm) {
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -343,8 +378,9 @@ __global__ void row_norm_kernel(const __nv_bfloat16* __restrict__ A, long long l
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) norm[row] = sqrtf(acc);
 }
-// one block: out[0] = max_i f(in[i]);  mode 0: f = identity, mode 1: f = scale * in[i] * other[0] * 1.001 + 1e-3 written to out2
-__global__ void max_reduce_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+// one block: out[0] = max_i in[i] (NaN entries are ignored by fmaxf; all-NaN / empty gives -inf)
+__global__ void max_reduce_kernel(const float* __restrict__ in, long long n, float* __restrict__ out, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   __shared__ float sh[32];
   float m = mi::neg_inf();
   for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, in[i]);
@@ -353,108 +389,149 @@ __global__ void max_reduce_kernel(const float* __restrict__ in, long long n, flo
   __syncthreads();
   if (threadIdx.x == 0) { float g = mi::neg_inf(); for (int i = 0; i < (int)(blockDim.x >> 5); ++i) g = fmaxf(g, sh[i]); out[0] = g; }
 }
-// Cauchy-Schwarz: S[q,k] = scale <Q_q, K_k> <= scale |Q_q| max_k |K_k| =: rho[q]  (a hair above, for rounding)
-__global__ void rho_kernel(const float* __restrict__ qnorm, const float* __restrict__ kmax, float scale, long long n,
-                           float* __restrict__ rho) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < n) rho[i] = scale * qnorm[i] * kmax[0] * 1.001f + 1e-3f;
+
+// The single pass writes P~ = incl e^{S - ref_q} BEFORE the exact row statistics are known, so it needs a per-row reference
+// close enough to the row's log-sum-exp that neither P~ nor its row sum leaves the fp32 / bf16 range (about +-87 in the
+// exponent).  ref_q is the log-sum-exp over a strided SAMPLE of the row's columns (computed by the statistics epilogue on
+// K[c0 + s * stride]); with stride 1 the sample is every column and ref_q is exact.  Merge of the sample's (max, sum) partials:
+//   include_diag = 0:  ref = LSE over the sampled negatives            (the positive pair if the sample has no negative)
+//   include_diag = 1:  ref = logaddexp(that, positive-pair score)
+// `margin` (sampled references only) lifts the reference above the sample's log-sum-exp: the row's true maximum may sit
+// above everything the sample saw, and the window is one-sided — P~ may fall to 1e-38 but must stay below ~1e30.
+__global__ void ref_merge_kernel(const float4* __restrict__ part, int n_part, int rows_padded, int q_rows,
+                                 const float* __restrict__ diag_in, int include_diag, float margin, float* __restrict__ ref_out,
+                                 const int* __restrict__ run_if) {
+  MI_PRED(run_if);
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= q_rows) return;
+  float m = mi::neg_inf();
+  for (int p = 0; p < n_part; ++p) m = fmaxf(m, part[(size_t)p * rows_padded + row].x);
+  float s = 0.f;
+  for (int p = 0; p < n_part; ++p) {
+    const float4 v = part[(size_t)p * rows_padded + row];
+    if (v.y > 0.f) s += v.y * exp2f(v.x - m);
+  }
+  const float diag = diag_in[row];
+  const float lse = (s > 0.f) ? (m + log2f(s)) * mi::kLn2 : mi::neg_inf();
+  float ref;
+  if (include_diag) {
+    const float hi = fmaxf(lse, diag), lo = fminf(lse, diag);
+    ref = (lo > mi::neg_inf()) ? hi + log1pf(expf(lo - hi)) : hi;
+  } else {
+    ref = (lse > mi::neg_inf()) ? lse : diag;
+  }
+  ref_out[row] = ref + margin;
 }
-// rows of one panel: l = sum of the partial row sums of P~ = e^{S - rho};  row_out = {lse_neg, n_neg, diag, lse_all},
-// wrow = weight of the row inside the G^T Q contraction, flag += rows whose reference was too loose
+
+// rows of one panel: l = sum of the partial row sums of P~ = e^{S - ref};  row_out = {lse_neg, n_neg, diag, lse_all},
+// wrow = weight of the row inside the G^T Q contraction.  flag counts the rows whose reference left the safe window
+// (l not in [1e-30, 1e30], NaN included, or the row's weight e^{ref - lambda} would overflow): the caller must then
+// repeat the step with exact references (stride 1), for which l = 1 by construction.
 __global__ void sum_merge_kernel(const float* __restrict__ part, int n_part, int rows_padded, int rows,
-                                 const float* __restrict__ rho, const float* __restrict__ lambda, const int* __restrict__ n_same,
+                                 const float* __restrict__ ref, const float* __restrict__ lambda, const int* __restrict__ n_same,
                                  int k_cols, const float* __restrict__ diag_in, int include_diag, float inv_bg,
-                                 float4* __restrict__ row_out, float* __restrict__ lsum, float* __restrict__ wrow,
-                                 int* __restrict__ flag) {
+                                 float4* __restrict__ row_out, float* __restrict__ wrow,
+                                 int* __restrict__ flag, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   float l = 0.f;
   for (int p = 0; p < n_part; ++p) l += part[(size_t)p * rows_padded + row];
   const float cnt = static_cast<float>(k_cols - n_same[row]);
-  const float diag = diag_in[row], r = rho[row];
+  const float diag = diag_in[row], r = ref[row];
   const float n_incl = cnt + (include_diag ? 1.f : 0.f);
-  if (n_incl > 0.f && !(l >= 1e-26f)) atomicAdd(flag, 1);          // reference > ~60 above every score of the row
+  bool bad = n_incl > 0.f && !(l >= 1e-30f && l <= 1e30f);
   float lse_neg, lse_all;
   if (include_diag) {
     lse_all = r + logf(l);
     lse_neg = cnt > 0.f ? lse_all + log1pf(-fminf(expf(diag - lse_all), 1.f)) : mi::neg_inf();
-    wrow[row] = inv_bg / l;                                          // (1/B) e^{rho - r_i}
+    wrow[row] = inv_bg / l;                                          // (1/B) e^{ref - r_i}
   } else {
     lse_neg = (cnt > 0.f && l > 0.f) ? r + logf(l) : mi::neg_inf();
     const float hi = fmaxf(lse_neg, diag), lo = fminf(lse_neg, diag);
     lse_all = hi + log1pf(expf(lo - hi));
-    wrow[row] = expf(r - lambda[0]);                                 // e^{rho - lambda}; e^{lambda - LSE} is applied at the end
-    if (r - lambda[0] > 60.f) atomicAdd(flag, 1);                    // lambda taken from an earlier panel was far too small
+    const float d = r - lambda[0];
+    wrow[row] = expf(d);                                             // e^{ref - lambda}; e^{lambda - LSE} is applied at the end
+    bad = bad || !(d <= 60.f);                                       // lambda far below this row's reference (or NaN)
   }
-  lsum[row] = l;
+  if (bad) atomicAdd(flag, 1);
   row_out[row] = make_float4(lse_neg, cnt, diag, lse_all);
 }
-// out[c, r] = bf16(w[r] * in[r, c]) (+ residual half at out_lo); in may be a hi/lo pair
-__global__ void transpose_scale_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, int in_split, long long Dp,
-                                       const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo,
-                                       long long ld_out, long long R, long long C) {
-  __shared__ float tile[64][65];
-  const long long r0 = blockIdx.y * 64LL, c0 = blockIdx.x * 64LL;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  for (int i = ty; i < 64; i += 4) {
-    const long long r = r0 + i, c = c0 + tx;
-    float v = 0.f;
-    if (r < R && c < C) {
-      v = __bfloat162float(in[r * ld_in + c]);
-      if (in_split == 2) v += __bfloat162float(in[r * ld_in + Dp + c]);
-      v *= w[r];
-    }
-    tile[i][tx] = v;
-  }
-  __syncthreads();
-  for (int i = ty; i < 64; i += 4) {
-    const long long c = c0 + i, r = r0 + tx;
-    if (c < C && r < R) {
-      const float v = tile[tx][i];
-      const __nv_bfloat16 h = __float2bfloat16(v);
-      out[c * ld_out + r] = h;
-      if (out_lo) out_lo[c * ld_out + r] = __float2bfloat16(v - __bfloat162float(h));
-    }
-  }
-}
-// out[r, c] = bf16(w[r] * in[r, c]) (+ residual half at out_lo), row-major: the MN-major B operand of P~^T (w Q)
+// out[r, c] = bf16(w[r] * in[r, c]) (+ residual half at out_lo), row-major: the MN-major B operand of P~^T (w Q).  8 elements / thread
 __global__ void scale_rows_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, int in_split, long long Dp,
                                   const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo,
-                                  long long ld_out, long long R, long long C) {
-  const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2;
+                                  long long ld_out, long long R, long long C, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
+  const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
   if (idx >= R * C) return;
-  const long long r = idx / C, c = idx - r * C;         // C is even (D % 8 == 0)
-  float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + r * ld_in + c));
+  const long long r = idx / C, c = idx - r * C;         // C % 8 == 0: the 8 elements share a row
+  const uint4 hv = *reinterpret_cast<const uint4*>(in + r * ld_in + c);
+  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(hw[j] << 16); v[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u); }
   if (in_split == 2) {
-    const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + r * ld_in + Dp + c));
-    v.x += l.x; v.y += l.y;
+    const uint4 lv = *reinterpret_cast<const uint4*>(in + r * ld_in + Dp + c);
+    const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[2 * j] += __uint_as_float(lw[j] << 16); v[2 * j + 1] += __uint_as_float(lw[j] & 0xffff0000u); }
   }
   const float wr = w[r];
-  v.x *= wr; v.y *= wr;
-  const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
-  *reinterpret_cast<__nv_bfloat162*>(out + r * ld_out + c) = h;
+  uint32_t h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[2 * j] *= wr; v[2 * j + 1] *= wr; h[j] = ptx::pack_bf16(v[2 * j], v[2 * j + 1]); }
+  *reinterpret_cast<uint4*>(out + r * ld_out + c) = make_uint4(h[0], h[1], h[2], h[3]);
   if (out_lo) {
-    const float2 hf = __bfloat1622float2(h);
-    *reinterpret_cast<__nv_bfloat162*>(out_lo + r * ld_out + c) = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
+    uint32_t l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      l[j] = ptx::pack_bf16(v[2 * j] - __uint_as_float(h[j] << 16), v[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
+    *reinterpret_cast<uint4*>(out_lo + r * ld_out + c) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
-// Oq[i,:] = alpha (c_i Oraw[i,:] - gamma Kdiag[i,:]),  c_i = e^{rho_i - LSE} (DV) or wrow_i (row InfoNCE)
-__global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, long long rows, const float* __restrict__ rho,
+// Oq[i,:] = alpha (c_i Oraw[i,:] - gamma Kdiag[i,:]),  c_i = e^{ref_i - LSE} (DV) or wrow_i (row InfoNCE).  8 elements / thread
+__global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, long long rows, const float* __restrict__ ref,
                                   const float* __restrict__ wrow, const float* __restrict__ lse, int dv_like,
                                   float alpha, float gamma, const __nv_bfloat16* __restrict__ kdiag, long long ldk, int k_split, long long Dp,
-                                  float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ out_lo, long long ld16) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+                                  float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ out_lo, long long ld16,
+                                  const int* __restrict__ run_if) {
+  MI_PRED(run_if);
+  const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
   if (idx >= rows * D) return;
-  const long long i = idx / D, d = idx - i * D;
-  const float c = dv_like ? expf(rho[i] - lse[0]) : wrow[i];
-  float kd = __bfloat162float(kdiag[i * ldk + d]);
-  if (k_split == 2) kd += __bfloat162float(kdiag[i * ldk + Dp + d]);
-  const float o = alpha * (c * raw[idx] - gamma * kd);
-  if (out_f32) out_f32[idx] = o;
+  const long long i = idx / D, d = idx - i * D;          // D % 8 == 0
+  const float c = dv_like ? expf(ref[i] - lse[0]) : wrow[i];
+  const uint4 kv = *reinterpret_cast<const uint4*>(kdiag + i * ldk + d);
+  const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
+  float kd[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { kd[2 * j] = __uint_as_float(kw[j] << 16); kd[2 * j + 1] = __uint_as_float(kw[j] & 0xffff0000u); }
+  if (k_split == 2) {
+    const uint4 lv = *reinterpret_cast<const uint4*>(kdiag + i * ldk + Dp + d);
+    const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { kd[2 * j] += __uint_as_float(lw[j] << 16); kd[2 * j + 1] += __uint_as_float(lw[j] & 0xffff0000u); }
+  }
+  const float4 r0 = *reinterpret_cast<const float4*>(raw + idx), r1 = *reinterpret_cast<const float4*>(raw + idx + 4);
+  const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = alpha * (c * rv[j] - gamma * kd[j]);
+  if (out_f32) {
+    *reinterpret_cast<float4*>(out_f32 + idx) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(out_f32 + idx + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
   if (out_bf16) {
-    const __nv_bfloat16 h = __float2bfloat16(o);
-    out_bf16[i * ld16 + d] = h;
-    if (out_lo) out_lo[i * ld16 + d] = __float2bfloat16(o - __bfloat162float(h));
+    uint32_t h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = ptx::pack_bf16(o[2 * j], o[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out_bf16 + i * ld16 + d) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (out_lo) {
+      uint32_t l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        l[j] = ptx::pack_bf16(o[2 * j] - __uint_as_float(h[j] << 16), o[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
+      *reinterpret_cast<uint4*>(out_lo + i * ld16 + d) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
   }
 }
 // Ok[k,:] = alpha (kappa Ok[k,:] - gamma [0 <= k-q_offset < Bq] Q[k-q_offset,:]),  kappa = e^{lambda - LSE} (DV) or 1
@@ -496,8 +573,10 @@ __global__ void stats_merge_kernel(const float4* __restrict__ part, int n_part, 
   row_out[row] = make_float4(lse_neg, cnt, diag, lse_all);
 }
 
-// one block: scal = {max lse_neg, sum exp(lse_neg - max), sum n_neg, sum diag, sum (lse_all - diag), #rows w/o neg}
-__global__ void stats_reduce_kernel(const float4* __restrict__ row_out, int q_rows, double* __restrict__ scal) {
+// one block: scal = {max lse_neg, sum exp(lse_neg - max), sum n_neg, sum diag, sum (lse_all - diag), #rows w/o neg, 0, 0}
+__global__ void stats_reduce_kernel(const float4* __restrict__ row_out, int q_rows, double* __restrict__ scal,
+                                    const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   __shared__ double sh[6][32];
   __shared__ float shm[32];
   __shared__ float gmax;
@@ -529,25 +608,33 @@ __global__ void stats_reduce_kernel(const float4* __restrict__ row_out, int q_ro
     scal[0] = g; scal[1] = t[0]; scal[2] = t[1]; scal[3] = t[2]; scal[4] = t[3]; scal[5] = t[4]; scal[6] = 0; scal[7] = 0;
   }
 }
+// scal[6] = number of rows whose single-pass reference left the safe window (travels with the rank's scalars)
+__global__ void flag_to_scal_kernel(const int* __restrict__ flag, double* __restrict__ scal, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
+  scal[6] = static_cast<double>(flag[0]);
+}
 
 // ranks' reduced scalars [world][8] -> one row of the same layout (global max / rescaled sum-exp, plain sums)
 __global__ void merge_scal_kernel(const double* __restrict__ scal_all, int world, double* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double gm = -INFINITY;
   for (int r = 0; r < world; ++r) gm = fmax(gm, scal_all[r * 8]);
-  double s = 0, t[4] = {0, 0, 0, 0};
+  double s = 0, t[5] = {0, 0, 0, 0, 0};
   for (int r = 0; r < world; ++r) {
     const double* v = scal_all + r * 8;
     if (isfinite(v[0])) s += v[1] * exp(v[0] - gm);
-    for (int k = 0; k < 4; ++k) t[k] += v[2 + k];
+    for (int k = 0; k < 5; ++k) t[k] += v[2 + k];
   }
-  out[0] = gm; out[1] = s; out[2] = t[0]; out[3] = t[1]; out[4] = t[2]; out[5] = t[3]; out[6] = 0; out[7] = 0;
+  out[0] = gm; out[1] = s; out[2] = t[0]; out[3] = t[1]; out[4] = t[2]; out[5] = t[3]; out[6] = t[4]; out[7] = 0;
 }
 
-// fused single-GPU glue: loss from the reduced scalars (fp64), and the scalar references as floats
-// loss_out = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, rows w/o negatives, 0 }
+// fused glue: loss from the reduced scalars (fp64), and the scalar references as floats
+// loss_out = { loss, pos_mean, lse_neg, n_neg, loss_row, loss_col, rows w/o negatives, guard rows }
+// `lambda` (dv-like single pass only): the guard also trips when e^{lambda - LSE} would leave the fp32 range.
 __global__ void loss_finalize_kernel(const double* __restrict__ scal_row, const double* __restrict__ scal_col,
-                                     long long B, int estimator, double* __restrict__ loss_out, float* __restrict__ lse_f) {
+                                     long long B, int estimator, double* __restrict__ loss_out, float* __restrict__ lse_f,
+                                     const float* __restrict__ lambda, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double lse = scal_row[0] + log(scal_row[1]);
   const double n_neg = scal_row[2];
@@ -559,9 +646,26 @@ __global__ void loss_finalize_kernel(const double* __restrict__ scal_row, const 
   else if (estimator == MI_EST_INFONCE_REF) loss = lse - pos;
   else if (estimator == MI_EST_INFONCE_ROW) loss = loss_row;
   else loss = 0.5 * (loss_row + loss_col);
+  double guard = scal_row[6];
+  if (lambda != nullptr && (estimator == MI_EST_DV || estimator == MI_EST_INFONCE_REF) && n_neg > 0.0 &&
+      !(fabs((double)lambda[0] - lse) <= 60.0)) guard += 1.0;
   loss_out[0] = loss; loss_out[1] = pos; loss_out[2] = lse; loss_out[3] = n_neg;
-  loss_out[4] = loss_row; loss_out[5] = loss_col; loss_out[6] = scal_row[5]; loss_out[7] = 0;
+  loss_out[4] = loss_row; loss_out[5] = loss_col; loss_out[6] = scal_row[5]; loss_out[7] = guard;
   *lse_f = (float)lse;
+}
+// flag[0] = (loss_out[7] != 0): the device predicate of the exact fallback
+__global__ void guard_to_flag_kernel(const double* __restrict__ loss_out, int* __restrict__ flag, double* __restrict__ guard_a) {
+  guard_a[0] = loss_out[7];
+  flag[0] = (loss_out[7] != 0.0) ? 1 : 0;
+}
+// after the (predicated) exact repeat: loss_out[7] keeps the number of rows that tripped the sampled pass (informational:
+// > 0 means the results come from the exact repeat); a trip of the exact repeat itself is impossible by construction
+// (l = 1 for every row) and would poison the loss instead of passing silently.
+__global__ void guard_report_kernel(const int* __restrict__ flag_a, const double* __restrict__ guard_a, double* __restrict__ loss_out) {
+  if (flag_a[0] != 0) {
+    if (loss_out[7] != 0.0) loss_out[0] = nan("");
+    loss_out[7] = guard_a[0];
+  }
 }
 
 // dst[i] = const (from device scalar) or column `col` of row_out
@@ -576,7 +680,9 @@ __global__ void make_ref_kernel(float* __restrict__ dst, const float4* __restric
 
 // out[r, c] (pitch ld_out) (+)= sum_p part[p][r, c] (compact partials, pitch ldp): split-K reduction
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int n_part, long long stride, long long ldp,
-                                       float* __restrict__ out, long long ld_out, long long rows, long long cols, int accumulate) {
+                                       float* __restrict__ out, long long ld_out, long long rows, long long cols, int accumulate,
+                                       const int* __restrict__ run_if) {
+  MI_PRED(run_if);
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const long long r = i / cols, c = i - r * cols;
@@ -668,7 +774,7 @@ int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
     if (!g.out_f32 || g.sub || g.bias || g.relu_mask || g.acc_first || g.alpha != 1.f) return MI_ERR_BAD_ARG;
     const long long n = static_cast<long long>(g.M) * g.N;
     reduce_partials_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(partial, sc.n_ksplit, static_cast<long long>(g.M) * ldp, ldp,
-                                                                   g.out_f32, g.ld_out, g.M, g.N, g.accumulate ? 1 : 0);
+                                                                   g.out_f32, g.ld_out, g.M, g.N, g.accumulate ? 1 : 0, t_run_if);
     MI_LAUNCH_CHECK("reduce_partials_kernel");
   }
   return MI_OK;
@@ -741,7 +847,7 @@ int transpose_impl(const void* in, long long ld_in, void* out, long long ld_out,
 }
 
 // hash pre-pass + padded study ids: everything the epilogue's negatives mask needs
-struct MaskBuf { int* sidk_pad; int* keys; int* counts; int* members; int4* excl; int* n_same; long long slots; };
+struct MaskBuf { int* sidk_pad; unsigned long long* keys; int* counts; int* members; int4* excl; int* n_same; long long slots; };
 
 MaskBuf take_mask(Bump& ws, long long Bq, long long k_pad, long long Bk) {
   MaskBuf b;
@@ -749,20 +855,21 @@ MaskBuf take_mask(Bump& ws, long long Bq, long long k_pad, long long Bk) {
   while (slots < 2 * Bk) slots *= 2;
   b.slots = slots;
   b.sidk_pad = ws.take<int>(k_pad);
-  b.keys = ws.take<int>(slots); b.counts = ws.take<int>(slots); b.members = ws.take<int>(slots * mi::kMaxExcl);
+  b.keys = ws.take<unsigned long long>(slots); b.counts = ws.take<int>(slots); b.members = ws.take<int>(slots * mi::kMaxExcl);
   b.excl = ws.take<int4>(Bq); b.n_same = ws.take<int>(Bq);
   return b;
 }
 
 int build_mask(const MaskBuf& b, const int* sid_q, const int* sid_k, long long Bq, long long Bk, long long k_pad, cudaStream_t stream) {
-  pad_int_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(sid_k, b.sidk_pad, Bk, k_pad, -2);
+  const int* pr = t_run_if;
+  pad_int_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(sid_k, b.sidk_pad, Bk, k_pad, -2, pr);
   MI_LAUNCH_CHECK("pad_int_kernel");
-  excl_init_kernel<<<blocks_for(b.slots, 256), 256, 0, stream>>>(b.keys, b.counts, b.members, b.slots);
+  excl_init_kernel<<<blocks_for(b.slots, 256), 256, 0, stream>>>(b.keys, b.counts, b.members, b.slots, pr);
   MI_LAUNCH_CHECK("excl_init_kernel");
   const uint32_t mask = static_cast<uint32_t>(b.slots - 1);
-  excl_insert_kernel<<<blocks_for(Bk, 256), 256, 0, stream>>>(sid_k, Bk, b.keys, b.counts, b.members, mask);
+  excl_insert_kernel<<<blocks_for(Bk, 256), 256, 0, stream>>>(sid_k, Bk, b.keys, b.counts, b.members, mask, pr);
   MI_LAUNCH_CHECK("excl_insert_kernel");
-  excl_lookup_kernel<<<blocks_for(Bq, 256), 256, 0, stream>>>(sid_q, Bq, b.keys, b.counts, b.members, mask, b.excl, b.n_same);
+  excl_lookup_kernel<<<blocks_for(Bq, 256), 256, 0, stream>>>(sid_q, Bq, b.keys, b.counts, b.members, mask, b.excl, b.n_same, pr);
   MI_LAUNCH_CHECK("excl_lookup_kernel");
   return MI_OK;
 }
@@ -787,7 +894,7 @@ int stats_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   if (!Q.p || !K.p || !sid_q || !sid_k || !row_out || !scal_out || !(scale > 0.f)) return MI_ERR_BAD_ARG;
   MI_TRY(build_mask(mb, sid_q, sid_k, Bq, Bk, k_pad, stream));
   diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Q.p, Q.ld, Q.split, K.p, K.ld, K.split, q_offset, Bq, D,
-                                                             round_up(D, kSplitAlign), scale, diag);
+                                                             round_up(D, kSplitAlign), scale, diag, t_run_if);
   MI_LAUNCH_CHECK("diag_kernel");
   mi::EpiStats::Params ep;
   ep.mask = mi::MaskInfo{mb.excl, mb.n_same, sid_q, mb.sidk_pad};
@@ -798,8 +905,74 @@ int stats_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   stats_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(Bq),
                                                               mb.n_same, static_cast<int>(Bk), diag, reinterpret_cast<float4*>(row_out));
   MI_LAUNCH_CHECK("stats_merge_kernel");
-  stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out);
+  stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out, t_run_if);
   MI_LAUNCH_CHECK("stats_reduce_kernel");
+  return MI_OK;
+}
+
+// Sampled references sit kRefMargin nats above the sample's log-sum-exp (see ref_merge_kernel): a row stays inside the
+// safe window while its true log-sum-exp is within [-45, +93] nats of what the sample saw.
+constexpr float kRefMargin = 24.f;
+
+// Column sample of the single pass's references: stride such that about g_ref_sample_cols columns are scored per row;
+// 1 (every column: exact references, the pass can never leave the safe window) when the sample would not be cheaper
+// than ~80 us of tensor time — below that the exact statistics pass costs less than the predicated repeat's empty launches.
+long long ref_stride_auto(long long Bq, long long ncols, long long D) {
+  const long long target = g_ref_sample_cols.load(std::memory_order_relaxed);
+  if (target <= 0) return 1;
+  long long stride = ncols / target;
+  if (stride < 2) return 1;
+  if (2.0 * static_cast<double>(Bq) * static_cast<double>(ncols) * static_cast<double>(D) < 1.0e11 && target >= 2048) return 1;
+  return stride;
+}
+
+// Per-row softmax references of the single pass (see ref_merge_kernel) from the columns c0 + s * stride, s in [0, ns),
+// ns = ceil(nc / stride), of K — one statistics launch over a strided view of K (a TMA map whose row pitch is
+// stride * ld; no gather).  Also: diag_out[q] = the positive-pair score S[q, q_offset + q]; lam_out[0] = max_q ref_out[q].
+int ref_sample_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k, long long q_offset,
+                    long long Bq, long long Bk, long long D, float scale, int include_diag,
+                    long long c0, long long nc, long long stride,
+                    float* ref_out, float* diag_out, float* lam_out, Bump& ws, cudaStream_t stream) {
+  if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0 || stride < 1 || c0 < 0 || nc <= 0 || c0 + nc > Bk) return MI_ERR_BAD_ARG;
+  const long long ns = cdiv(nc, stride);
+  Sched sc;
+  sc.n_mblk = static_cast<int>(cdiv(Bq, rows_per_mblk()));
+  sc.n_ntile = static_cast<int>(cdiv(ns, mi::TILE_N));
+  sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
+  sc.n_ksplit = 1; sc.order = 0;
+  MI_TRY(score_segments(sc, Q, K, D));
+  const long long k_pad = static_cast<long long>(sc.n_ntile) * mi::TILE_N;
+  const int rows_padded = sc.n_mblk * rows_per_mblk();
+  const MaskBuf mb = take_mask(ws, Bq, k_pad, ns);
+  int* sid_s = ws.take<int>(ns);
+  float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * mi::kColQuarters * rows_padded);
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  if (ws.dry) return MI_OK;
+  if (!Q.p || !K.p || !sid_q || !sid_k || !ref_out || !diag_out || !(scale > 0.f)) return MI_ERR_BAD_ARG;
+  const int* pr = t_run_if;
+  const int* sid_cols = sid_k + c0;
+  if (stride > 1) {
+    gather_int_kernel<<<blocks_for(ns, 256), 256, 0, stream>>>(sid_k + c0, stride, sid_s, ns, pr);
+    MI_LAUNCH_CHECK("gather_int_kernel");
+    sid_cols = sid_s;
+  }
+  MI_TRY(build_mask(mb, sid_q, sid_cols, Bq, ns, k_pad, stream));
+  diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Q.p, Q.ld, Q.split, K.p, K.ld, K.split, q_offset, Bq, D,
+                                                             round_up(D, kSplitAlign), scale, diag_out, pr);
+  MI_LAUNCH_CHECK("diag_kernel");
+  mi::EpiStats::Params ep;
+  ep.mask = mi::MaskInfo{mb.excl, mb.n_same, sid_q, mb.sidk_pad};
+  ep.q_rows = static_cast<int>(Bq); ep.k_cols = static_cast<int>(ns);
+  ep.scale = scale; ep.part = part; ep.rows_padded = rows_padded;
+  MI_TRY(launch_engine<mi::EpiStats>(MapSpec{Q.p, Bq, opnd_k_extent(Q, D), Q.ld},
+                                     MapSpec{K.p + c0 * K.ld, ns, opnd_k_extent(K, D), K.ld * stride}, sc, ep, stream));
+  ref_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(Bq),
+                                                            diag_out, include_diag, stride > 1 ? kRefMargin : 0.f, ref_out, pr);
+  MI_LAUNCH_CHECK("ref_merge_kernel");
+  if (lam_out != nullptr) {
+    max_reduce_kernel<<<1, 1024, 0, stream>>>(ref_out, Bq, lam_out, pr);
+    MI_LAUNCH_CHECK("max_reduce_kernel");
+  }
   return MI_OK;
 }
 
@@ -821,11 +994,11 @@ struct GradOut {            // fp32 and/or bf16 (split == 2: [hi | lo] rows) des
   __nv_bfloat16* bf16 = nullptr; long long ld16 = 0; int split = 1;
 };
 
-// The fused gradient pass.  For every row panel of Q: (1) recompute score tiles and write the bf16 dS
-// panel P (EpiPStore), (2) Oq[panel] = alpha (P K - gamma K_diag)  and, when `ok` is requested,
-// (3) Ok += alpha (P^T Q[panel] - gamma Q_diag) with P read MN-major from the same panel — one score
-// recompute serves both gradients.  "diag" is the positive-pair term: row q pairs with column
-// q_offset + q.  The B x B matrix never exists; P is a bounded row panel in `ws`.
+// The fused gradient pass with EXACT references (symmetric InfoNCE, and the mi_score_grad stage op).  For every row panel
+// of Q: (1) recompute score tiles and write the bf16 dS panel P (EpiPStore), (2) Ok += alpha (P^T Q[panel] - gamma Q_diag)
+// with P read MN-major from the same panel, (3) Oq[panel] = alpha (P K - gamma K_diag) — one score recompute serves both
+// gradients; K and Q are read in place as MN-major B operands (no transposed copies).  "diag" is the positive-pair term:
+// row q pairs with column q_offset + q.  P is a bounded row panel in `ws`, streamed through HBM panel by panel.
 int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
               long long q_offset, long long Bq, long long Bk, long long D, float scale,
               const float* refq, float wq, const float* refk, float wk, int include_diag, int precision,
@@ -840,16 +1013,10 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   const long long pitch = k_pad * (strict ? 2 : 1);
   const long long Dp = round_up(D, kSplitAlign);
   const bool k_hl = strict && K.split == 2, q_hl = strict && Q.split == 2;
-  const long long ld_kt = k_pad * (k_hl ? 2 : 1);
-  const long long q_pad = round_up(Bq, kSplitAlign);
-  const long long ld_qt = q_pad * (q_hl ? 2 : 1);
   const long long mb_panel = panel_mblks(Bq, Bk, D, precision);
   const long long panel_rows = mb_panel * rows_per_mblk();
   const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
   float* refk2 = ws.take<float>(k_pad);
-  const bool mn = g_mn_operands;     // K and Q are read in place as MN-major B operands: no transposed copies
-  bf* Kt = (mn && !ws.dry) ? nullptr : ws.take<bf>(static_cast<size_t>(D) * ld_kt);
-  bf* Qt = (ok && !(mn && !ws.dry)) ? ws.take<bf>(static_cast<size_t>(D) * ld_qt) : nullptr;
   bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
@@ -861,17 +1028,6 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   if (use_k) {
     make_refk2_kernel<<<blocks_for(k_pad, 256), 256, 0, stream>>>(refk, logf(wk), refk2, Bk, k_pad);
     MI_LAUNCH_CHECK("make_refk2_kernel");
-  }
-  // V^T for the P K product (K-major B operand): [D, k_pad] (+ the lo half next to it in strict mode)
-  if (!mn) {
-    if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
-    MI_TRY(transpose_impl(K.p, K.ld, Kt, ld_kt, Bk, D, stream));
-    if (k_hl) MI_TRY(transpose_impl(K.p + Dp, K.ld, Kt + k_pad, ld_kt, Bk, D, stream));
-    if (ok) {
-      if (q_hl) MI_CUDA(cudaMemsetAsync(Qt, 0, static_cast<size_t>(D) * ld_qt * sizeof(bf), stream));
-      MI_TRY(transpose_impl(Q.p, Q.ld, Qt, ld_qt, Bq, D, stream));
-      if (q_hl) MI_TRY(transpose_impl(Q.p + Dp, Q.ld, Qt + q_pad, ld_qt, Bq, D, stream));
-    }
   }
   const Opnd Qe{Q.p, Q.ld, strict ? Q.split : 1}, Ke{K.p, K.ld, strict ? K.split : 1};
 
@@ -890,7 +1046,7 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     ep.q_offset = q_offset + r0; ep.scale = scale;
     ep.refq = use_q ? refq + r0 : nullptr; ep.ln_wq = use_q ? logf(wq) : 0.f; ep.use_q = use_q ? 1 : 0;
     ep.refk2 = refk2; ep.use_k = use_k ? 1 : 0; ep.include_diag = include_diag;
-    ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch; ep.dbg = g_debug;
+    ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
     ep.sum_part = nullptr; ep.rows_padded = 0;
     MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
                                         MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
@@ -901,16 +1057,11 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
       const int kr = static_cast<int>(cdiv(rows, bk()));
       g.a_mn = true;
       g.a = MapSpec{P, rows, pitch, pitch};            // map rows = K (panel rows), contiguous = M (columns of S)
-      if (mn) { g.b_mn = true; g.b = MapSpec{Q.p + r0 * Q.ld, rows, q_hl ? Dp + D : D, Q.ld}; }
-      else g.b = MapSpec{Qt + r0, D, q_hl ? q_pad + (Bq - r0) : (Bq - r0), ld_qt};
+      g.b_mn = true; g.b = MapSpec{Q.p + r0 * Q.ld, rows, q_hl ? Dp + D : D, Q.ld};
       g.M = Bk; g.N = D; g.seg_len = kr; g.k_blocks = kr;
-      const int q_lo_blk = static_cast<int>(q_pad / bk());
       if (strict) {                                  // P_hi^T Q_hi + P_lo^T Q_hi (+ P_hi^T Q_lo)
         g.k_blocks = 2 * kr; g.a_moff[1] = static_cast<int>(k_pad);
-        if (q_hl) {
-          g.k_blocks = 3 * kr;
-          if (mn) g.b_noff[2] = static_cast<int>(Dp); else g.b_seg[2] = q_lo_blk;
-        }
+        if (q_hl) { g.k_blocks = 3 * kr; g.b_noff[2] = static_cast<int>(Dp); }
       }
       g.alpha = alpha; g.gamma = gamma;
       g.accumulate = r0 > 0;
@@ -924,22 +1075,18 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
       // the K-side output is complete after the last panel: let the caller start its reduce-scatter here
       if (ev_after_k != nullptr && r0 + panel_rows >= Bq) {
         MI_CUDA(cudaEventRecord(ev_after_k, stream));
-        t_reserve_sms = g_overlap_reserve_sms;
+        t_reserve_sms = g_overlap_reserve_sms.load(std::memory_order_relaxed);
       }
     }
     // (3) Oq[panel] = alpha (P V - gamma SUB), contraction over the Bk columns
     if (oq.f32 || oq.bf16) {
       GemmArgs g;
       g.a = MapSpec{P, rows, pitch, pitch};
-      if (mn) { g.b_mn = true; g.b = MapSpec{K.p, Bk, k_hl ? Dp + D : D, K.ld}; }
-      else g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
+      g.b_mn = true; g.b = MapSpec{K.p, Bk, k_hl ? Dp + D : D, K.ld};
       g.M = rows; g.N = D; g.seg_len = kp; g.k_blocks = kp;
       if (strict) {                                  // P_hi V_hi + P_lo V_hi (+ P_hi V_lo)
         g.k_blocks = 2 * kp; g.a_seg[1] = kp;
-        if (k_hl) {
-          g.k_blocks = 3 * kp;
-          if (mn) g.b_noff[2] = static_cast<int>(Dp); else g.b_seg[2] = kp;
-        }
+        if (k_hl) { g.k_blocks = 3 * kp; g.b_noff[2] = static_cast<int>(Dp); }
       }
       g.alpha = alpha; g.gamma = gamma;
       if (gamma != 0.f) {                            // - gamma K[q_offset + q]
@@ -967,27 +1114,26 @@ struct SingleFin {
 
 // The rows of Q may become available panel by panel (host-buffer entry point: the image embeddings are still crossing
 // PCIe while the first panels are processed).  before_panel(r0, rows) enqueues on the stream whatever makes
-// Q[r0, r0 + rows) valid; the per-row statistics of the bound are then taken per panel and lambda — any constant near the
-// largest bound works, it only centres e^{rho - lambda} — is the maximum over the FIRST panel (guarded in sum_merge_kernel).
+// Q[r0, r0 + rows), ref[r0, ...) and diag[r0, ...) valid — and, for r0 == 0, lambda (any constant near the largest
+// reference works, it only centres e^{ref - lambda}; later panels are guarded in sum_merge_kernel).
 struct PanelFeed { std::function<int(long long, long long)> before_panel; };
 
-// Single-pass variant of the forward statistics + gradient pass (dv / infonce / row InfoNCE).
-// rho[q] = scale |Q_q| max_k |K_k| bounds every score of row q from above (Cauchy-Schwarz), so
-// P~ = incl * e^{S - rho} <= 1 needs no running max and no statistics pass BEFORE the panel is written:
-// the same score tiles give (a) the row sums l_q = sum_k P~ (=> LSE_q = rho_q + ln l_q, the loss) and
-// (b) the bf16 panel P~ whose two contractions, rescaled per row / globally afterwards, are the gradients:
+// Single-pass form of the forward statistics + gradient pass (dv / infonce / row InfoNCE): ONE score computation.
+// ref[q] (caller supplied: ref_sample_impl) is a per-row softmax reference; P~ = incl * e^{S - ref} is written without a
+// statistics pass before it, and the same score tiles give (a) the exact row sums l_q = sum_k P~ (=> LSE_q = ref_q + ln l_q,
+// the loss) and (b) the bf16 panel P~ whose two contractions, rescaled per row / globally afterwards, are the gradients:
 //   dV-side   Oq_raw = P~ K                         final: alpha (c_q Oq_raw - gamma K_diag)
 //   dQ-side   Ok_raw = sum_q P~[q,:]^T (w_q Q_q)    final: alpha (kappa Ok_raw - gamma Q_diag)
-//   DV: c_q = e^{rho_q - LSE}, w_q = e^{rho_q - lambda}, kappa = e^{lambda - LSE};  row InfoNCE: c_q = w_q = 1/(B l_q), kappa = 1.
-// One score computation instead of two: 6 B^2 D executed = the algorithmic count.  If a row's reference is
-// more than ~60 above all of its scores (flag_out > 0) the caller must redo the step with the two-pass path.
+//   DV: c_q = e^{ref_q - LSE}, w_q = e^{ref_q - lambda}, kappa = e^{lambda - LSE};  row InfoNCE: c_q = w_q = 1/(B l_q), kappa = 1.
+// 6 B^2 D executed = the algorithmic count.  Any reference is mathematically valid; flag_out counts the rows whose
+// reference left the numerically safe window (see sum_merge_kernel) — the caller then repeats with exact references.
 int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
                      long long q_offset, long long Bq, long long Bk, long long D, float scale,
-                     int include_diag, int precision, float inv_bg, const float* qmax_in,
-                     float* row_out, float* oq_raw, float* ok_raw,
-                     float* rho, float* wrow, float* lambda_out, int* flag_out, Bump& ws, cudaStream_t stream,
+                     int include_diag, int precision, float inv_bg,
+                     const float* ref, const float* lambda, const float* diag,
+                     float* row_out, float* oq_raw, float* ok_raw, float* wrow, int* flag_out, Bump& ws, cudaStream_t stream,
                      cudaEvent_t ev_after_k = nullptr, double* scal_out = nullptr, cudaEvent_t ev_after_scal = nullptr,
-                     const float* kmax_in = nullptr, cudaEvent_t ev_k_ready = nullptr, const struct SingleFin* fin = nullptr,
+                     cudaEvent_t ev_k_ready = nullptr, const struct SingleFin* fin = nullptr,
                      const struct PanelFeed* feed = nullptr, bool k_local_valid = false) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
@@ -998,89 +1144,36 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   const long long pitch = k_pad * (strict ? 2 : 1);
   const long long Dp = round_up(D, kSplitAlign);
   const bool k_hl = strict && K.split == 2;
-  const long long ld_kt = k_pad * (k_hl ? 2 : 1);
   const long long mb_panel = panel_mblks(Bq, Bk, D, precision & 1);
   const long long panel_rows = mb_panel * rows_per_mblk();
-  const long long r_pad = round_up(panel_rows, kSplitAlign);
-  const long long ld_qt = r_pad * (strict ? 2 : 1);
   const int max_split = n_ntile;
   const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
-  const bool mn = g_mn_operands;     // K and w Q are read as row-major MN-major B operands: no transposed copies
   const long long ld_qs = strict ? 2 * Dp : D;               // w Q [panel_rows, hi | lo]
-  bf* Kt = (mn && !ws.dry) ? nullptr : ws.take<bf>(static_cast<size_t>(D) * ld_kt);
-  const size_t qt_elems = std::max(static_cast<size_t>(D) * ld_qt, static_cast<size_t>(panel_rows) * ld_qs);   // either layout
-  bf* Qt = ok_raw || ws.dry ? ws.take<bf>(qt_elems) : nullptr;
+  bf* Qs = ok_raw || ws.dry ? ws.take<bf>(static_cast<size_t>(panel_rows) * ld_qs) : nullptr;
   bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
   // (x3: the first panel may be written by up to three launches — own columns first, the rest once K has arrived)
   const size_t part_slices = static_cast<size_t>(max_split > 64 ? 64 : max_split) * mi::kColQuarters;
   float* part = ws.take<float>(3 * part_slices * panel_rows);
-  float* qnorm = ws.take<float>(Bq);
-  float* knorm = ws.take<float>(Bk);
-  float* kmax = ws.take<float>(1);
-  float* diag = ws.take<float>(Bq);
-  float* lsum = ws.take<float>(Bq);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
-  if (!Q.p || !K.p || !sid_q || !sid_k || !row_out || !oq_raw || !rho || !wrow || !lambda_out || !flag_out || !(scale > 0.f))
+  if (!Q.p || !K.p || !sid_q || !sid_k || !ref || !diag || !row_out || !oq_raw || !wrow || !flag_out || !(scale > 0.f) ||
+      (!include_diag && !lambda))
     return MI_ERR_BAD_ARG;
+  const int* pr = t_run_if;
 
   MI_TRY(build_mask(mb, sid_q, sid_k, Bq, Bk, k_pad, stream));
-  MI_CUDA(cudaMemsetAsync(flag_out, 0, sizeof(int), stream));
   const Opnd Qe{Q.p, Q.ld, strict ? Q.split : 1}, Ke{K.p, K.ld, strict ? K.split : 1};
-  // references
-  if (feed == nullptr) {
-    row_norm_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Dp, Bq, D, qnorm);
-    MI_LAUNCH_CHECK("row_norm_kernel");
-  }
-  if (kmax_in != nullptr) {
-    kmax = const_cast<float*>(kmax_in);              // max_k |K_k| supplied by the caller (e.g. gathered with the study ids)
-  } else {
-    // the K rows may still be arriving (all-gather): everything above needed the study ids and Q only
-    if (ev_k_ready != nullptr) { MI_CUDA(cudaStreamWaitEvent(stream, ev_k_ready, 0)); ev_k_ready = nullptr; }
-    row_norm_kernel<<<blocks_for(Bk * 32, 256), 256, 0, stream>>>(Ke.p, Ke.ld, Ke.split, Dp, Bk, D, knorm);
-    MI_LAUNCH_CHECK("row_norm_kernel");
-    max_reduce_kernel<<<1, 1024, 0, stream>>>(knorm, Bk, kmax);
-    MI_LAUNCH_CHECK("max_reduce_kernel");
-  }
-  if (feed == nullptr) {
-    rho_kernel<<<blocks_for(Bq, 256), 256, 0, stream>>>(qnorm, kmax, scale, Bq, rho);
-    MI_LAUNCH_CHECK("rho_kernel");
-    // lambda = the same bound for the largest row norm (of ALL ranks when qmax_in is given): a global constant
-    if (qmax_in) { rho_kernel<<<1, 32, 0, stream>>>(qmax_in, kmax, scale, 1, lambda_out); MI_LAUNCH_CHECK("rho_kernel"); }
-    else { max_reduce_kernel<<<1, 1024, 0, stream>>>(rho, Bq, lambda_out); MI_LAUNCH_CHECK("max_reduce_kernel"); }
-  }
   // from here on the K rows are read: wait for the caller's "K complete" event (the all-gather of the text embeddings).
-  // When the caller vouches for this rank's own rows (k_local_valid) the wait moves further down: the positive-pair
-  // scores and the score tiles of the own column block need nothing else, so they run under the all-gather.
+  // When the caller vouches for this rank's own rows (k_local_valid) the wait moves further down: the score tiles of the
+  // own column block need nothing else, so they run under the all-gather.
   const long long own_t0 = q_offset / mi::TILE_N, own_t1 = (q_offset + Bq) / mi::TILE_N;
-  const bool own_first = ev_k_ready != nullptr && k_local_valid && kmax_in != nullptr && feed == nullptr && mn &&
+  const bool own_first = ev_k_ready != nullptr && k_local_valid && feed == nullptr &&
                          (q_offset % mi::TILE_N) == 0 && (Bq % mi::TILE_N) == 0 && Bq < Bk;
   if (ev_k_ready != nullptr && !own_first) MI_CUDA(cudaStreamWaitEvent(stream, ev_k_ready, 0));
-  if (feed == nullptr) {
-    diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Qe.p, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split, q_offset, Bq, D, Dp, scale, diag);
-    MI_LAUNCH_CHECK("diag_kernel");
-  }
-  // V^T for the P K product
-  if (!mn) {
-    if (k_hl) MI_CUDA(cudaMemsetAsync(Kt, 0, static_cast<size_t>(D) * ld_kt * sizeof(bf), stream));
-    MI_TRY(transpose_impl(K.p, K.ld, Kt, ld_kt, Bk, D, stream));
-    if (k_hl) MI_TRY(transpose_impl(K.p + Dp, K.ld, Kt + k_pad, ld_kt, Bk, D, stream));
-    if (Qt && strict) MI_CUDA(cudaMemsetAsync(Qt, 0, static_cast<size_t>(D) * ld_qt * sizeof(bf), stream));
-  }
 
   for (long long r0 = 0; r0 < Bq; r0 += panel_rows) {
     const long long rows = (Bq - r0 < panel_rows) ? (Bq - r0) : panel_rows;
-    if (feed != nullptr) {        // this panel's Q rows arrive now: their bound, the positive-pair scores, and (once) lambda
-      MI_TRY(feed->before_panel(r0, rows));
-      row_norm_kernel<<<blocks_for(rows * 32, 256), 256, 0, stream>>>(Qe.p + r0 * Qe.ld, Qe.ld, Qe.split, Dp, rows, D, qnorm + r0);
-      MI_LAUNCH_CHECK("row_norm_kernel");
-      rho_kernel<<<blocks_for(rows, 256), 256, 0, stream>>>(qnorm + r0, kmax, scale, rows, rho + r0);
-      MI_LAUNCH_CHECK("rho_kernel");
-      if (r0 == 0) { max_reduce_kernel<<<1, 1024, 0, stream>>>(rho, rows, lambda_out); MI_LAUNCH_CHECK("max_reduce_kernel"); }
-      diag_kernel<<<blocks_for(rows * 32, 256), 256, 0, stream>>>(Qe.p + r0 * Qe.ld, Qe.ld, Qe.split, Ke.p, Ke.ld, Ke.split,
-                                                                  q_offset + r0, rows, D, Dp, scale, diag + r0);
-      MI_LAUNCH_CHECK("diag_kernel");
-    }
+    if (feed != nullptr) MI_TRY(feed->before_panel(r0, rows));     // this panel's Q rows, references and diag arrive now
     // (1) score tiles -> P~ panel + row sums; a launch covers the N tiles [t0, t1) and appends its partial row sums
     const int n_mblk_p = static_cast<int>(cdiv(rows, rows_per_mblk()));
     const int rows_padded = n_mblk_p * rows_per_mblk();
@@ -1099,10 +1192,10 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
       ep.mask = mi::MaskInfo{mb.excl + r0, mb.n_same + r0, sid_q + r0, mb.sidk_pad};
       ep.q_rows = static_cast<int>(rows); ep.k_cols = static_cast<int>(Bk);
       ep.q_offset = q_offset + r0; ep.scale = scale;
-      ep.refq = rho + r0; ep.ln_wq = 0.f; ep.use_q = 1;
+      ep.refq = ref + r0; ep.ln_wq = 0.f; ep.use_q = 1;
       ep.refk2 = nullptr; ep.use_k = 0; ep.include_diag = include_diag;
       ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
-      ep.sum_part = part + static_cast<size_t>(n_part) * rows_padded; ep.rows_padded = rows_padded; ep.dbg = g_debug;
+      ep.sum_part = part + static_cast<size_t>(n_part) * rows_padded; ep.rows_padded = rows_padded;
       MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
                                           MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
       n_part += sc.n_split * mi::kColQuarters;
@@ -1117,50 +1210,45 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
       MI_TRY(score_tiles(0, n_ntile));
     }
     sum_merge_kernel<<<blocks_for(rows, 128), 128, 0, stream>>>(part, n_part, rows_padded, static_cast<int>(rows),
-                                                                rho + r0, lambda_out, mb.n_same + r0, static_cast<int>(Bk), diag + r0,
+                                                                ref + r0, lambda, mb.n_same + r0, static_cast<int>(Bk), diag + r0,
                                                                 include_diag, inv_bg, reinterpret_cast<float4*>(row_out) + r0,
-                                                                lsum + r0, wrow + r0, flag_out);
+                                                                wrow + r0, flag_out, pr);
     MI_LAUNCH_CHECK("sum_merge_kernel");
     if (scal_out != nullptr && r0 + panel_rows >= Bq) {
       // every row's statistics are final once the last panel's sums are merged: reduce them NOW (before the two
       // contractions of this panel) so a caller can exchange the scalars of the loss while the GEMMs still run
-      stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out);
+      stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out, pr);
       MI_LAUNCH_CHECK("stats_reduce_kernel");
+      flag_to_scal_kernel<<<1, 1, 0, stream>>>(flag_out, scal_out, pr);
+      MI_LAUNCH_CHECK("flag_to_scal_kernel");
       if (ev_after_scal != nullptr) MI_CUDA(cudaEventRecord(ev_after_scal, stream));
       if (fin != nullptr) {
-        loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_out, nullptr, fin->B, fin->estimator, fin->loss_out, fin->lse_f);
+        loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_out, nullptr, fin->B, fin->estimator, fin->loss_out, fin->lse_f,
+                                                   fin->dv_like ? lambda : nullptr, pr);
         MI_LAUNCH_CHECK("loss_finalize_kernel");
       }
     }
     Bump none(nullptr, 0, false);
     // (2) Ok_raw += P~^T (w Q)[panel]: contraction over the panel rows, P~ read MN-major
     if (ok_raw) {
-      if (mn) {
-        scale_rows_kernel<<<blocks_for(rows * D / 2, 256), 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qt,
-                                                                            strict ? Qt + Dp : nullptr, ld_qs, rows, D);
-        MI_LAUNCH_CHECK("scale_rows_kernel");
-      } else {
-        dim3 tg(static_cast<unsigned>(cdiv(D, 64)), static_cast<unsigned>(cdiv(rows, 64)));
-        transpose_scale_kernel<<<tg, 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qt, strict ? Qt + r_pad : nullptr,
-                                                       ld_qt, rows, D);
-        MI_LAUNCH_CHECK("transpose_scale_kernel");
-      }
+      scale_rows_kernel<<<blocks_for(rows * D / 8, 256), 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qs,
+                                                                          strict ? Qs + Dp : nullptr, ld_qs, rows, D, pr);
+      MI_LAUNCH_CHECK("scale_rows_kernel");
       GemmArgs g;
       const int kr = static_cast<int>(cdiv(rows, bk()));
       g.a_mn = true;
       g.a = MapSpec{P, rows, pitch, pitch};
-      if (mn) { g.b_mn = true; g.b = MapSpec{Qt, rows, strict ? Dp + D : D, ld_qs}; }
-      else g.b = MapSpec{Qt, D, strict ? r_pad + rows : rows, ld_qt};
+      g.b_mn = true; g.b = MapSpec{Qs, rows, strict ? Dp + D : D, ld_qs};
       g.M = Bk; g.N = D; g.seg_len = kr; g.k_blocks = kr;
       if (strict) {                                  // P_hi^T Q_hi + P_lo^T Q_hi + P_hi^T Q_lo
         g.k_blocks = 3 * kr; g.a_moff[1] = static_cast<int>(k_pad);
-        if (mn) g.b_noff[2] = static_cast<int>(Dp); else g.b_seg[2] = static_cast<int>(r_pad / bk());
+        g.b_noff[2] = static_cast<int>(Dp);
       }
       g.accumulate = r0 > 0;
       g.out_f32 = ok_raw; g.ld_out = D;
       if (fin != nullptr && scal_out != nullptr && r0 + panel_rows >= Bq) {      // last panel: finish the K-side output here
         g.acc_first = true;
-        if (fin->dv_like) { g.kappa_a = lambda_out; g.kappa_b = fin->lse_f; }
+        if (fin->dv_like) { g.kappa_a = lambda; g.kappa_b = fin->lse_f; }
         g.alpha = fin->alpha; g.gamma = fin->gamma;
         g.sub = Q.p; g.ld_sub = Q.ld; g.sub_lo = (strict && Q.split == 2) ? Q.p + Dp : nullptr;
         g.sub_row0 = q_offset; g.sub_rows = Bq;
@@ -1168,22 +1256,18 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
       MI_TRY(run_gemm(g, none, stream));
       if (ev_after_k != nullptr && r0 + panel_rows >= Bq) {
         MI_CUDA(cudaEventRecord(ev_after_k, stream));
-        t_reserve_sms = g_overlap_reserve_sms;      // the caller's collective starts here: leave it some SMs
+        t_reserve_sms = g_overlap_reserve_sms.load(std::memory_order_relaxed);   // the caller's collective starts here
       }
     }
     // (3) Oq_raw[panel] = P~ K
     {
       GemmArgs g;
       g.a = MapSpec{P, rows, pitch, pitch};
-      if (mn) { g.b_mn = true; g.b = MapSpec{K.p, Bk, k_hl ? Dp + D : D, K.ld}; }
-      else g.b = MapSpec{Kt, D, k_hl ? k_pad + Bk : Bk, ld_kt};
+      g.b_mn = true; g.b = MapSpec{K.p, Bk, k_hl ? Dp + D : D, K.ld};
       g.M = rows; g.N = D; g.seg_len = kp; g.k_blocks = kp;
       if (strict) {
         g.k_blocks = 2 * kp; g.a_seg[1] = kp;
-        if (k_hl) {
-          g.k_blocks = 3 * kp;
-          if (mn) g.b_noff[2] = static_cast<int>(Dp); else g.b_seg[2] = kp;
-        }
+        if (k_hl) { g.k_blocks = 3 * kp; g.b_noff[2] = static_cast<int>(Dp); }
       }
       g.out_f32 = oq_raw + r0 * D; g.ld_out = D;
       const int st = run_gemm(g, none, stream);
@@ -1194,19 +1278,24 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   return MI_OK;
 }
 
-__global__ void flag_to_loss_kernel(const int* __restrict__ flag, double* __restrict__ loss_out) { loss_out[7] = static_cast<double>(flag[0]); }
-
-bool g_single_pass = true;
-inline bool grads_or_plan_single(int estimator, int precision) {
-  return g_single_pass && estimator != MI_EST_INFONCE_SYM && (precision & MI_PREC_TWO_PASS) == 0;
+inline bool single_pass_estimator(int estimator, int precision) {
+  return estimator != MI_EST_INFONCE_SYM && (precision & MI_PREC_TWO_PASS) == 0;
 }
+
+// How critic_impl deals with a tripped single-pass guard (loss_out[7] != 0 after the sampled-reference pass):
+//   predicated: the exact repeat (references from EVERY column) is enqueued behind a device flag — a few empty launches
+//               when the guard stayed clear; fully asynchronous and CUDA-graph capturable (the device-pointer ABI);
+//   host:       nothing is enqueued; the caller reads loss_out[7] and repeats with MI_PREC_TWO_PASS (the host-buffer ABI,
+//               which synchronises anyway).
+struct Fallback { bool predicated = true; };
 
 int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, long long B, long long D,
                 int critic, int estimator, int precision, float inv_tau,
                 double* loss_out, float* dX, float* dY, float* dW, Bump& ws, cudaStream_t stream,
                 cudaEvent_t ev_dy_final = nullptr, bool* ev_recorded = nullptr,     // event recorded once dY is final (the
                                                                                      // dT / dX / dW work follows it)
-                const std::function<int(long long, long long)>* x_ready = nullptr) { // single-pass only: X rows arrive per panel
+                const std::function<int(long long, long long)>* x_ready = nullptr,  // single pass only: X rows arrive per panel
+                const Fallback& fb = Fallback()) {
   if (B <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   if (estimator < MI_EST_DV || estimator > MI_EST_INFONCE_SYM) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
@@ -1217,15 +1306,14 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   const bool sym = estimator == MI_EST_INFONCE_SYM;
   const bool dv_like = estimator == MI_EST_DV || estimator == MI_EST_INFONCE_REF;
   const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
-  // one score computation instead of two (see single_pass_impl); the symmetric estimator needs column
-  // references and stays on the two-pass path, as does any call that asks for it (MI_PREC_TWO_PASS)
-  const bool single = grads_or_plan_single(estimator, precision) && (dX != nullptr || dY != nullptr || dW != nullptr || ws.dry);
+  // one score computation instead of two (see single_pass_impl); the symmetric estimator needs exact column statistics
+  // before its gradient pass and stays on the statistics-pass + gradient-pass path.  MI_PREC_TWO_PASS asks for exact
+  // references (stride 1) in the single pass: the same statistics, then the pass can never trip its guard.
+  const bool single = !sym && (grads || ws.dry);
+  const bool exact_refs = (precision & MI_PREC_TWO_PASS) != 0;
   const int tsplit = (bilinear && strict) ? 2 : 1;        // T = X W kept as a hi/lo bf16 pair in strict mode
   const long long Dp = round_up(D, kSplitAlign);
   const long long ldT = tsplit == 2 ? 2 * Dp : D;
-  const long long b_pad = round_up(B, kSplitAlign);
-  const bool mn = g_mn_operands && !ws.dry;   // W, X and dT are read in place (MN-major descriptors); planning covers both
-  bf* Wt = (bilinear && !mn) ? ws.take<bf>(static_cast<size_t>(D) * D) : nullptr;
   bf* T = bilinear ? ws.take<bf>(static_cast<size_t>(B) * ldT) : nullptr;
   float* rows_r = ws.take<float>(static_cast<size_t>(B) * 4);
   float* rows_c = sym ? ws.take<float>(static_cast<size_t>(B) * 4) : nullptr;
@@ -1235,12 +1323,11 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   float* ref_r = ws.take<float>(B);
   float* ref_c = sym ? ws.take<float>(B) : nullptr;
   bf* dT16 = (bilinear && plan) ? ws.take<bf>(static_cast<size_t>(B) * ldT) : nullptr;
-  bf* Xt = (bilinear && plan && !mn) ? ws.take<bf>(static_cast<size_t>(D) * b_pad) : nullptr;
-  bf* dTt = (bilinear && plan && !mn) ? ws.take<bf>(static_cast<size_t>(D) * b_pad * tsplit) : nullptr;
-  float* sp_rho = single ? ws.take<float>(B) : nullptr;
+  float* sp_diag = single ? ws.take<float>(B) : nullptr;
   float* sp_wrow = single ? ws.take<float>(B) : nullptr;
   float* sp_lambda = single ? ws.take<float>(1) : nullptr;
-  int* sp_flag = single ? ws.take<int>(1) : nullptr;
+  int* sp_flags = single ? ws.take<int>(4) : nullptr;     // [0] rows tripped (sampled pass), [1] fallback predicate, [2] rows tripped (repeat)
+  double* sp_guard = single ? ws.take<double>(1) : nullptr;
   float* sp_oq = (single && (bilinear || !dX)) ? ws.take<float>(static_cast<size_t>(B) * D) : nullptr;   // dot: dX doubles as the raw buffer
   float* sp_ok = (single && !dY) ? ws.take<float>(static_cast<size_t>(B) * D) : nullptr;
   if (!ws.ok()) return MI_ERR_WORKSPACE;
@@ -1249,25 +1336,25 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   const Opnd Xo{X, D, 1}, Yo{Y, D, 1};
   const Opnd To = bilinear ? Opnd{T, ldT, tsplit} : Xo;
   size_t mk = ws.mark();
+  const bool streamed = x_ready != nullptr && single && !ws.dry;
+  Bump none(nullptr, 0, false);
+  // T[r0 : r0 + rows] = X[r0 : r0 + rows] W  (B operand of the engine is [N, K] = W^T: W itself read MN-major)
+  auto project = [&](long long r0, long long rows, Bump& w) -> int {
+    GemmArgs g;
+    g.a = MapSpec{X + r0 * D, rows, D, D};
+    g.b_mn = true; g.b = MapSpec{W, D, D, D};
+    g.M = rows; g.N = D; g.k_blocks = static_cast<int>(cdiv(D, bk()));
+    g.out_bf16 = T + r0 * ldT; g.ld_out16 = ldT; g.out_bf16_lo = tsplit == 2 ? T + r0 * ldT + Dp : nullptr;
+    return run_gemm(g, w, stream);
+  };
   if (bilinear) {
-    if (!ws.dry) {
-      if (!mn) MI_TRY(transpose_impl(W, D, Wt, D, D, D, stream));
-      if (tsplit == 2) MI_CUDA(cudaMemsetAsync(T, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
+    if (!ws.dry && tsplit == 2) {        // zero the gap columns between the hi and lo halves once
+      MI_CUDA(cudaMemsetAsync(T, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
+      if (dT16) MI_CUDA(cudaMemsetAsync(dT16, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
     }
-    // T = X W  (B operand of the engine is [N, K] = W^T: W itself read MN-major, or the transposed copy)
-    if (mn && x_ready != nullptr && single) {
-      // projected panel by panel inside the pass (see PanelFeed)
-    } else if (mn) {
-      GemmArgs g;
-      g.a = MapSpec{X, B, D, D};
-      g.b_mn = true; g.b = MapSpec{W, D, D, D};
-      g.M = B; g.N = D; g.k_blocks = static_cast<int>(cdiv(D, bk()));
-      g.out_bf16 = T; g.ld_out16 = ldT; g.out_bf16_lo = tsplit == 2 ? T + Dp : nullptr;
-      MI_TRY(run_gemm(g, ws, stream));
-    } else {
-      MI_TRY(gemm_impl(Xo, Opnd{Wt, D, 1}, B, D, D, 1.f, 0.f, nullptr, 0, nullptr, 0, T, ldT, tsplit, 1, ws, stream));
+    if (!streamed) {                     // (streamed: projected panel by panel inside the pass, see PanelFeed)
+      if (!ws.dry) MI_TRY(project(0, B, ws));
     }
-    ws.release(mk);
   }
   if (single) {
     const int incl = dv_like ? 0 : 1;
@@ -1277,90 +1364,112 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     // the loss is finalised inside the pass and, when dY is wanted, the last panel's contraction finishes dY in its epilogue
     SingleFin fin{loss_out, lse_f, B, estimator, inv_tau, gam, dv_like ? 1 : 0};
     const bool fused_k = dY != nullptr;
-    PanelFeed feed;
-    const bool streamed = x_ready != nullptr && mn && !ws.dry;
-    if (streamed) {
-      feed.before_panel = [&](long long r0, long long rows) -> int {
-        MI_TRY((*x_ready)(r0, rows));
-        if (bilinear) {                                  // T[r0 : r0 + rows] = X[r0 : r0 + rows] W
-          GemmArgs g;
-          g.a = MapSpec{X + r0 * D, rows, D, D};
-          g.b_mn = true; g.b = MapSpec{W, D, D, D};
-          g.M = rows; g.N = D; g.k_blocks = static_cast<int>(cdiv(D, bk()));
-          g.out_bf16 = T + r0 * ldT; g.ld_out16 = ldT; g.out_bf16_lo = tsplit == 2 ? T + r0 * ldT + Dp : nullptr;
-          Bump none(nullptr, 0, false);
-          MI_TRY(run_gemm(g, none, stream));
-        }
-        return MI_OK;
-      };
-    }
-    MI_TRY(single_pass_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, precision, gam, nullptr,
-                            rows_r, oq_raw, ok_raw, sp_rho, sp_wrow, sp_lambda, sp_flag, ws, stream,
-                            fused_k ? ev_dy_final : nullptr, scal_r, nullptr, nullptr, nullptr, fused_k ? &fin : nullptr,
-                            streamed ? &feed : nullptr));
-    if (fused_k && ev_dy_final && ev_recorded && !ws.dry) *ev_recorded = true;
-    ws.release(mk);
-    if (!ws.dry) {
+    const long long stride0 = exact_refs ? 1 : ref_stride_auto(B, B, D);
+    const long long panel_rows = panel_mblks(B, B, D, precision & 1) * rows_per_mblk();
+    // one complete pass: references (column sample of the given stride) -> score tiles / statistics / both contractions
+    // -> loss and dT.  `flag` counts the rows that tripped the guard of THIS pass.
+    auto run_pass = [&](long long stride, int* flag, bool feed_x) -> int {
+      if (!ws.dry) MI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+      PanelFeed feed;
+      if (feed_x) {
+        feed.before_panel = [&, stride](long long r0, long long rows) -> int {
+          MI_TRY((*x_ready)(r0, rows));
+          if (bilinear) MI_TRY(project(r0, rows, none));
+          const Opnd Tp{To.p + r0 * To.ld, To.ld, To.split};
+          const size_t m2 = ws.mark();
+          MI_TRY(ref_sample_impl(Tp, Yo, sid + r0, sid, r0, rows, B, D, inv_tau, incl, 0, B, stride,
+                                 ref_r + r0, sp_diag + r0, r0 == 0 ? sp_lambda : nullptr, ws, stream));
+          ws.release(m2);
+          return MI_OK;
+        };
+      } else {
+        MI_TRY(ref_sample_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, 0, B, stride, ref_r, sp_diag, sp_lambda, ws, stream));
+        ws.release(mk);
+      }
+      MI_TRY(single_pass_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, precision, gam, ref_r, sp_lambda, sp_diag,
+                              rows_r, oq_raw, ok_raw, sp_wrow, flag, ws, stream,
+                              fused_k ? ev_dy_final : nullptr, scal_r, nullptr, nullptr, fused_k ? &fin : nullptr,
+                              feed_x ? &feed : nullptr));
+      if (ws.dry) {                      // the per-panel reference sample of the streamed form lives on top of the pass
+        const size_t m2 = ws.mark();
+        MI_TRY(ref_sample_impl(To, Yo, sid, sid, 0, panel_rows < B ? panel_rows : B, B, D, inv_tau, incl, 0, B, stride,
+                               ref_r, sp_diag, sp_lambda, ws, stream));
+        ws.release(m2);
+      }
+      ws.release(mk);
+      if (ws.dry) return MI_OK;
       if (!fused_k) {
-        loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, nullptr, B, estimator, loss_out, lse_f);
+        loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, nullptr, B, estimator, loss_out, lse_f, dv_like ? sp_lambda : nullptr, t_run_if);
         MI_LAUNCH_CHECK("loss_finalize_kernel");
       }
-      flag_to_loss_kernel<<<1, 1, 0, stream>>>(sp_flag, loss_out);
-      MI_LAUNCH_CHECK("flag_to_loss_kernel");
-      const long long n = B * D;
-      if (tsplit == 2) MI_CUDA(cudaMemsetAsync(dT16, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
       // dT = inv_tau (c G~ Y - Y/B): fp32 (dot critic: this is dX) or the bf16 (hi/lo) operand of the dX / dW GEMMs
-      finalize_q_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(oq_raw, D, B, sp_rho, sp_wrow, lse_f, dv_like ? 1 : 0, inv_tau, gam,
-                                                                Y, D, 1, Dp, bilinear ? nullptr : dX, bilinear ? dT16 : nullptr,
-                                                                (bilinear && tsplit == 2) ? dT16 + Dp : nullptr, ldT);
+      finalize_q_kernel<<<blocks_for(B * D / 8, 256), 256, 0, stream>>>(oq_raw, D, B, ref_r, sp_wrow, lse_f, dv_like ? 1 : 0, inv_tau, gam,
+                                                                        Y, D, 1, Dp, bilinear ? nullptr : dX, bilinear ? dT16 : nullptr,
+                                                                        (bilinear && tsplit == 2) ? dT16 + Dp : nullptr, ldT, t_run_if);
       MI_LAUNCH_CHECK("finalize_q_kernel");
       // (dY was finished by the last panel's contraction: see SingleFin)
+      return MI_OK;
+    };
+    MI_TRY(run_pass(stride0, sp_flags, streamed));
+    if (fused_k && ev_dy_final && ev_recorded && !ws.dry) *ev_recorded = true;
+    if (!ws.dry && stride0 > 1) {
+      if (fb.predicated) {
+        guard_to_flag_kernel<<<1, 1, 0, stream>>>(loss_out, sp_flags + 1, sp_guard);
+        MI_LAUNCH_CHECK("guard_to_flag_kernel");
+        {
+          PredGuard pg(sp_flags + 1);
+          MI_TRY(run_pass(1, sp_flags + 2, false));
+        }
+        guard_report_kernel<<<1, 1, 0, stream>>>(sp_flags + 1, sp_guard, loss_out);
+        MI_LAUNCH_CHECK("guard_report_kernel");
+      }
+    } else if (ws.dry && stride0 > 1) {
+      MI_TRY(run_pass(1, sp_flags, false));
     }
   }
-  if (!single || ws.dry) {        // (planning covers both paths)
-  MI_TRY(stats_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
-  ws.release(mk);
-  if (sym) { MI_TRY(stats_impl(Yo, To, sid, sid, 0, B, B, D, inv_tau, rows_c, scal_c, ws, stream)); ws.release(mk); }
-  if (!ws.dry) {
-    loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, scal_c, B, estimator, loss_out, lse_f);
-    MI_LAUNCH_CHECK("loss_finalize_kernel");
-  }
-  if (!plan) return MI_OK;
-
-  if (!ws.dry) {
-    if (dv_like) make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_r, nullptr, 0, lse_f, B);
-    else make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_r, reinterpret_cast<const float4*>(rows_r), 3, nullptr, B);
-    MI_LAUNCH_CHECK("make_ref_kernel");
-    if (sym) {
-      make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_c, reinterpret_cast<const float4*>(rows_c), 3, nullptr, B);
-      MI_LAUNCH_CHECK("make_ref_kernel");
-    }
-  }
-  // G = incl (wq e^{S - refq[row]} + wk e^{S - refk[col]}):  DV: e^{S - LSE} on the negatives;
-  // InfoNCE row: (1/B) e^{S - r_i};  symmetric: (1/2B)(e^{S - r_i} + e^{S - c_j}); positives included.
-  float wq = 1.f, wk = 0.f;
-  const float* refq = ref_r; const float* refk = nullptr;
-  if (estimator == MI_EST_INFONCE_ROW) { wq = 1.f / B; }
-  else if (sym) { wq = 0.5f / B; wk = 0.5f / B; refk = ref_c; }
-  const int incl_diag = dv_like ? 0 : 1;
-  const float gamma = 1.f / static_cast<float>(B);
-
-  // one pass: dT = inv_tau (G Y - Y/B)  and  dY = inv_tau (G^T T - T/B)
-  GradOut oq, okk;
-  if (bilinear) { oq.bf16 = dT16; oq.ld16 = ldT; oq.split = tsplit; }
-  else { oq.f32 = dX; oq.ld = D; }
-  okk.f32 = dY; okk.ld = D;
-  const bool want_q = bilinear ? (dX || dW || ws.dry) : (dX || ws.dry);
-  const bool want_k = dY || ws.dry;
-  GradOut oq_none;
-  if (want_q || want_k) {
-    if (tsplit == 2 && !ws.dry) MI_CUDA(cudaMemsetAsync(dT16, 0, static_cast<size_t>(B) * ldT * sizeof(bf), stream));
-    MI_TRY(grad_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, refq, wq, refk, wk, incl_diag, precision & 1,
-                     inv_tau, gamma, want_q ? oq : oq_none, want_k ? &okk : nullptr, ws, stream, want_k ? ev_dy_final : nullptr));
-    if (want_k && ev_dy_final && ev_recorded && !ws.dry) *ev_recorded = true;
+  if (!single || ws.dry) {        // statistics pass(es) + gradient pass with exact references (planning covers both paths)
+    MI_TRY(stats_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
     ws.release(mk);
+    if (sym) { MI_TRY(stats_impl(Yo, To, sid, sid, 0, B, B, D, inv_tau, rows_c, scal_c, ws, stream)); ws.release(mk); }
+    if (!ws.dry) {
+      loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, scal_c, B, estimator, loss_out, lse_f, nullptr, nullptr);
+      MI_LAUNCH_CHECK("loss_finalize_kernel");
+    }
+    if (!plan) return MI_OK;
+
+    if (!ws.dry) {
+      if (dv_like) make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_r, nullptr, 0, lse_f, B);
+      else make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_r, reinterpret_cast<const float4*>(rows_r), 3, nullptr, B);
+      MI_LAUNCH_CHECK("make_ref_kernel");
+      if (sym) {
+        make_ref_kernel<<<blocks_for(B, 256), 256, 0, stream>>>(ref_c, reinterpret_cast<const float4*>(rows_c), 3, nullptr, B);
+        MI_LAUNCH_CHECK("make_ref_kernel");
+      }
+    }
+    // G = incl (wq e^{S - refq[row]} + wk e^{S - refk[col]}):  DV: e^{S - LSE} on the negatives;
+    // InfoNCE row: (1/B) e^{S - r_i};  symmetric: (1/2B)(e^{S - r_i} + e^{S - c_j}); positives included.
+    float wq = 1.f, wk = 0.f;
+    const float* refq = ref_r; const float* refk = nullptr;
+    if (estimator == MI_EST_INFONCE_ROW) { wq = 1.f / B; }
+    else if (sym) { wq = 0.5f / B; wk = 0.5f / B; refk = ref_c; }
+    const int incl_diag = dv_like ? 0 : 1;
+    const float gamma = 1.f / static_cast<float>(B);
+
+    // one pass: dT = inv_tau (G Y - Y/B)  and  dY = inv_tau (G^T T - T/B)
+    GradOut oq, okk;
+    if (bilinear) { oq.bf16 = dT16; oq.ld16 = ldT; oq.split = tsplit; }
+    else { oq.f32 = dX; oq.ld = D; }
+    okk.f32 = dY; okk.ld = D;
+    const bool want_q = bilinear ? (dX || dW || ws.dry) : (dX || ws.dry);
+    const bool want_k = dY || ws.dry;
+    GradOut oq_none;
+    if (want_q || want_k) {
+      MI_TRY(grad_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, refq, wq, refk, wk, incl_diag, precision & 1,
+                       inv_tau, gamma, want_q ? oq : oq_none, want_k ? &okk : nullptr, ws, stream, want_k ? ev_dy_final : nullptr));
+      if (want_k && ev_dy_final && ev_recorded && !ws.dry) *ev_recorded = true;
+      ws.release(mk);
+    }
   }
-  }   // two-pass path
   if (bilinear) {
     const Opnd dTo{dT16, ldT, tsplit};
     // dX = dT W^T : B operand [N = d, K = e] is W itself
@@ -1368,28 +1477,14 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
       MI_TRY(gemm_impl(dTo, Opnd{W, D, 1}, B, D, D, 1.f, 0.f, nullptr, 0, dX, D, nullptr, 0, 1, 1, ws, stream));
       ws.release(mk);
     }
-    // dW = X^T dT : A = X^T [D, B], B operand = dT^T [D, B] (hi | lo halves side by side), split-K over the batch
+    // dW = X^T dT : both operands are row-major [B, D] matrices contracted over their rows (MN-major), split-K over the batch
     if (dW || ws.dry) {
-      if (!ws.dry && !mn) {
-        MI_TRY(transpose_impl(X, D, Xt, b_pad, B, D, stream));
-        if (tsplit == 2) MI_CUDA(cudaMemsetAsync(dTt, 0, static_cast<size_t>(D) * b_pad * tsplit * sizeof(bf), stream));
-        MI_TRY(transpose_impl(dT16, ldT, dTt, b_pad * tsplit, B, D, stream));
-        if (tsplit == 2) MI_TRY(transpose_impl(dT16 + Dp, ldT, dTt + b_pad, b_pad * tsplit, B, D, stream));
-      }
       GemmArgs g;
-      const int kb = static_cast<int>(b_pad / bk());
-      if (mn) {        // both operands are row-major [B, D] matrices contracted over their rows
-        g.a_mn = true; g.a = MapSpec{X, B, D, D};
-        g.b_mn = true; g.b = MapSpec{dT16, B, tsplit == 2 ? Dp + D : D, ldT};
-      } else {
-        g.a = MapSpec{Xt, D, B, b_pad};
-        g.b = MapSpec{dTt, D, tsplit == 2 ? b_pad + B : B, b_pad * tsplit};
-      }
+      const int kb = static_cast<int>(round_up(B, kSplitAlign) / bk());
+      g.a_mn = true; g.a = MapSpec{X, B, D, D};
+      g.b_mn = true; g.b = MapSpec{dT16, B, tsplit == 2 ? Dp + D : D, ldT};
       g.M = D; g.N = D; g.seg_len = kb; g.k_blocks = kb;
-      if (tsplit == 2) {
-        g.k_blocks = 2 * kb;
-        if (mn) g.b_noff[1] = static_cast<int>(Dp); else g.b_seg[1] = kb;
-      }
+      if (tsplit == 2) { g.k_blocks = 2 * kb; g.b_noff[1] = static_cast<int>(Dp); }
       const long long tiles = cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N);
       long long ks = cdiv(num_pairs(), tiles);
       if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
@@ -1417,7 +1512,8 @@ int device_check() {
 
 // second stream + event of the host-buffer entry point (one per device, created on first use)
 constexpr int kMaxFeedChunks = 64;
-struct CopySide { cudaStream_t stream; cudaEvent_t ev; cudaEvent_t ev_y; cudaEvent_t ev_x[kMaxFeedChunks]; };
+struct CopySide { cudaStream_t stream; cudaEvent_t ev; cudaEvent_t ev_y; cudaEvent_t ev_in; cudaEvent_t ev_x[kMaxFeedChunks]; };
+std::mutex g_host_entry_mu[64];      // the host-buffer entry point shares one CopySide per device: one call at a time per device
 int copy_side(CopySide* out) {
   static std::mutex mu;
   static CopySide cache[64];
@@ -1429,6 +1525,7 @@ int copy_side(CopySide* out) {
     MI_CUDA(cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking));
     MI_CUDA(cudaEventCreateWithFlags(&cache[dev].ev, cudaEventDisableTiming));
     MI_CUDA(cudaEventCreateWithFlags(&cache[dev].ev_y, cudaEventDisableTiming));
+    MI_CUDA(cudaEventCreateWithFlags(&cache[dev].ev_in, cudaEventDisableTiming));
     for (int i = 0; i < kMaxFeedChunks; ++i) MI_CUDA(cudaEventCreateWithFlags(&cache[dev].ev_x[i], cudaEventDisableTiming));
     have[dev] = true;
   }
@@ -1453,7 +1550,7 @@ const char* mi_status_string(int status) {
   }
 }
 const char* mi_last_cuda_error(void) { return g_cuda_err; }
-int mi_abi_version(void) { return 3; }
+int mi_abi_version(void) { return 4; }
 int mi_device_check(void) { return device_check(); }
 int64_t mi_launch_count(void) { return g_launches.load(); }
 void mi_set_profiling(int on) { g_profiling = on != 0; }
@@ -1471,12 +1568,10 @@ int mi_profile_read(double* ms, int64_t* launches) {
   g_prof.clear();
   return MI_OK;
 }
-void mi_set_debug(int v) { g_debug = v; }
-void mi_set_single_pass(int on) { g_single_pass = on != 0; }
-void mi_set_mn_operands(int on) { g_mn_operands = on != 0; }
-void mi_set_overlap_reserve_sms(int n) { g_overlap_reserve_sms = (n > 0 && n < 128) ? (n & ~1) : 0; }
+void mi_set_ref_sample_columns(int64_t n) { g_ref_sample_cols.store(n, std::memory_order_relaxed); }
+void mi_set_overlap_reserve_sms(int n) { g_overlap_reserve_sms.store((n > 0 && n < 128) ? (n & ~1) : 0, std::memory_order_relaxed); }
 void mi_set_mlp_panel_pairs(int64_t pairs) { g_mlp_max_pairs = pairs > 0 ? pairs : (1LL << 20); }
-void mi_set_cta_group(int g) { g_cta_group = (g == 1) ? 1 : 2; }
+void mi_set_cta_group(int g) { g_cta_group.store((g == 1) ? 1 : 2, std::memory_order_relaxed); }
 int mi_get_cta_group(void) { return cta_group(); }
 
 int mi_gemm_bf16(const void* A, int64_t lda, int a_split, const void* B, int64_t ldb, int b_split,
@@ -1570,11 +1665,36 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
                    reinterpret_cast<cudaEvent_t>(event_after_outk));
 }
 
+size_t mi_score_ref_sample_workspace_bytes(int64_t Bq, int64_t n_cols, int64_t D, int64_t stride) {
+  Bump ws(nullptr, 0, true);
+  if (stride < 1) stride = ref_stride_auto(Bq, n_cols, D);
+  // planned for a hi/lo Q (the larger K loop does not change the workspace, only the mask / partial buffers matter)
+  if (ref_sample_impl(Opnd{nullptr, D, 1}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, n_cols, D, 1.f, 0, 0, n_cols, stride,
+                      nullptr, nullptr, nullptr, ws, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_score_ref_sample(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
+                        const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                        int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag,
+                        int64_t col0, int64_t n_cols, int64_t stride,
+                        float* ref_out, float* diag_out, float* lambda_out,
+                        void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
+  MI_TRY(device_check());
+  if (q_offset < 0 || q_offset + Bq > Bk) return MI_ERR_BAD_ARG;
+  if (stride < 1) stride = ref_stride_auto(Bq, n_cols, D);
+  Bump ws(workspace, workspace_bytes, false);
+  return ref_sample_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
+                         Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
+                         sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, col0, n_cols, stride,
+                         ref_out, diag_out, lambda_out, ws, reinterpret_cast<cudaStream_t>(stream_));
+}
+int64_t mi_ref_sample_stride(int64_t Bq, int64_t n_cols, int64_t D) { return ref_stride_auto(Bq, n_cols, D); }
+
 size_t mi_score_single_pass_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision) {
   Bump ws(nullptr, 0, true);
   const int sp = (precision & 1) ? 2 : 1;
-  if (single_pass_impl(Opnd{nullptr, D, sp}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, Bk, D, 1.f, 0, precision, 1.f, nullptr,
-                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws, nullptr) != MI_OK) return 0;
+  if (single_pass_impl(Opnd{nullptr, D, sp}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, Bk, D, 1.f, 0, precision, 1.f,
+                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws, nullptr) != MI_OK) return 0;
   return ws.peak + 256;
 }
 int mi_row_norm_max(const void* A, int64_t lda, int a_split, int64_t rows, int64_t D, float* norm_out, float* max_out, mi_stream_t stream_) {
@@ -1584,52 +1704,54 @@ int mi_row_norm_max(const void* A, int64_t lda, int a_split, int64_t rows, int64
   row_norm_kernel<<<blocks_for(rows * 32, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda, a_split == 2 ? 2 : 1,
                                                                    round_up(D, kSplitAlign), rows, D, norm_out);
   MI_LAUNCH_CHECK("row_norm_kernel");
-  max_reduce_kernel<<<1, 1024, 0, stream>>>(norm_out, rows, max_out);
+  max_reduce_kernel<<<1, 1024, 0, stream>>>(norm_out, rows, max_out, nullptr);
   MI_LAUNCH_CHECK("max_reduce_kernel");
   return MI_OK;
 }
 int mi_score_single_pass(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
                          const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
                          int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag, int precision, float inv_bg,
-                         const float* qnorm_max_in, float* row_out, double* scal_out, float* oq_raw, float* ok_raw,
-                         float* rho, float* wrow, float* lambda_out, int32_t* flag_out, void* event_after_outk,
-                         void* event_after_scal, const float* knorm_max_in, void* event_k_ready, int k_local_valid,
+                         const float* ref, const float* lambda, const float* diag,
+                         float* row_out, double* scal_out, float* oq_raw, float* ok_raw,
+                         float* wrow, int32_t* flag_out, void* event_after_outk,
+                         void* event_after_scal, void* event_k_ready, int k_local_valid,
                          void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
   MI_TRY(device_check());
-  if (q_offset < 0 || q_offset + Bq > Bk || !scal_out) return MI_ERR_BAD_ARG;
+  if (q_offset < 0 || q_offset + Bq > Bk || !scal_out || !flag_out) return MI_ERR_BAD_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   Bump ws(workspace, workspace_bytes, false);
+  MI_CUDA(cudaMemsetAsync(flag_out, 0, sizeof(int), stream));
   MI_TRY(single_pass_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
                           Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
-                          sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, precision, inv_bg, qnorm_max_in,
-                          row_out, oq_raw, ok_raw, rho, wrow, lambda_out, flag_out, ws, stream,
+                          sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, precision, inv_bg, ref, lambda, diag,
+                          row_out, oq_raw, ok_raw, wrow, flag_out, ws, stream,
                           reinterpret_cast<cudaEvent_t>(event_after_outk), scal_out, reinterpret_cast<cudaEvent_t>(event_after_scal),
-                          knorm_max_in, reinterpret_cast<cudaEvent_t>(event_k_ready), nullptr, nullptr, k_local_valid != 0));
+                          reinterpret_cast<cudaEvent_t>(event_k_ready), nullptr, nullptr, k_local_valid != 0));
   return MI_OK;
 }
-int mi_merge_scalars(const double* scal_all, int world, int64_t B_global, int estimator, double* loss_out, float* lse_out,
-                     double* scratch8, mi_stream_t stream_) {
+int mi_merge_scalars(const double* scal_all, int world, int64_t B_global, int estimator, const float* lambda,
+                     double* loss_out, float* lse_out, double* scratch8, mi_stream_t stream_) {
   MI_TRY(device_check());
   if (!scal_all || world <= 0 || !loss_out || !lse_out || !scratch8 || estimator < MI_EST_DV || estimator > MI_EST_INFONCE_ROW)
     return MI_ERR_BAD_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   merge_scal_kernel<<<1, 32, 0, stream>>>(scal_all, world, scratch8);
   MI_LAUNCH_CHECK("merge_scal_kernel");
-  loss_finalize_kernel<<<1, 32, 0, stream>>>(scratch8, nullptr, B_global, estimator, loss_out, lse_out);
+  loss_finalize_kernel<<<1, 32, 0, stream>>>(scratch8, nullptr, B_global, estimator, loss_out, lse_out, lambda, nullptr);
   MI_LAUNCH_CHECK("loss_finalize_kernel");
   return MI_OK;
 }
-int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const float* rho, const float* wrow, const float* lse,
+int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const float* ref, const float* wrow, const float* lse,
                          int dv_like, float alpha, float gamma, const void* kdiag, int64_t ldk, int k_split,
                          float* out_f32, void* out_bf16, int64_t ld16, int out_split, mi_stream_t stream_) {
   MI_TRY(device_check());
-  if (!oq_raw || !rho || !wrow || !kdiag || rows <= 0 || D <= 0 || (dv_like && !lse) || (!out_f32 && !out_bf16)) return MI_ERR_BAD_ARG;
+  if (!oq_raw || !ref || !wrow || !kdiag || rows <= 0 || D <= 0 || (D % 8) != 0 || (dv_like && !lse) || (!out_f32 && !out_bf16)) return MI_ERR_BAD_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long Dp = round_up(D, kSplitAlign);
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
-  finalize_q_kernel<<<blocks_for(rows * D, 256), 256, 0, stream>>>(oq_raw, D, rows, rho, wrow, lse, dv_like, alpha, gamma,
-                                                                   static_cast<const __nv_bfloat16*>(kdiag), ldk, k_split == 2 ? 2 : 1, Dp,
-                                                                   out_f32, ob, (ob && out_split == 2) ? ob + Dp : nullptr, ld16);
+  finalize_q_kernel<<<blocks_for(rows * D / 8, 256), 256, 0, stream>>>(oq_raw, D, rows, ref, wrow, lse, dv_like, alpha, gamma,
+                                                                       static_cast<const __nv_bfloat16*>(kdiag), ldk, k_split == 2 ? 2 : 1, Dp,
+                                                                       out_f32, ob, (ob && out_split == 2) ? ob + Dp : nullptr, ld16, nullptr);
   MI_LAUNCH_CHECK("finalize_q_kernel");
   return MI_OK;
 }
@@ -1695,69 +1817,94 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
   uint8_t* core = ws.base + ws.off;
   const size_t core_bytes = dev_scratch_bytes - ws.off;
   // Input side: the text embeddings go first; the image embeddings follow in row panels on a second stream, each with
-  // its own event, and the single pass consumes them panel by panel (cast + projection inside the pass) while the rest
-  // is still crossing PCIe.  Output side: dY is final before the last panel's dT contraction and the dX / dW GEMMs, its
-  // copy back starts from an in-pass event on the second stream.
+  // its own event, and the single pass consumes them panel by panel (cast + projection + references inside the pass)
+  // while the rest is still crossing PCIe.  Output side: dY is final before the last panel's dT contraction and the
+  // dX / dW GEMMs, its copy back starts from an in-pass event on the second stream.
+  // The second stream and its events are per device: calls on the same device are serialised here (the call
+  // synchronises before it returns, so nothing is lost).
+  int dev = 0;
+  MI_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> entry_lock(g_host_entry_mu[dev & 63]);
   CopySide side;
   const bool have_side = copy_side(&side) == MI_OK;
+  // every exit below this point leaves no copy in flight into / out of the caller's buffers
+  auto fail = [&](int st) -> int {
+    if (have_side) (void)cudaStreamSynchronize(side.stream);
+    (void)cudaStreamSynchronize(stream);
+    return st;
+  };
+#define MI_HOST_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(set_cuda_err(e__, #call)); } while (0)
+#define MI_HOST_TRY(call) do { int s__ = (call); if (s__ != MI_OK) return fail(s__); } while (0)
   const long long chunk_rows = panel_mblks(B, B, D, precision & 1) * rows_per_mblk();
   const long long n_chunks = cdiv(B, chunk_rows);
   const bool want_grads = dX_host || dY_host || (dW_host && bilinear);
-  const bool streamed = have_side && want_grads && g_mn_operands && grads_or_plan_single(estimator, precision) &&
-                        n_chunks <= kMaxFeedChunks;
-  MI_CUDA(cudaMemcpyAsync(sid, sid_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, stream));
+  const bool streamed = have_side && want_grads && single_pass_estimator(estimator, precision) && n_chunks <= kMaxFeedChunks;
+  if (have_side) {      // the second stream starts after whatever the caller's stream still does with dev_scratch
+    MI_HOST_CUDA(cudaEventRecord(side.ev_in, stream));
+    MI_HOST_CUDA(cudaStreamWaitEvent(side.stream, side.ev_in, 0));
+  }
+  MI_HOST_CUDA(cudaMemcpyAsync(sid, sid_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, stream));
   if (bilinear) {
-    MI_CUDA(cudaMemcpyAsync(W32, W_host, nDD * 4, cudaMemcpyHostToDevice, stream));
-    MI_TRY(mi_cast_f32_to_bf16(W32, W16, static_cast<int64_t>(nDD), stream_));
+    MI_HOST_CUDA(cudaMemcpyAsync(W32, W_host, nDD * 4, cudaMemcpyHostToDevice, stream));
+    MI_HOST_TRY(mi_cast_f32_to_bf16(W32, W16, static_cast<int64_t>(nDD), stream_));
   }
   std::function<int(long long, long long)> x_ready;
   if (streamed) {
-    MI_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, side.stream));
-    MI_CUDA(cudaEventRecord(side.ev_y, side.stream));
+    MI_HOST_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, side.stream));
+    MI_HOST_CUDA(cudaEventRecord(side.ev_y, side.stream));
     for (long long c = 0; c < n_chunks; ++c) {
       const long long r0 = c * chunk_rows, rows = (B - r0 < chunk_rows) ? (B - r0) : chunk_rows;
-      MI_CUDA(cudaMemcpyAsync(X32 + r0 * D, X_host + r0 * D, static_cast<size_t>(rows) * D * 4, cudaMemcpyHostToDevice, side.stream));
-      MI_CUDA(cudaEventRecord(side.ev_x[c], side.stream));
+      MI_HOST_CUDA(cudaMemcpyAsync(X32 + r0 * D, X_host + r0 * D, static_cast<size_t>(rows) * D * 4, cudaMemcpyHostToDevice, side.stream));
+      MI_HOST_CUDA(cudaEventRecord(side.ev_x[c], side.stream));
     }
-    MI_CUDA(cudaStreamWaitEvent(stream, side.ev_y, 0));
-    MI_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
+    MI_HOST_CUDA(cudaStreamWaitEvent(stream, side.ev_y, 0));
+    MI_HOST_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
     x_ready = [&](long long r0, long long rows) -> int {
       if (r0 % chunk_rows != 0) return MI_ERR_BAD_ARG;                // the pass walks the same panels
       MI_CUDA(cudaStreamWaitEvent(stream, side.ev_x[r0 / chunk_rows], 0));
       return mi_cast_f32_to_bf16(X32 + r0 * D, X16 + r0 * D, static_cast<int64_t>(rows * D), stream_);
     };
   } else {
-    MI_CUDA(cudaMemcpyAsync(X32, X_host, nBD * 4, cudaMemcpyHostToDevice, stream));
-    MI_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, stream));
-    MI_TRY(mi_cast_f32_to_bf16(X32, X16, static_cast<int64_t>(nBD), stream_));
-    MI_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
+    MI_HOST_CUDA(cudaMemcpyAsync(X32, X_host, nBD * 4, cudaMemcpyHostToDevice, stream));
+    MI_HOST_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, stream));
+    MI_HOST_TRY(mi_cast_f32_to_bf16(X32, X16, static_cast<int64_t>(nBD), stream_));
+    MI_HOST_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
   }
   const bool early = dY_host != nullptr && have_side;
-  bool recorded = false;
-  {
+  // Pass 0: sampled references, no device-side fallback (the host decides: this call synchronises anyway).
+  // Pass 1 (only if the guard tripped): exact references, inputs already on the device.
+  double guard0 = 0.0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    bool recorded = false;
+    Fallback fb; fb.predicated = false;
     Bump cws(core, core_bytes, false);
-    const int st = critic_impl(X16, Y16, bilinear ? W16 : nullptr, sid, B, D, critic, estimator, precision, inv_tau, loss,
-                               dX_host ? dX : nullptr, dY_host ? dY : nullptr, (dW_host && bilinear) ? dW : nullptr, cws, stream,
-                               early ? side.ev : nullptr, &recorded, streamed ? &x_ready : nullptr);
-    if (st != MI_OK) {                                   // leave no copy in flight into the caller's scratch
-      if (have_side) (void)cudaStreamSynchronize(side.stream);
-      (void)cudaStreamSynchronize(stream);
-      return st;
+    MI_HOST_TRY(critic_impl(X16, Y16, bilinear ? W16 : nullptr, sid, B, D, critic, estimator,
+                            attempt == 0 ? precision : (precision | MI_PREC_TWO_PASS), inv_tau, loss,
+                            dX_host ? dX : nullptr, dY_host ? dY : nullptr, (dW_host && bilinear) ? dW : nullptr, cws, stream,
+                            early ? side.ev : nullptr, &recorded, (streamed && attempt == 0) ? &x_ready : nullptr, fb));
+    if (dY_host) {
+      cudaStream_t cs = stream;
+      if (early && recorded) {
+        MI_HOST_CUDA(cudaStreamWaitEvent(side.stream, side.ev, 0));
+        cs = side.stream;
+      }
+      MI_HOST_CUDA(cudaMemcpyAsync(dY_host, dY, nBD * 4, cudaMemcpyDeviceToHost, cs));
     }
-  }
-  if (dY_host) {
-    cudaStream_t cs = stream;
-    if (early && recorded) {
-      MI_CUDA(cudaStreamWaitEvent(side.stream, side.ev, 0));
-      cs = side.stream;
+    MI_HOST_CUDA(cudaMemcpyAsync(loss_out_host, loss, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (dX_host) MI_HOST_CUDA(cudaMemcpyAsync(dX_host, dX, nBD * 4, cudaMemcpyDeviceToHost, stream));
+    if (dW_host && bilinear) MI_HOST_CUDA(cudaMemcpyAsync(dW_host, dW, nDD * 4, cudaMemcpyDeviceToHost, stream));
+    MI_HOST_CUDA(cudaStreamSynchronize(stream));
+    if (have_side) MI_HOST_CUDA(cudaStreamSynchronize(side.stream));
+    if (attempt == 1) {          // same report as the device entry: [7] = rows that tripped the sampled pass
+      if (loss_out_host[7] != 0.0) loss_out_host[0] = std::nan("");   // impossible by construction (l = 1 for every row)
+      loss_out_host[7] = guard0;
+      break;
     }
-    MI_CUDA(cudaMemcpyAsync(dY_host, dY, nBD * 4, cudaMemcpyDeviceToHost, cs));
+    if (!(loss_out_host[7] != 0.0)) break;
+    guard0 = loss_out_host[7];
   }
-  MI_CUDA(cudaMemcpyAsync(loss_out_host, loss, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-  if (dX_host) MI_CUDA(cudaMemcpyAsync(dX_host, dX, nBD * 4, cudaMemcpyDeviceToHost, stream));
-  if (dW_host && bilinear) MI_CUDA(cudaMemcpyAsync(dW_host, dW, nDD * 4, cudaMemcpyDeviceToHost, stream));
-  MI_CUDA(cudaStreamSynchronize(stream));
-  if (early && recorded) MI_CUDA(cudaStreamSynchronize(side.stream));
+#undef MI_HOST_CUDA
+#undef MI_HOST_TRY
   return MI_OK;
 }
 

@@ -308,9 +308,9 @@ int mlp_impl(const float* X, const float* Y, const MlpParams& prm, const int* si
     // ---- estimator on S (same reductions and fp64 finalisation as the separable critics)
     mlp_row_stats_kernel<<<blocks_for(B * 32, 256), 256, 0, stream>>>(S, sid, B, reinterpret_cast<float4*>(rows_r));
     MI_LAUNCH_CHECK("mlp_row_stats_kernel");
-    stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(rows_r), static_cast<int>(B), scal);
+    stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(rows_r), static_cast<int>(B), scal, nullptr);
     MI_LAUNCH_CHECK("stats_reduce_kernel");
-    loss_finalize_kernel<<<1, 32, 0, stream>>>(scal, nullptr, B, estimator, loss_out, lse_f);
+    loss_finalize_kernel<<<1, 32, 0, stream>>>(scal, nullptr, B, estimator, loss_out, lse_f, nullptr, nullptr);
     MI_LAUNCH_CHECK("loss_finalize_kernel");
   }
   if (!plan) return MI_OK;

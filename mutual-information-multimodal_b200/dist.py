@@ -42,7 +42,7 @@ def _all_gather_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
 
 
 def merge_scalars(scal_all: torch.Tensor) -> dict:
-    """scal_all [world, 8] fp64 rows {m, sum exp(lse-m), n_neg, diag_sum, rowloss_sum, rows_wo_neg, 0, 0}
+    """scal_all [world, 8] fp64 rows {m, sum exp(lse-m), n_neg, diag_sum, rowloss_sum, rows_wo_neg, guard rows, 0}
     -> global quantities (pure tensor math, no host sync)."""
     m = scal_all[:, 0]
     gm = torch.max(m)
@@ -54,6 +54,7 @@ def merge_scalars(scal_all: torch.Tensor) -> dict:
         "diag_sum": scal_all[:, 3].sum(),
         "rowloss_sum": scal_all[:, 4].sum(),
         "rows_without_negatives": scal_all[:, 5].sum(),
+        "guard": scal_all[:, 6].sum(),
     }
 
 
@@ -134,9 +135,24 @@ class _A2ASum:
         return self.slabs.sum(0)
 
 
+_guard_host = {}
+
+
+def _guard_buffer(device):
+    key = torch.device(device).index
+    if key not in _guard_host:
+        _guard_host[key] = torch.zeros(1, dtype=torch.float64).pin_memory()
+    return _guard_host[key]
+
+
+class GuardTripped(Exception):
+    """Internal: the sampled references of the single pass left the safe window on some rank (same verdict on all)."""
+
+
 def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
-                      precision, qmax, world, group, nccl, kmax=None, ev_y=None, own_first=False):
-    """dv / infonce / row InfoNCE with ONE score computation per rank (see mi_score_single_pass)."""
+                      precision, smp, lam, world, group, nccl, ev_y=None, own_first=False, check_guard=True):
+    """dv / infonce / row InfoNCE with ONE score computation per rank (see mi_score_single_pass).  ``smp`` = this rank's
+    reference sample (ref, diag), ``lam`` = the global constant (max over ranks of the largest reference)."""
     bilinear = Wb is not None
     strict = precision == "strict"
     dv_like = estimator != "infonce_row"
@@ -146,36 +162,53 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
         ev, ev_s = torch.cuda.Event(), torch.cuda.Event()
         ev.record(); ev_s.record()                    # (creates the CUDA events; the library re-records them in the pass)
     sp = backend.score_single_pass(T_local, Y_all, sid_loc, sid_all, off, inv_tau, not dv_like, precision, gamma,
-                                   qmax=qmax, want_k=True, event_after_k=ev,
-                                   **({"event_after_scal": ev_s, "kmax": kmax, "event_k_ready": ev_y,
-                                       "k_local_valid": own_first} if nccl else {}))
+                                   smp["ref"], lam, smp["diag"], want_k=True, event_after_k=ev,
+                                   **({"event_after_scal": ev_s, "event_k_ready": ev_y, "k_local_valid": own_first} if nccl else {}))
     scal = sp["scal"].reshape(1, 8)
     if nccl:
-        # the loss scalars are final BEFORE the panel's two contractions: exchange them first, then start the big
-        # reduce-scatter — both from the side stream, so NCCL runs them in this order under the GEMMs and the
-        # finalisation that follows never queues behind the reduce-scatter
+        # the loss scalars (and the guard counts, scal[6]) are final BEFORE the panel's two contractions: exchange and merge
+        # them on the side stream under the GEMMs.  The host reads the merged guard there — it waits for the score tiles,
+        # not for the step — and only then enqueues the reduce-scatter and the rest (or abandons the step for the exact path).
         side = _side_stream(scal.device)
         scal_all = torch.empty((world, 8), dtype=scal.dtype, device=scal.device)
         side.wait_event(ev_s)
+        ev_m = torch.cuda.Event()
         with torch.cuda.stream(side):
-            s_work = dist.all_gather_into_tensor(scal_all, scal, group=group, async_op=True)
+            dist.all_gather_into_tensor(scal_all, scal, group=group)
+            out = backend.merge_scalars_loss(scal_all, estimator, Bg, lam if dv_like else None)
+            if check_guard:
+                gh = _guard_buffer(scal.device)
+                gh.copy_(out["guard"].reshape(1), non_blocking=True)
+            ev_m.record(side)
+        main = torch.cuda.current_stream()
         scal.record_stream(side)
         scal_all.record_stream(side)
+        for t in list(out.values()):          # allocated on the side stream, consumed on the compute stream
+            t.record_stream(main)
+        if check_guard:
+            ev_m.synchronize()
+            if float(gh[0]) != 0.0:
+                raise GuardTripped()
         dY, rs_work = _reduce_scatter_rows(sp["ok_raw"], Bl, off, world, group, nccl, ev)
-        s_work.wait()
+        torch.cuda.current_stream().wait_event(ev_m)
+        lse32 = out.pop("lse32")
     else:
         dY, rs_work = _reduce_scatter_rows(sp["ok_raw"], Bl, off, world, group, nccl, ev)
         scal_all = _all_gather_rows(scal, world, group)
-    if hasattr(backend, "merge_scalars_loss"):        # two tiny kernels instead of ~25 framework ops
-        out = backend.merge_scalars_loss(scal_all, estimator, Bg)
-        lse32 = out.pop("lse32")
-    else:
-        g = merge_scalars(scal_all)
-        out = {"pos_mean": g["diag_sum"] / Bg, "lse_neg": g["lse_neg"], "n_neg": g["n_neg"], "loss_row": g["rowloss_sum"] / Bg}
-        out["loss"] = _loss_from(out, estimator)
-        lse32 = out["lse_neg"].to(torch.float32).reshape(1)
-    out["loose_reference_rows"] = sp["flag"]
-    dT32, dT16 = backend.single_finalize_q(sp["oq_raw"], sp["rho"], sp["wrow"], lse32, dv_like, inv_tau, gamma, Yb,
+        if hasattr(backend, "merge_scalars_loss"):        # two tiny kernels instead of ~25 framework ops
+            out = backend.merge_scalars_loss(scal_all, estimator, Bg, lam if dv_like else None)
+            lse32 = out.pop("lse32")
+        else:
+            g = merge_scalars(scal_all)
+            out = {"pos_mean": g["diag_sum"] / Bg, "lse_neg": g["lse_neg"], "n_neg": g["n_neg"], "loss_row": g["rowloss_sum"] / Bg,
+                   "guard": g["guard"]}
+            out["loss"] = _loss_from(out, estimator)
+            lse32 = out["lse_neg"].to(torch.float32).reshape(1)
+            if dv_like:
+                out["guard"] = out["guard"] + ((lam.double().reshape(()) - out["lse_neg"]).abs() > 60.0).double()
+        if check_guard and float(out["guard"]) != 0.0:
+            raise GuardTripped()
+    dT32, dT16 = backend.single_finalize_q(sp["oq_raw"], smp["ref"], sp["wrow"], lse32, dv_like, inv_tau, gamma, Yb,
                                            want_f32=not bilinear, want_bf16=bilinear, out_split=bilinear and strict)
     dX, dW, dw_work = dT32, None, None
     if bilinear:
@@ -187,7 +220,7 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
         rs_work.wait()
     if isinstance(dY, _A2ASum):
         dY = dY.resolve()
-    backend.single_finalize_k(dY, sp["lam"], lse32, dv_like, inv_tau, gamma, T_local)
+    backend.single_finalize_k(dY, lam, lse32, dv_like, inv_tau, gamma, T_local)
     if dw_work is not None:
         dw_work.wait()
     return out, dX, dY, dW
@@ -196,9 +229,15 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
 def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W: Optional[torch.Tensor],
                                 sid_local: torch.Tensor, estimator: str = "dv", precision: str = "fast",
                                 inv_tau: float = 1.0, need_grads: bool = True, group=None, backend=None,
-                                two_pass: bool = False):
+                                two_pass: bool = False, check_guard: bool = True):
     """Returns (stats dict of 0-d fp64 tensors incl. 'loss', dX_local, dY_local, dW) — dW already
-    summed over ranks.  All ranks must hold the same number of rows."""
+    summed over ranks.  All ranks must hold the same number of rows.
+
+    dv / infonce / infonce_row take the single pass with sampled references.  Its guard (rows whose reference left the safe
+    window, summed over ranks — every rank sees the same number) is read on the host as soon as the score tiles are done; if
+    it is non-zero the step is repeated on the exact path (``two_pass=True``: statistics pass + gradient pass).
+    ``check_guard=False`` skips that host read (no synchronisation at all); the count is then left in stats['guard'] for the
+    caller to act on."""
     if backend is None:
         from . import ops as backend  # the CUDA path; raises if the library / device is missing
     world, rank = _world(group)
@@ -217,27 +256,27 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     nccl = world > 1 and dist.get_backend(group) != "gloo"
     single = need_grads and not sym and not two_pass
     T_local = backend.gemm(Xb, Wb, b_t=True, out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb   # X W, W in place
-    qmax = kmax = None
+    smp = lam = None
     sid_all = None
-    if single and world > 1 and sid_local.dtype == torch.int32:
-        # ONE small all-gather carries the study ids and the two norm maxima of the single-pass score bound
-        # (max_i |T_i|, max_k |Y_k| as raw float bits); it goes first, so the mask pre-pass runs under the big one
-        _, qm = backend.row_norm_max(T_local)
-        _, km = backend.row_norm_max(Yb)
-        bits = lambda v: v.reshape(1).to(torch.float32).view(torch.int32)
-        meta = torch.cat((sid_local.reshape(-1), bits(qm), bits(km)))
-        meta_all = _all_gather_rows(meta.reshape(1, Bl + 2), world, group)
-        sid_all = meta_all[:, :Bl].reshape(-1)
-        qmax = meta_all[:, Bl].contiguous().view(torch.float32).max().reshape(1)
-        kmax = meta_all[:, Bl + 1].contiguous().view(torch.float32).max().reshape(1)
-    elif single:                                      # largest |T_i| over ALL ranks: the global constant of the bound
-        _, qmax = backend.row_norm_max(T_local)
-        if world > 1:
-            dist.all_reduce(qmax, op=dist.ReduceOp.MAX, group=group)
+    if single:
+        # softmax references of this rank's rows from a sample of its OWN column block (needs nothing from the other ranks,
+        # so it runs before / under the all-gather of the text embeddings); lambda = the largest reference of ALL ranks
+        sid_own = sid_local if sid_local.dtype == torch.int32 else dense_labels(sid_local.to(torch.int64))
+        smp = backend.score_ref_sample(T_local, Yb, sid_own, sid_own, 0, inv_tau, not dv_like)
+        lam = smp["lam"]
+        if world > 1 and sid_local.dtype == torch.int32:
+            # ONE small all-gather carries the study ids and lambda (raw float bits); it goes first, so the mask pre-pass
+            # runs under the big one
+            meta = torch.cat((sid_local.reshape(-1), lam.reshape(1).to(torch.float32).view(torch.int32)))
+            meta_all = _all_gather_rows(meta.reshape(1, Bl + 1), world, group)
+            sid_all = meta_all[:, :Bl].reshape(-1)
+            lam = meta_all[:, Bl].contiguous().view(torch.float32).max().reshape(1)
+        elif world > 1:
+            lam = lam.clone()
+            dist.all_reduce(lam, op=dist.ReduceOp.MAX, group=group)
     Y_all, ev_y = Yb, None
-    # (experiment knob, off by default: correct on NCCL — scripts/dist_check.py — but not yet measured on 8 GPUs; at 2 GPUs
-    #  the all-gather it hides is 1 % of the step and the A/B was within the thermal drift of the box)
-    own_first = nccl and single and kmax is not None and os.environ.get("MI_OWN_COLUMNS_FIRST", "0") == "1"
+    # (experiment knob, off by default: correct on NCCL — scripts/dist_check.py)
+    own_first = nccl and single and os.environ.get("MI_OWN_COLUMNS_FIRST", "0") == "1"
     if world > 1:
         Y_all = torch.empty((Bg, D), dtype=Yb.dtype, device=Yb.device)
         if own_first:
@@ -249,7 +288,7 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
             y_work = dist.all_gather_into_tensor(Y_all, Yb, group=group, async_op=True)
         if nccl and single:
             # the compute stream does NOT wait here: the library waits for this event right before it first reads
-            # the text embeddings, after the mask pre-pass and the image-side statistics are enqueued
+            # the text embeddings, after the mask pre-pass is enqueued
             side = _side_stream(Yb.device)
             with torch.cuda.stream(side):
                 y_work.wait()
@@ -270,8 +309,17 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         # (experiment knob) SMs left free for the overlapped dY exchange; 0 = the engine uses every SM
         backend.set_overlap_reserve_sms(int(os.environ.get("MI_RS_RESERVE_SMS", "0")))
     if single:
-        return _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
-                                 precision, qmax, world, group, nccl, kmax=kmax, ev_y=ev_y, own_first=own_first)
+        try:
+            return _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off, Bl, Bg, D, inv_tau, estimator,
+                                     precision, smp, lam, world, group, nccl, ev_y=ev_y, own_first=own_first,
+                                     check_guard=check_guard)
+        except GuardTripped:
+            # every rank raised (the merged count is identical everywhere): repeat with exact references; the work the
+            # abandoned pass still has queued finishes first, in stream order
+            out, dX, dY, dW = sharded_critic_loss_fwd_bwd(X_local, Y_local, W, sid_local, estimator, precision, inv_tau,
+                                                           need_grads, group, backend, two_pass=True)
+            out["guard"] = torch.ones((), dtype=torch.float64, device=out["loss"].device)
+            return out, dX, dY, dW
 
     # ---- statistics (S never materialised)
     rows_r, scal_r = backend.score_stats(T_local, Y_all, sid_loc, sid_all, off, inv_tau)

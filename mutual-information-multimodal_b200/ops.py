@@ -95,12 +95,17 @@ _workspaces = {}
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Persistent per-device scratch, grown on demand (stream-ordered reuse inside the library)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """Persistent scratch per (device, stream), grown on demand.  The library reuses it in stream order, so a
+    buffer must never be shared between streams; a buffer that is outgrown is handed back to the caching allocator
+    with ``record_stream`` semantics (it was only ever used on its own stream).  CUDA-graph steps do NOT use this
+    cache: a captured graph bakes the pointer in, so ``GraphedCriticStep`` owns a private workspace tensor."""
+    idx = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if torch.cuda.is_current_stream_capturing():
+        raise MIError("the shared workspace cache cannot be used under CUDA-graph capture: pass workspace=")
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        _workspaces[key] = None
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=f"cuda:{key}")
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=f"cuda:{idx}")
         _workspaces[key] = buf
     return buf
 
@@ -259,7 +264,7 @@ def score_grad(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
 
 
 def row_norm_max(A: Mat) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(|A_i| per row, max_i |A_i| as a 1-element tensor) — the ingredients of the single-pass score bound."""
+    """(|A_i| per row, max_i |A_i| as a 1-element tensor)."""
     _need_cuda(A)
     At, lda, asp, D = _opnd(A)
     rows = At.shape[0]
@@ -269,13 +274,43 @@ def row_norm_max(A: Mat) -> Tuple[torch.Tensor, torch.Tensor]:
     return norms, mx
 
 
+def set_ref_sample_columns(n: int) -> None:
+    """Columns sampled per row for the single pass's references (mi_set_ref_sample_columns; default 2048)."""
+    _lib.load().mi_set_ref_sample_columns(int(n))
+
+
+def score_ref_sample(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float, include_diag: bool,
+                     col0: int = 0, n_cols: Optional[int] = None, stride: int = 0) -> dict:
+    """mi_score_ref_sample: per-row softmax references of the single pass from a strided column sample
+    (``stride`` = 1: every column, exact; 0: the library's choice).  Returns {"ref" [Bq], "diag" [Bq], "lam" [1], "stride"}."""
+    _need_cuda(Q, K, sid_q, sid_k)
+    lib = _lib.load()
+    Qt, ldq, qsp, D = _opnd(Q)
+    Kt, ldk, ksp, Dk = _opnd(K)
+    assert D == Dk
+    sid_q, sid_k = sid_q.to(torch.int32).contiguous(), sid_k.to(torch.int32).contiguous()
+    Bq, Bk = Qt.shape[0], Kt.shape[0]
+    n_cols = Bk - col0 if n_cols is None else n_cols
+    if stride < 1:
+        stride = int(lib.mi_ref_sample_stride(Bq, n_cols, D))
+    dev = Qt.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    r = {"ref": torch.empty(Bq, **f32), "diag": torch.empty(Bq, **f32), "lam": torch.empty(1, **f32), "stride": stride}
+    ws = workspace(lib.mi_score_ref_sample_workspace_bytes(Bq, n_cols, D, stride), dev)
+    _check(lib.mi_score_ref_sample(_ptr(Qt), ldq, qsp, _ptr(Kt), ldk, ksp, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D,
+                                   scale, int(include_diag), col0, n_cols, stride, _ptr(r["ref"]), _ptr(r["diag"]), _ptr(r["lam"]),
+                                   _ptr(ws), ws.numel(), _stream()), "mi_score_ref_sample")
+    return r
+
+
 def score_single_pass(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float, include_diag: bool, precision: str,
-                      inv_bg: float, qmax: Optional[torch.Tensor] = None, want_k: bool = True,
+                      inv_bg: float, ref: torch.Tensor, lam: Optional[torch.Tensor], diag: torch.Tensor, want_k: bool = True,
                       event_after_k: Optional["torch.cuda.Event"] = None,
-                      event_after_scal: Optional["torch.cuda.Event"] = None, kmax: Optional[torch.Tensor] = None,
+                      event_after_scal: Optional["torch.cuda.Event"] = None,
                       event_k_ready: Optional["torch.cuda.Event"] = None, k_local_valid: bool = False) -> dict:
-    """mi_score_single_pass: statistics and raw gradient contractions from ONE score computation."""
-    _need_cuda(Q, K, sid_q, sid_k, qmax)
+    """mi_score_single_pass: statistics and raw gradient contractions from ONE score computation, relative to the
+    per-row references ``ref`` (score_ref_sample) and the global constant ``lam`` (dv-like estimators)."""
+    _need_cuda(Q, K, sid_q, sid_k, ref, lam, diag)
     lib = _lib.load()
     Qt, ldq, qsp, D = _opnd(Q)
     Kt, ldk, ksp, Dk = _opnd(K)
@@ -287,36 +322,35 @@ def score_single_pass(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
     f32 = dict(dtype=torch.float32, device=dev)
     r = {"rows": torch.empty((Bq, 4), **f32), "scal": torch.empty(8, dtype=torch.float64, device=dev),
          "oq_raw": torch.empty((Bq, D), **f32), "ok_raw": torch.empty((Bk, D), **f32) if want_k else None,
-         "rho": torch.empty(Bq, **f32), "wrow": torch.empty(Bq, **f32), "lam": torch.empty(1, **f32),
+         "ref": ref, "wrow": torch.empty(Bq, **f32), "lam": lam,
          "flag": torch.empty(1, dtype=torch.int32, device=dev)}
     ws = workspace(lib.mi_score_single_pass_workspace_bytes(Bq, Bk, D, prec), dev)
+    ev = lambda e: None if e is None else C.c_void_p(e.cuda_event)
     _check(lib.mi_score_single_pass(_ptr(Qt), ldq, qsp, _ptr(Kt), ldk, ksp, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D,
-                                    scale, int(include_diag), prec, inv_bg, _ptr(qmax), _ptr(r["rows"]), _ptr(r["scal"]),
-                                    _ptr(r["oq_raw"]), _ptr(r["ok_raw"]), _ptr(r["rho"]), _ptr(r["wrow"]), _ptr(r["lam"]),
-                                    _ptr(r["flag"]),
-                                    None if event_after_k is None else C.c_void_p(event_after_k.cuda_event),
-                                    None if event_after_scal is None else C.c_void_p(event_after_scal.cuda_event),
-                                    _ptr(kmax), None if event_k_ready is None else C.c_void_p(event_k_ready.cuda_event),
+                                    scale, int(include_diag), prec, inv_bg, _ptr(ref), _ptr(lam), _ptr(diag),
+                                    _ptr(r["rows"]), _ptr(r["scal"]), _ptr(r["oq_raw"]), _ptr(r["ok_raw"]), _ptr(r["wrow"]),
+                                    _ptr(r["flag"]), ev(event_after_k), ev(event_after_scal), ev(event_k_ready),
                                     int(k_local_valid), _ptr(ws), ws.numel(), _stream()), "mi_score_single_pass")
     return r
 
 
-def merge_scalars_loss(scal_all: torch.Tensor, estimator: str, b_global: int) -> dict:
+def merge_scalars_loss(scal_all: torch.Tensor, estimator: str, b_global: int, lam: Optional[torch.Tensor] = None) -> dict:
     """Ranks' reduced scalars [world, 8] (fp64) -> the global loss terms as 0-d fp64 views plus the global
-    log-sum-exp as a 1-element fp32 tensor (mi_merge_scalars: two tiny kernels, no host sync)."""
+    log-sum-exp as a 1-element fp32 tensor (mi_merge_scalars: two tiny kernels, no host sync).  "guard" = the ranks'
+    guard counts summed (+1 when e^{lam - lse} would leave the fp32 range): must be 0, else repeat with exact references."""
     _need_cuda(scal_all)
     scal_all = scal_all.contiguous()
     dev = scal_all.device
     out = torch.empty(8, dtype=torch.float64, device=dev)
     scratch = torch.empty(8, dtype=torch.float64, device=dev)
     lse32 = torch.empty(1, dtype=torch.float32, device=dev)
-    _check(_lib.load().mi_merge_scalars(_ptr(scal_all), scal_all.shape[0], b_global, ESTIMATOR[estimator], _ptr(out), _ptr(lse32),
-                                        _ptr(scratch), _stream()), "mi_merge_scalars")
+    _check(_lib.load().mi_merge_scalars(_ptr(scal_all), scal_all.shape[0], b_global, ESTIMATOR[estimator], _ptr(lam), _ptr(out),
+                                        _ptr(lse32), _ptr(scratch), _stream()), "mi_merge_scalars")
     return {"loss": out[0], "pos_mean": out[1], "lse_neg": out[2], "n_neg": out[3], "loss_row": out[4],
-            "rows_without_negatives": out[6], "lse32": lse32}
+            "rows_without_negatives": out[6], "guard": out[7], "lse32": lse32}
 
 
-def single_finalize_q(oq_raw, rho, wrow, lse, dv_like: bool, alpha: float, gamma: float, kdiag: Mat,
+def single_finalize_q(oq_raw, ref, wrow, lse, dv_like: bool, alpha: float, gamma: float, kdiag: Mat,
                       want_f32: bool = True, want_bf16: bool = False, out_split: bool = False):
     """Oq = alpha (c_q oq_raw - gamma Kdiag): fp32 and/or bf16 (hi/lo) result."""
     Kt, ldk, ksp, D = _opnd(kdiag)
@@ -332,7 +366,7 @@ def single_finalize_q(oq_raw, rho, wrow, lse, dv_like: bool, alpha: float, gamma
         else:
             o16 = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
             ob, ld16 = o16, D
-    _check(_lib.load().mi_single_finalize_q(_ptr(oq_raw), rows, D, _ptr(rho), _ptr(wrow), _ptr(lse), int(dv_like), alpha, gamma,
+    _check(_lib.load().mi_single_finalize_q(_ptr(oq_raw), rows, D, _ptr(ref), _ptr(wrow), _ptr(lse), int(dv_like), alpha, gamma,
                                             _ptr(Kt), ldk, ksp, _ptr(o32), _ptr(ob), ld16, 2 if out_split else 1, _stream()),
            "mi_single_finalize_q")
     return o32, o16
@@ -348,12 +382,13 @@ def single_finalize_k(ok, lam, lse, dv_like: bool, alpha: float, gamma: float, q
 
 def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tensor], sid: torch.Tensor,
                         estimator: str = "dv", precision: str = "fast", inv_tau: float = 1.0,
-                        need_grads: bool = True, out=None, two_pass: bool = False):
+                        need_grads: bool = True, out=None, two_pass: bool = False, workspace_buf: Optional[torch.Tensor] = None):
     """The whole path on one GPU (mi_critic_loss_fwd_bwd).  Returns (loss_out fp64[8], dX, dY, dW).
     ``out`` = (loss, dX, dY, dW) reuses caller-owned result buffers (no allocation in the call).
-    ``two_pass`` forces the statistics-pass + gradient-pass path (MI_PREC_TWO_PASS); by default dv / infonce /
-    infonce_row take the single pass with a Cauchy-Schwarz score bound as reference — loss_out[7] counts the
-    rows for which that bound was too loose (must be 0, else repeat with two_pass=True)."""
+    dv / infonce / infonce_row take the single pass with sampled softmax references; if a row's reference leaves the
+    numerically safe window the library itself repeats the step with exact references (device-side predicate, no host
+    sync) — loss_out[7] counts the rows that tripped (informational).  ``two_pass`` asks for exact references from the
+    start (MI_PREC_TWO_PASS).  ``workspace_buf``: caller-owned scratch of ``critic_workspace_bytes`` (CUDA graphs)."""
     _need_cuda(X, Y, W, sid)
     lib = _lib.load()
     X, Y = as_bf16(X), as_bf16(Y)
@@ -373,7 +408,9 @@ def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tens
         if W is not None:
             dW = torch.empty((D, D), dtype=torch.float32, device=X.device)
     nbytes = lib.mi_critic_workspace_bytes(B, D, critic, est, prec, int(need_grads))
-    ws = workspace(nbytes, X.device)
+    ws = workspace(nbytes, X.device) if workspace_buf is None else workspace_buf
+    if ws.numel() < nbytes:
+        raise MIError(f"workspace_buf too small: {ws.numel()} < {nbytes} bytes")
     _check(lib.mi_critic_loss_fwd_bwd(_ptr(X), _ptr(Y), _ptr(W), _ptr(sid), B, D, critic, est, prec, inv_tau,
                                       _ptr(loss), _ptr(dX), _ptr(dY), _ptr(dW), _ptr(ws), ws.numel(), _stream()),
            "mi_critic_loss_fwd_bwd")
@@ -395,11 +432,14 @@ class GraphedCriticStep:
         self.sid = torch.arange(B, dtype=torch.int32, device=dev)
         self.out = (torch.empty(8, dtype=torch.float64, device=dev), torch.empty((B, D), device=dev),
                     torch.empty((B, D), device=dev), torch.empty((D, D), device=dev) if bilinear else None)
+        # the captured graph bakes the scratch pointer in: a PRIVATE workspace that lives as long as the graph does
+        nbytes = _lib.load().mi_critic_workspace_bytes(B, D, 1 if bilinear else 0, ESTIMATOR[estimator], PRECISION[precision], 1)
+        self.ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
         self.graph = None
 
     def _run(self):
         est, prec, inv_tau = self.args
-        critic_loss_fwd_bwd(self.X, self.Y, self.W, self.sid, est, prec, inv_tau, True, out=self.out)
+        critic_loss_fwd_bwd(self.X, self.Y, self.W, self.sid, est, prec, inv_tau, True, out=self.out, workspace_buf=self.ws)
 
     def __call__(self, X, Y, W, sid):
         """Returns (loss_out fp64[8], dX, dY, dW) — static buffers, overwritten by the next call."""

@@ -71,42 +71,61 @@ def row_norm_max(A):
     return n, n.max().reshape(1)
 
 
-def score_single_pass(Q, K, sid_q, sid_k, q_offset, scale, include_diag, precision, inv_bg, qmax=None, want_k=True,
-                      event_after_k=None, event_after_scal=None, kmax=None, event_k_ready=None, k_local_valid=False):
+REF_STRIDE = 1      # tests set this to exercise the sampled references (the library picks its own stride)
+
+
+def score_ref_sample(Q, K, sid_q, sid_k, q_offset, scale, include_diag, col0=0, n_cols=None, stride=0):
     S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
-    qn, kn = Q.double().norm(dim=1), K.double().norm(dim=1)
-    kmx = kn.max() if kmax is None else kmax.double().reshape(())
-    rho = scale * qn * kmx * 1.001 + 1e-3
-    lam = (scale * (qn.max() if qmax is None else qmax.double().reshape(())) * kmx * 1.001 + 1e-3).reshape(1)
+    n_cols = K.shape[0] - col0 if n_cols is None else n_cols
+    stride = REF_STRIDE if stride < 1 else stride
+    cols = torch.arange(col0, col0 + n_cols, stride)
+    lse = torch.logsumexp(torch.where(M[:, cols], S[:, cols], torch.full_like(S[:, cols], float("-inf"))), 1)
+    diag = S[i, j]
+    ref = torch.logaddexp(lse, diag) if include_diag else torch.where(torch.isfinite(lse), lse, diag)
+    if stride > 1:
+        ref = ref + 24.0                                  # kRefMargin of the library
+    return {"ref": ref, "diag": diag, "lam": ref.max().reshape(1), "stride": stride}
+
+
+def score_single_pass(Q, K, sid_q, sid_k, q_offset, scale, include_diag, precision, inv_bg, ref, lam, diag, want_k=True,
+                      event_after_k=None, event_after_scal=None, event_k_ready=None, k_local_valid=False):
+    S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
+    ref = ref.double()
     incl = M.clone()
     if include_diag:
         incl[i, j] = True
-    P = torch.where(incl, torch.exp(S - rho[:, None]), torch.zeros_like(S))
+    P = torch.where(incl, torch.exp(S - ref[:, None]), torch.zeros_like(S))
     l = P.sum(1)
-    diag = S[i, j]
     n_neg = M.sum(1).double()
+    n_incl = n_neg + (1.0 if include_diag else 0.0)
+    bad = (n_incl > 0) & ~((l >= 1e-30) & (l <= 1e30))              # the fp32 window of the kernel's row sums
     if include_diag:
-        lse_all = rho + torch.log(l)
+        lse_all = ref + torch.log(l)
         lse_neg = torch.logsumexp(torch.where(M, S, torch.full_like(S, float("-inf"))), 1)
         wrow = inv_bg / l
     else:
-        lse_neg = rho + torch.log(l)
-        lse_all = torch.logaddexp(lse_neg, diag)
-        wrow = torch.exp(rho - lam)
-    rows = torch.stack([lse_neg, n_neg, diag, lse_all], 1)
-    m = lse_neg.max()
+        lse_neg = ref + torch.log(l)
+        lse_all = torch.logaddexp(lse_neg, diag.double())
+        d = ref - lam.double().reshape(())
+        wrow = torch.exp(d)
+        bad = bad | ~(d <= 60.0)
+    rows = torch.stack([lse_neg, n_neg, diag.double(), lse_all], 1)
+    fin = torch.isfinite(lse_neg)
+    m = lse_neg[fin].max() if fin.any() else torch.tensor(float("-inf"), dtype=torch.float64)
     scal = torch.zeros(8, dtype=torch.float64)
     scal[0] = m
-    scal[1] = torch.exp(lse_neg[torch.isfinite(lse_neg)] - m).sum()
+    scal[1] = torch.exp(lse_neg[fin] - m).sum()
     scal[2] = n_neg.sum()
-    scal[3] = diag.sum()
-    scal[4] = (lse_all - diag).sum()
+    scal[3] = diag.double().sum()
+    scal[4] = (lse_all - diag.double()).sum()
+    scal[5] = (n_neg == 0).sum()
+    scal[6] = bad.sum()
     return {"rows": rows, "scal": scal, "oq_raw": P @ K.double(), "ok_raw": (P * wrow[:, None]).t() @ Q.double(),
-            "rho": rho, "wrow": wrow, "lam": lam, "flag": torch.zeros(1, dtype=torch.int32)}
+            "ref": ref, "wrow": wrow, "lam": lam, "flag": bad.sum().to(torch.int32).reshape(1)}
 
 
-def single_finalize_q(oq_raw, rho, wrow, lse, dv_like, alpha, gamma, kdiag, want_f32=True, want_bf16=False, out_split=False):
-    c = torch.exp(rho - lse.double()) if dv_like else wrow
+def single_finalize_q(oq_raw, ref, wrow, lse, dv_like, alpha, gamma, kdiag, want_f32=True, want_bf16=False, out_split=False):
+    c = torch.exp(ref.double() - lse.double()) if dv_like else wrow
     O = alpha * (c[:, None] * oq_raw - gamma * kdiag.double())
     return (O if want_f32 else None), (O if want_bf16 else None)
 

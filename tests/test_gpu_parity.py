@@ -4,7 +4,9 @@ same seeded bf16-rounded inputs, (c) size-independent properties at the BASELINE
 
 Tolerances (north star): strict ("fp32-accumulate") mode — loss 1e-4 relative, gradients 1e-3
 relative max-norm; fast mode (single bf16 rounding of T and of the dS panel) — loss 2e-3,
-gradients 1e-2."""
+gradients 1e-2.  The loss bound is TRUE relative error plus an explicit absolute term of 1e-6 x the magnitude of
+the terms the loss is a difference of (|mean positive score| + |log-sum-exp|): the row statistics are fp32, so a
+loss that happens to cancel to ~0 cannot be resolved below that (see _loss_ok)."""
 import ctypes
 import glob
 import math
@@ -41,10 +43,18 @@ def _rel(a, ref):
     return float((a.detach().cpu().double() - ref.double()).abs().max() / ref.double().abs().max().clamp_min(1e-30))
 
 
+def _loss_ok(a, ref, rel):
+    """|a - loss| <= rel * |loss| + 1e-6 * (|pos_mean| + |loss + pos_mean|): true relative error, plus the fp32 resolution of
+    the two terms (mean positive score, log-sum-exp) whose difference the loss is.  ``ref`` is an oracle result dict."""
+    loss, pos = float(ref["loss"]), float(ref["pos_mean"])
+    bound = rel * abs(loss) + 1e-6 * (abs(pos) + abs(loss + pos))
+    err = abs(float(a) - loss)
+    assert err <= bound, f"loss {float(a)!r} vs oracle {loss!r}: |err| {err:.3e} > {bound:.3e}"
+
+
 def _loss_rel(a, ref):
-    # relative, with a floor so that losses that happen to sit near zero are judged on the scale of
-    # the terms they are made of (|lse| + |pos| >= O(1))
-    return abs(float(a) - float(ref)) / max(abs(float(ref)), 1.0)
+    """plain relative error against a non-oracle value (another code path's loss)"""
+    return abs(float(a) - float(ref)) / max(abs(float(ref)), 1e-30)
 
 
 def _run_adapter(mi_b200, dev, X, Y, W, study_id, inv_tau, est, precision):
@@ -74,7 +84,9 @@ def test_golden_vectors_from_the_reference(env, path):
     loss, dX, dY, dW = _run_adapter(mi_b200, dev, X, Y, W, sid, float(z["inv_tau"]), est, "strict")
     assert tuple(loss.shape) == tuple(z["loss_shape"])               # [1] for dv, [] for infonce
     lt, gt = TOL["strict"]
-    assert _loss_rel(loss.sum().item(), z["loss"].reshape(-1)[0]) < lt
+    B = X.shape[0]
+    pos_mean = float(np.asarray(z["logits"], dtype=np.float64).reshape(-1)[:B].mean())   # the reference's own positive logits
+    _loss_ok(loss.sum().item(), {"loss": z["loss"].reshape(-1)[0], "pos_mean": pos_mean}, lt)
     assert _rel(dX, torch.from_numpy(z["dX"])) < gt
     assert _rel(dY, torch.from_numpy(z["dY"])) < gt
     if W is not None:
@@ -106,11 +118,29 @@ def test_oracle_parity(env, B, D, critic, est, dup, precision):
     ref = mo.critic_loss(Xb, Yb, sid, Wb, inv_tau, est)
     loss, dX, dY, dW = _run_adapter(mi_b200, dev, Xb, Yb, Wb, [int(s) for s in sid], inv_tau, est, precision)
     lt, gt = TOL[precision]
-    assert _loss_rel(loss.sum().item(), ref["loss"]) < lt
+    _loss_ok(loss.sum().item(), ref, lt)
     assert _rel(dX, ref["dX"]) < gt
     assert _rel(dY, ref["dY"]) < gt
     if W is not None:
         assert _rel(dW, ref["dW"]) < gt
+
+
+@pytest.mark.parametrize("precision", ["strict", "fast"])
+@pytest.mark.parametrize("est", ["infonce", "infonce_sym", "infonce_row", "dv"])
+def test_baseline_config2_exact(env, est, precision):
+    """BASELINE.json configs[1] at its stated size: bilinear critic + InfoNCE, B = 4096, D = 768, bf16 embeddings,
+    against the fp64 matrix oracle on the same rounded inputs (all four estimators; 5 % duplicated study ids)."""
+    mi_b200, ops, mo, dev = env
+    B, D = 4096, 768
+    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=2, dup_frac=0.05, bilinear=True)
+    Xb, Yb, Wb = X.bfloat16().float(), Y.bfloat16().float(), W.bfloat16().float()
+    ref = mo.critic_loss(Xb, Yb, sid, Wb, 1.0, est)
+    out, dX, dY, dW = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), Wb.to(dev), sid.to(dev), est, precision, 1.0, True)
+    torch.cuda.synchronize()
+    lt, gt = TOL[precision]
+    _loss_ok(out[0].item(), ref, lt)
+    assert float(out[3]) == float(ref["n_neg"]) and float(out[7]) == 0.0
+    assert _rel(dX, ref["dX"]) < gt and _rel(dY, ref["dY"]) < gt and _rel(dW, ref["dW"]) < gt
 
 
 def test_peaked_softmax_strict(env):
@@ -124,7 +154,7 @@ def test_peaked_softmax_strict(env):
     for est in ("dv", "infonce_sym"):
         ref = mo.critic_loss(Xb, Yb, sid, None, inv_tau, est)
         loss, dX, dY, _ = _run_adapter(mi_b200, dev, Xb, Yb, None, [int(s) for s in sid], inv_tau, est, "strict")
-        assert _loss_rel(loss.sum().item(), ref["loss"]) < 1e-4
+        _loss_ok(loss.sum().item(), ref, 1e-4)
         assert _rel(dX, ref["dX"]) < 1e-3 and _rel(dY, ref["dY"]) < 1e-3
 
 
@@ -148,13 +178,15 @@ def test_edge_cases(env):
     X, Y = torch.randn(2, D).bfloat16().float(), torch.randn(2, D).bfloat16().float()
     ref = mo.critic_loss(X, Y, torch.tensor([0, 1]), None, 0.25, "dv")
     loss, dX, dY, _ = _run_adapter(mi_b200, dev, X, Y, None, ["a", "b"], 0.25, "dv", "strict")
-    assert _loss_rel(loss.item(), ref["loss"]) < 1e-4 and _rel(dX, ref["dX"]) < 1e-3
+    _loss_ok(loss.item(), ref, 1e-4)
+    assert _rel(dX, ref["dX"]) < 1e-3
     # forward only (no_grad): loss still right, nothing saved
     with torch.no_grad():
         l2 = mi_b200.infonce_bound_loss(mi_b200.FusedCritic(D, "dot", temperature=4.0).to(dev)(
             mi_b200.create_mi_pairs(X.to(dev), Y.to(dev), ["a", "b"], dev)), 2, dev)
     ref2 = mo.critic_loss(X, Y, torch.tensor([0, 1]), None, 0.25, "infonce", grads=False)
-    assert l2.shape == () and _loss_rel(l2.item(), ref2["loss"]) < 1e-4
+    assert l2.shape == ()
+    _loss_ok(l2.item(), ref2, 1e-4)
 
 
 def test_stage_ops_with_offsets(env):
@@ -199,31 +231,136 @@ def test_sharded_composition_world1_equals_fused_call(env):
             assert float(lo[7]) == 0.0 and abs(float(out["loss"]) - float(lo[0])) < 1e-6 * max(1.0, abs(float(lo[0])))
             for a, b in ((dX, fX), (dY, fY), (dW, fW)):
                 assert _rel(a, b.cpu()) < 1e-4
-            assert _loss_rel(out["loss"], ref[est]["loss"]) < 1e-4
+            _loss_ok(out["loss"], ref[est], 1e-4)
             assert _rel(dX, ref[est]["dX"]) < 1e-3 and _rel(dY, ref[est]["dY"]) < 1e-3 and _rel(dW, ref[est]["dW"]) < 1e-3
 
 
-def test_single_pass_reference_guard(env):
-    """Rows whose Cauchy-Schwarz bound is far above all of their scores (here: an image embedding that is
-    orthogonal to every text embedding but has a huge norm) must be reported (loss_out[7] > 0) and the adapter
-    must fall back to the exact two-pass path."""
-    mi_b200, ops, mo, dev = env
-    B, D = 256, 64
-    g = torch.Generator().manual_seed(3)
-    Y = torch.zeros(B, D)
-    Y[:, : D // 2] = torch.randn(B, D // 2, generator=g)
-    X = torch.zeros(B, D)
-    X[:, : D // 2] = torch.randn(B, D // 2, generator=g)
-    X[7, :] = 0.0
-    X[7, D // 2:] = 40.0                                  # |X_7| large, <X_7, Y_j> = 0 for all j: bound ~ 1e3, scores 0
+def _guard_case(mo, B, D, seed, planted):
+    """Embeddings whose row 7 has one score hundreds of nats above every SAMPLED column of the row (the planted column 5 is
+    not a multiple of the sample stride) — the single pass's sampled reference must trip its guard there."""
+    X, Y, sid, _ = mo.synthetic_embeddings(B, D, seed=seed, dup_frac=0.05, bilinear=False)
     Xb, Yb = X.bfloat16().float(), Y.bfloat16().float()
-    sid = torch.arange(B)
-    out, *_ = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), None, sid.to(dev), "dv", "strict", 1.0, True)
-    assert float(out[7]) >= 1.0
-    ref = mo.critic_loss(Xb, Yb, sid, None, 1.0, "dv")
-    loss, dX, dY, _ = _run_adapter(mi_b200, dev, Xb, Yb, None, list(range(B)), 1.0, "dv", "strict")
-    assert _loss_rel(loss.sum().item(), ref["loss"]) < 1e-4
+    if planted:
+        Yb[7] = -Yb[5]                                       # (its own positive pair far BELOW: the reference cannot lean on it)
+        Xb[7] = (100.0 * Yb[5]).bfloat16().float()
+    return Xb, Yb, sid
+
+
+@pytest.mark.parametrize("est", ["dv", "infonce_row"])
+def test_single_pass_guard_falls_back_inside_the_library(env, est):
+    """a tripped guard must never yield a silently wrong result.  The sampled single pass is forced
+    (64 sampled columns of 1024: stride 16) on data with a planted outlier: loss_out[7] reports the tripped row AND the
+    results equal the oracle, because the library repeats the step with exact references behind a device predicate —
+    through the device-pointer ABI, the adapter (no host check involved) and the host-buffer ABI alike."""
+    mi_b200, ops, mo, dev = env
+    from mi_b200 import _lib
+    lib = _lib.load()
+    B, D, inv_tau = 1024, 64, 0.125
+    ops.set_ref_sample_columns(64)
+    try:
+        for planted in (False, True):
+            Xb, Yb, sid = _guard_case(mo, B, D, 3, planted)
+            ref = mo.critic_loss(Xb, Yb, sid, None, inv_tau, est)
+            out, dX, dY, _ = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), None, sid.to(dev), est, "strict", inv_tau, True)
+            torch.cuda.synchronize()
+            assert (float(out[7]) >= 1.0) == planted, float(out[7])
+            _loss_ok(out[0].item(), ref, 1e-4)
+            assert _rel(dX, ref["dX"]) < 1e-3 and _rel(dY, ref["dY"]) < 1e-3
+            # adapter: check_negatives=False means NO host read at all — the fallback is the library's
+            x = Xb.to(dev).requires_grad_(True); y = Yb.to(dev).requires_grad_(True)
+            critic = mi_b200.FusedCritic(D, "dot", temperature=1.0 / inv_tau, precision="strict", check_negatives=False).to(dev)
+            loss = mi_b200.select_estimator(est)(critic(mi_b200.create_mi_pairs(x, y, [int(v) for v in sid], dev)), B, dev)
+            loss.sum().backward()
+            _loss_ok(loss.sum().item(), ref, 1e-4)
+            assert _rel(x.grad, ref["dX"]) < 1e-3 and _rel(y.grad, ref["dY"]) < 1e-3
+            # host-buffer ABI: the repeat is decided on the host before the call returns
+            n = lib.mi_critic_host_scratch_bytes(B, D, 0, ops.ESTIMATOR[est], 1, 1)
+            scratch = torch.empty(n, dtype=torch.uint8, device=dev)
+            lh = torch.zeros(8, dtype=torch.float64)
+            hX, hY = torch.zeros(B, D), torch.zeros(B, D)
+            p = lambda t: ctypes.c_void_p(t.data_ptr())
+            sh = sid.to(torch.int32).contiguous()
+            st = lib.mi_critic_loss_fwd_bwd_host(p(Xb.contiguous()), p(Yb.contiguous()), None, p(sh), B, D, 0, ops.ESTIMATOR[est], 1,
+                                                 inv_tau, p(lh), p(hX), p(hY), None, p(scratch), n,
+                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert st == 0, lib.mi_status_string(st)
+            assert (float(lh[7]) >= 1.0) == planted
+            _loss_ok(lh[0].item(), ref, 1e-4)
+            assert _rel(hX, ref["dX"]) < 1e-3 and _rel(hY, ref["dY"]) < 1e-3
+    finally:
+        ops.set_ref_sample_columns(2048)
+
+
+def test_sampled_references_on_hostile_scales(env):
+    """The cases the round-1 Cauchy-Schwarz bound could not handle stay on the single pass with a
+    clear guard: (a) a huge-norm image row orthogonal to every text embedding (bound ~1e3 above its scores), (b) scores
+    x 8 (a nearly one-hot softmax), (c) unnormalised embeddings with W = I + noise at inv_tau = 1 (scores of +-100)."""
+    mi_b200, ops, mo, dev = env
+    ops.set_ref_sample_columns(128)            # stride 16 at B = 2048: the sampled path, not the exact one
+    try:
+        B, D = 2048, 64
+        g = torch.Generator().manual_seed(3)
+        Y = torch.zeros(B, D); Y[:, : D // 2] = torch.randn(B, D // 2, generator=g)
+        X = torch.zeros(B, D); X[:, : D // 2] = torch.randn(B, D // 2, generator=g)
+        X[7, :] = 0.0; X[7, D // 2:] = 40.0
+        cases = [("orthogonal huge-norm row", X.bfloat16().float(), Y.bfloat16().float(), None, 1.0)]
+        X2, Y2, sid2, W2 = mo.synthetic_embeddings(B, D, seed=5, dup_frac=0.05, bilinear=True)
+        cases.append(("scores x 8", X2.bfloat16().float(), Y2.bfloat16().float(), (8.0 * W2).bfloat16().float(), 1.0))
+        Wn = (torch.eye(D) + 0.1 * torch.randn(D, D, generator=g) / math.sqrt(D)).bfloat16().float()
+        cases.append(("unnormalised, inv_tau = 1", (4.0 * X2).bfloat16().float(), (4.0 * Y2).bfloat16().float(), Wn, 1.0))
+        for name, Xb, Yb, Wb, inv_tau in cases:
+            sid = torch.arange(B)
+            for est in ("dv", "infonce_row"):
+                ref = mo.critic_loss(Xb, Yb, sid, Wb, inv_tau, est)
+                out, dX, dY, dW = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), None if Wb is None else Wb.to(dev), sid.to(dev),
+                                                          est, "strict", inv_tau, True)
+                torch.cuda.synchronize()
+                assert float(out[7]) == 0.0, (name, est, float(out[7]))
+                _loss_ok(out[0].item(), ref, 1e-4)
+                assert _rel(dX, ref["dX"]) < 1e-3 and _rel(dY, ref["dY"]) < 1e-3, (name, est)
+    finally:
+        ops.set_ref_sample_columns(2048)
+
+
+def test_any_int32_study_id_is_legal(env):
+    """INT_MIN used to be the hash table's empty-slot sentinel.  Ids INT_MIN, -2 (the old pad value), -1, 0 and
+    INT_MAX, some of them duplicated, must give the same mask as the oracle's."""
+    mi_b200, ops, mo, dev = env
+    B, D = 300, 32
+    X, Y, _, _ = mo.synthetic_embeddings(B, D, seed=6, dup_frac=0.0, bilinear=False)
+    Xb, Yb = X.bfloat16().float(), Y.bfloat16().float()
+    sid = torch.arange(B, dtype=torch.int64) * 7919 - 1000
+    special = [-(2 ** 31), -2, -1, 0, 2 ** 31 - 1]
+    for k, v in enumerate(special):
+        sid[10 * k] = v
+        sid[10 * k + 3] = v                                   # a duplicate of each special id
+    ref = mo.critic_loss(Xb, Yb, sid, None, 0.2, "dv")
+    out, dX, dY, _ = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), None, sid.to(torch.int32).to(dev), "dv", "strict", 0.2, True)
+    torch.cuda.synchronize()
+    assert float(out[3]) == float(ref["n_neg"])
+    _loss_ok(out[0].item(), ref, 1e-4)
     assert _rel(dX, ref["dX"]) < 1e-3 and _rel(dY, ref["dY"]) < 1e-3
+
+
+def test_fp32_inputs_that_are_not_bf16_representable(env):
+    """'strict' is fp32 ACCUMULATION of bf16 operands — fp32 embeddings are rounded to bf16 once on entry (the
+    north star quotes its 1e-4 / 1e-3 bounds on identical bf16-rounded inputs and asks for 'a separately stated looser bound
+    for bf16 inputs').  Against the fp32-input oracle the stated bound is loss 5e-3, gradients 3e-2 (measured: see
+    profiles/); against the oracle on the rounded inputs the strict bounds hold as everywhere else."""
+    mi_b200, ops, mo, dev = env
+    B, D = 1024, 256
+    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=31, dup_frac=0.05, bilinear=True)     # fp32, NOT rounded
+    for est in ("dv", "infonce_sym"):
+        raw = mo.critic_loss(X, Y, sid, W, 1.0, est)
+        rnd = mo.critic_loss(X.bfloat16().float(), Y.bfloat16().float(), sid, W.bfloat16().float(), 1.0, est)
+        out, dX, dY, dW = ops.critic_loss_fwd_bwd(X.to(dev), Y.to(dev), W.to(dev), sid.to(dev), est, "strict", 1.0, True)
+        torch.cuda.synchronize()
+        _loss_ok(out[0].item(), rnd, 1e-4)
+        assert max(_rel(dX, rnd["dX"]), _rel(dY, rnd["dY"]), _rel(dW, rnd["dW"])) < 1e-3
+        e_loss = abs(float(out[0]) - float(raw["loss"])) / abs(float(raw["loss"]))
+        e_grad = max(_rel(dX, raw["dX"]), _rel(dY, raw["dY"]), _rel(dW, raw["dW"]))
+        print(f"fp32-input oracle, {est}: loss rel {e_loss:.2e}, grad rel-max {e_grad:.2e}")
+        assert e_loss < 5e-3 and e_grad < 3e-2
 
 
 def test_sharded_autograd_loss_world1(env):
@@ -266,7 +403,7 @@ def test_host_buffer_abi_matches_device_call(env):
                                          p(scratch), n, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert st == 0, lib.mi_status_string(st)
     ref = mo.critic_loss(Xh, Yh, sid, Wh, 1.0, "dv")
-    assert _loss_rel(loss[0], ref["loss"]) < 1e-4
+    _loss_ok(loss[0], ref, 1e-4)
     assert _rel(dX, ref["dX"]) < 1e-3 and _rel(dY, ref["dY"]) < 1e-3 and _rel(dW, ref["dW"]) < 1e-3
 
 
@@ -306,55 +443,123 @@ def test_host_buffer_abi_streams_panels(env, critic):
             assert _rel(dW, rW.cpu()) < tol
 
 
-@pytest.mark.parametrize("critic", ["dot", "bilinear"])
-def test_full_size_properties(env, critic):
-    """B = 65536, D = 1024 (the BASELINE metric's size): the CPU oracle cannot form the 4.3e9 pairs,
-    so parity is checked through (1) sampled rows / columns recomputed exactly on the CPU in fp64
-    from the kernel's own global statistics, (2) Euler-type identities that tie the independently
-    computed passes together: <dT,T> = <dY,Y> = <dW,W> (all equal sum(G * S))."""
+_FULL = {}
+
+
+def _full_size_case(mo, dev, critic):
+    """B = 65536, D = 1024 inputs (BASELINE metric size) on the device, generated once per module."""
+    if critic not in _FULL:
+        B, D = 65536, 1024
+        X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=1234, dup_frac=0.05, bilinear=(critic == "bilinear"))
+        _FULL[critic] = (X.bfloat16().to(dev), Y.bfloat16().to(dev), None if W is None else W.bfloat16().to(dev), sid.to(dev),
+                         {})
+    return _FULL[critic]
+
+
+FULL_CASES = [("bilinear", "dv", "fast"), ("bilinear", "dv", "strict"), ("bilinear", "infonce_sym", "fast"),
+              ("bilinear", "infonce_sym", "strict"), ("dot", "dv", "fast"), ("bilinear", "infonce_row", "fast")]
+
+
+@pytest.mark.parametrize("critic,est,precision", FULL_CASES, ids=["-".join(c) for c in FULL_CASES])
+def test_full_size_parity(env, critic, est, precision):
+    """BASELINE configs[2] at full size (B = 65536, D = 1024; dv AND symmetric InfoNCE, strict AND fast): EVERY element of
+    dX, dY and dW and the loss against oracle.chunked_oracle — the row-chunked plain-PyTorch restatement (fp32 matmuls, TF32
+    off, fp64 reductions) run on the same device, pinned to the matrix oracle / the reference's golden vectors on the CPU
+    (tests/test_oracle.py).  The oracle is given the path's own bf16 T = X W so that the comparison isolates the B^2-sized
+    work; T itself is checked against fp32 X W separately.  Identities between the passes as a second, oracle-free check."""
     mi_b200, ops, mo, dev = env
+    from oracle import chunked_oracle as co
     B, D = 65536, 1024
-    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=1234, dup_frac=0.05, bilinear=(critic == "bilinear"))
-    Xb, Yb = X.bfloat16(), Y.bfloat16()
-    Wb = None if W is None else W.bfloat16()
+    Xd, Yd, Wd, sd, cache = _full_size_case(mo, dev, critic)
     inv_tau = 1.0 / math.sqrt(D) if critic == "dot" else 1.0
-    out, dX, dY, dW = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), None if Wb is None else Wb.to(dev), sid.to(dev),
-                                              "dv", "fast", inv_tau, True)
+    T = None
+    if Wd is not None:
+        strict = precision == "strict"
+        Tm = ops.gemm(Xd, Wd, b_t=True, out_dtype=torch.bfloat16, out_split=strict)      # the path's projection
+        T = Tm.float() if strict else Tm.float()
+        T32 = Xd.float() @ Wd.float()
+        assert float((T - T32).abs().max() / T32.abs().max()) < (1e-4 if strict else 6e-3)
+    key = (est, precision if Wd is not None else "-")
+    if key not in cache:
+        cache.clear()                                        # one oracle result at a time (each holds 3 x 268 MB)
+        cache[key] = co.critic_loss_chunked(Xd.float(), Yd.float(), sd, None if Wd is None else Wd.float(), inv_tau, est,
+                                            chunk=4096, T=T)
+    ref = cache[key]
+    out, dX, dY, dW = ops.critic_loss_fwd_bwd(Xd, Yd, Wd, sd, est, precision, inv_tau, True)
     torch.cuda.synchronize()
-    out = out.cpu()
-    lse, n_neg, pos = float(out[2]), float(out[3]), float(out[1])
-    # exact N_neg from the study ids alone
-    _, counts = torch.unique(sid, return_counts=True)
-    assert n_neg == float(B) * B - float((counts.double() ** 2).sum())
-    assert abs(float(out[0]) - (lse - math.log(np.float32(n_neg)) - pos)) < 1e-9
-    # (1) sampled rows: S_i,: in fp64 on the CPU, row statistics and dT_i from the global LSE
-    Xd, Yd = Xb.double(), Yb.double()
-    T = Xd if Wb is None else (Xb.float() @ Wb.float()).bfloat16().double()      # the path's own bf16 T
-    rows = torch.tensor([0, 1, 4097, 33333, 65535])
-    S = (T[rows] @ Yd.t()) * inv_tau
-    M = sid[rows][:, None] != sid[None, :]
-    G = torch.where(M, torch.exp(S - lse), torch.zeros_like(S))
-    dT_ref = inv_tau * (G @ Yd - Yd[rows] / B)
-    if Wb is None:
-        assert _rel(dX[rows], dT_ref) < 1e-2
-    cols = torch.tensor([5, 4096, 65000])
-    Sc = (T @ Yd[cols].t()) * inv_tau
-    Mc = sid[:, None] != sid[cols][None, :]
-    Gc = torch.where(Mc, torch.exp(Sc - lse), torch.zeros_like(Sc))
-    dY_ref = inv_tau * (Gc.t() @ T - T[cols] / B)
-    assert _rel(dY[cols], dY_ref) < 1e-2
-    pos_ref = float(((T * Yd).sum(1) * inv_tau).mean())
-    assert abs(pos - pos_ref) < 1e-4 * max(1.0, abs(pos_ref))
-    # (2) identities between the passes
-    a = float((dY.double().cpu() * Yd).sum())
-    if Wb is None:
-        b = float((dX.double().cpu() * Xd).sum())
-        assert abs(a - b) < 2e-3 * max(abs(a), abs(b), 1e-3)
-    else:
-        c = float((dW.double().cpu() * Wb.double()).sum())
-        d = float((dX.double().cpu() * Xd).sum())
+    lt, gt = TOL[precision]
+    assert float(out[7]) == 0.0                              # sampled references: guard clear on the benchmark data
+    assert float(out[3]) == float(ref["n_neg"])
+    _, counts = torch.unique(sd, return_counts=True)
+    assert float(out[3]) == float(B) * B - float((counts.double() ** 2).sum())
+    _loss_ok(out[0].item(), ref, lt)
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    errs = {"dY": rel(dY, ref["dY"]), "dX": rel(dX, ref["dX"])}
+    if Wd is not None:
+        errs["dW"] = rel(dW, ref["dW"])
+    print(f"full size {critic}/{est}/{precision}: loss {float(out[0]):.8f} (oracle {float(ref['loss']):.8f}) "
+          + " ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    assert max(errs.values()) < gt, errs
+    # identities between the independently computed passes: <dT,T> = <dY,Y> (= <dW,W> = <dX,X>)  (all equal sum(G * S))
+    a = float((dY.double() * Yd.double()).sum())
+    d = float((dX.double() * Xd.double()).sum())
+    assert abs(a - d) < 5e-3 * max(abs(a), abs(d), 1e-3)
+    if Wd is not None:
+        c = float((dW.double() * Wd.double()).sum())
         assert abs(a - c) < 5e-3 * max(abs(a), abs(c), 1e-3)
-        assert abs(a - d) < 5e-3 * max(abs(a), abs(d), 1e-3)
+
+
+def _nccl_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import mi_b200  # noqa: F401
+    from mi_b200 import dist as mdist, ops
+    from oracle import matrix_oracle as mo
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    try:
+        errs = {}
+        B, D = 8192, 256
+        X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=11, dup_frac=0.05, bilinear=True)
+        Bl = B // world
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        for est, planted in (("dv", False), ("infonce_row", False), ("infonce_sym", False), ("dv", True)):
+            Xb, Yb, Wb = X.bfloat16(), Y.bfloat16(), W.bfloat16()
+            if planted:                                      # guard trip on rank 0 only: both ranks must take the exact path
+                ops.set_ref_sample_columns(64)
+                Xb = Xb.clone(); Yb = Yb.clone(); Yb[7] = -Yb[5]; Xb[7] = (80.0 * Yb[5].float()).bfloat16()
+            full = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), Wb.to(dev), sid.to(torch.int32).to(dev), est, "strict", 1.0, True,
+                                           two_pass=True)
+            out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xb[sl].to(dev), Yb[sl].to(dev), Wb.to(dev),
+                                                               sid[sl].to(torch.int32).to(dev), est, "strict", 1.0, True)
+            torch.cuda.synchronize()
+            ops.set_ref_sample_columns(2048)
+            r = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+            errs[(est, planted)] = [abs(float(out["loss"]) - float(full[0][0])) / abs(float(full[0][0])), r(dX, full[1][sl]),
+                                    r(dY, full[2][sl]), r(dW, full[3]), float(out.get("guard", 0.0))]
+        ret[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_path_nccl_2gpu_equals_single_gpu(env):
+    """The sharded path on REAL NCCL (2 ranks, one per GPU) == the single-GPU call on the same global batch, for dv, row and
+    symmetric InfoNCE, and with a planted guard trip on one rank (both ranks must fall back to the exact path).  Skipped
+    on a 1-GPU box (the driver's GPU tier); run with `gpurun --gpus 2 -- python -m pytest tests -m gpu -k nccl`."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert len(ret) == 2
+    for rank in range(2):
+        for (est, planted), e in ret[rank].items():
+            assert e[0] < 1e-5 and max(e[1:4]) < 1e-4, (rank, est, planted, e)
+            assert (e[4] != 0.0) == planted, (rank, est, planted, e)
 
 
 def test_cuda_graph_replay_equals_direct_call(env):

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/mi_b200.h but not exported"
         assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
     assert set(_lib.PROTOTYPES) == set(names)
-    assert _lib.load().mi_abi_version() == 3
+    assert _lib.load().mi_abi_version() == 4
 
 
 def test_ctypes_prototypes_match_the_header_signatures():
@@ -156,7 +156,7 @@ def _free_port():
     return p
 
 
-def _dist_worker(rank, world, port, est, critic, ret, int32_ids=False):
+def _dist_worker(rank, world, port, est, critic, ret, int32_ids=False, ref_stride=1, outlier=False):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -172,10 +172,16 @@ def _dist_worker(rank, world, port, est, critic, ret, int32_ids=False):
         sid_raw = sid * 1000003 + 17                         # arbitrary int64 ids
         if int32_ids:                                        # exact int32 ids: ids + norm maxima travel in ONE all-gather
             sid_raw = sid.to(torch.int32)
+        cpu_backend.REF_STRIDE = ref_stride                  # sampled softmax references (every ref_stride-th own column)
+        if outlier:                                          # one score far above its row's SAMPLED columns (column 5 is odd)
+            Yb[3] = -Yb[5]                                   # (its own positive pair far BELOW: the reference cannot lean on it)
+            Xb[3] = (400.0 * Yb[5]).bfloat16().float()
         Bl = B // world
         sl = slice(rank * Bl, (rank + 1) * Bl)
         out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xb[sl], Yb[sl], Wb, sid_raw[sl], est, "strict", 0.5,
                                                            True, None, backend=cpu_backend)
+        if ref_stride > 1:                                   # the guard verdict is the same on every rank
+            assert float(out["guard"]) == (1.0 if outlier else 0.0), float(out["guard"])
         ref = mo.critic_loss(Xb, Yb, sid, Wb, 0.5, est)
         errs = [abs(float(out["loss"]) - float(ref["loss"])),
                 float((dX.double() - ref["dX"][sl]).abs().max() / ref["dX"].abs().max()),
@@ -213,6 +219,24 @@ def test_sharded_path_world2_gloo_packed_int32_ids():
     for rank in range(2):
         errs = ret[rank]
         assert errs[0] < 1e-6 and max(errs[1:-1]) < 1e-6 and errs[-1] == 0, (rank, errs)
+
+
+@pytest.mark.parametrize("est", ["dv", "infonce_row"])
+@pytest.mark.parametrize("outlier", [False, True])
+def test_sharded_path_world2_gloo_sampled_references_and_guard(est, outlier):
+    """Sampled references (stride 2 over the rank's own column block): same results as the exact path; a planted score that
+    the sample misses by hundreds of nats overflows the row sum on ONE rank, the merged guard count reaches BOTH ranks and the step
+    is repeated on the exact path — never a silently wrong result (dist.py ignored the flag)."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dist_worker, args=(2, _free_port(), est, "dot", ret, False, 2, outlier), nprocs=2, join=True)
+    assert len(ret) == 2
+    for rank in range(2):
+        errs = ret[rank]
+        # (outlier: scores of several hundred, so the fp32 reference vectors of the exact path carry ~1e3 * 2^-24 relative)
+        tol = 3e-4 if outlier else 1e-6
+        assert errs[0] < 1000 * tol and max(errs[1:-1]) < tol and errs[-1] == 0, (rank, errs)
 
 
 def test_merge_scalars_matches_single_block():

@@ -162,3 +162,21 @@ def test_infonce_row_sym_properties():
     G = mo.score_gradient(S, M, "infonce_row")
     assert G.sum(1).abs().max() < 1e-12
     assert float(row["loss"]) >= 0.0
+
+
+@pytest.mark.parametrize("est", ["dv", "infonce", "infonce_row", "infonce_sym"])
+@pytest.mark.parametrize("critic", ["dot", "bilinear"])
+def test_chunked_oracle_equals_matrix_oracle(est, critic):
+    """oracle.chunked_oracle (the row-chunked fp32 restatement the full-size GPU parity tests use) == the matrix oracle
+    (itself pinned to the reference's golden vectors above), incl. duplicate study ids and a ragged last chunk."""
+    from oracle import chunked_oracle as co
+    B, D = 203, 40
+    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=21, dup_frac=0.15, bilinear=(critic == "bilinear"))
+    inv_tau = 1.0 / math.sqrt(D) if critic == "dot" else 1.0
+    ref = mo.critic_loss(X, Y, sid, W, inv_tau, est)
+    got = co.critic_loss_chunked(X, Y, sid, W, inv_tau, est, chunk=64)
+    assert abs(float(got["loss"]) - float(ref["loss"])) < 2e-6 * max(1.0, abs(float(ref["loss"])))
+    assert float(got["n_neg"]) == float(ref["n_neg"])
+    for k in ("dX", "dY") + (("dW",) if critic == "bilinear" else ()):
+        err = float((got[k].double() - ref[k]).abs().max() / ref[k].abs().max())
+        assert err < 2e-5, (k, err)                       # fp32 matmuls against the fp64 matrix form
