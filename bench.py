@@ -4,10 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one pass of the hot path (single pass: score tiles -> loss statistics and both gradient
-contractions, plus the bilinear projections and their backward) over one batch of synthetic CXR-shaped embeddings.  N=1: B=65536, D=1024 (the size the
-metric is quoted on).  N>1: the same global batch sharded by rows, strong scaling.
-Prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path (single pass: sampled softmax references -> score tiles -> loss statistics and
+both gradient contractions, plus the bilinear projections and their backward) over one batch of synthetic CXR-shaped
+embeddings.  N=1: B=65536, D=1024 (the size the metric is quoted on).  N>1: the same global batch sharded by rows,
+strong scaling.  Prints ONE JSON line on rank 0.  At N=1 the line also carries a `variants` array (the other
+estimators / precisions / BASELINE config 2 / numerically hostile inputs, a few steps each) and a second CPU
+baseline entry for BASELINE config 1.
 """
 from __future__ import annotations
 
@@ -44,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     return ap.parse_args()
 
 
@@ -61,7 +64,13 @@ def workload_name(a):
             f"bf16 operands / fp32 accumulate, precision={a.precision}")
 
 
+def f_alg(B, D, bilinear):
+    """6 D flops per scored pair (+ the three B x D x D projections of the bilinear critic)."""
+    return 6.0 * B * B * D + (6.0 * B * D * D if bilinear else 0.0)
+
+
 # ------------------------------------------------------------------------------------------- CPU arm
+# (the ONLY place bench.py touches oracle/: the reported CPU baseline and the `--impl reference` arm)
 def cpu_oracle_step(B, D, critic, estimator, seed=1234):
     """One fwd+bwd of the oracle's matrix form on the host (the reference's pair-form is O(B^4) and
     cannot run at these sizes — BASELINE.md section 2; /root/reference does not travel to the GPU box)."""
@@ -95,8 +104,33 @@ def time_cpu(a, steps, warmup, budget_s=25.0):
     t = sum(ts) / len(ts)
     return {"value": B * B / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"oracle matrix form (fp32, torch CPU), fwd+bwd, B={B}, D={a.dim}, {a.critic}/{a.estimator}, "
-                      f"{len(ts)} steps, {t * 1e3:.0f} ms/step",
+                      f"{len(ts)} steps, {t * 1e3:.0f} ms/step (port @ B={B}: NOT the benchmark's B)",
             "ms_per_step": t * 1e3, "steps": len(ts)}
+
+
+def time_cpu_config1(budget_s=12.0):
+    """BASELINE config 1 as the reference executes it: dot-product critic on the explicit pair rows
+    built by the growing-torch.cat loop of main_utils.py:99-108, dv_bound_loss, autograd backward; B=32, D=768, fp32."""
+    import torch
+    from oracle import matrix_oracle as mo
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, D = 32, 768
+    X, Y, sid, _ = mo.synthetic_embeddings(B, D, seed=1, dup_frac=0.0, bilinear=False)
+    ids = [str(int(s)) for s in sid]
+    ts = []
+    t_start = time.time()
+    for it in range(8):
+        t0 = time.perf_counter()
+        mo.critic_loss_pair_form(X, Y, ids, None, 1.0 / math.sqrt(D), "dv", dtype=torch.float32, catloop=True)
+        if it > 0:
+            ts.append(time.perf_counter() - t0)
+        if time.time() - t_start > budget_s and ts:
+            break
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": B * B / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"BASELINE config 1: pair form with the reference's torch.cat loop, dot critic + dv, B={B}, D={D}, fp32, "
+                      f"fwd+bwd, median of {len(ts)} ({med * 1e3:.0f} ms/step, min {ts[0] * 1e3:.0f} ms)"}
 
 
 def run_reference(a):
@@ -108,7 +142,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": cb["steps"], "warmup": max(1, a.warmup), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "note": "CPU arm: bounded sample of the same workload"},
+        "config": {"workload": workload_name(a),
+                   "note": f"CPU arm: bounded sample of the same workload (oracle port at B={a.cpu_sample_batch}, not {a.batch}: "
+                           "the matrix form at the full size needs ~50 GB and ~10 min per step on the host)"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -201,9 +237,8 @@ def run_ours(a):
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
     import mi_b200  # noqa: F401
-    from mi_b200 import _lib, ops
+    from mi_b200 import _lib, ops, synthetic
     from mi_b200 import dist as mdist
-    from oracle import matrix_oracle as mo
     lib = _lib.load()
 
     B, D = a.batch, a.dim
@@ -213,7 +248,7 @@ def run_ours(a):
     bilinear = a.critic == "bilinear"
     inv_tau = 1.0 / math.sqrt(D) if not bilinear else 1.0
     # synthetic CXR-shaped embeddings, generated once on the host, rounded to bf16
-    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=1234, dup_frac=0.05, bilinear=bilinear)
+    X, Y, sid, W = synthetic.synthetic_embeddings(B, D, seed=1234, dup_frac=0.05, bilinear=bilinear)
     Xh = X[off:off + Bl].contiguous().pin_memory()
     Yh = Y[off:off + Bl].contiguous().pin_memory()
     Wh = W.contiguous().pin_memory() if bilinear else None
@@ -221,7 +256,6 @@ def run_ours(a):
     Xd, Yd = Xh.to(dev).bfloat16(), Yh.to(dev).bfloat16()
     Wd = Wh.to(dev).bfloat16() if bilinear else None
     sd32 = sh.to(dev)
-    sd64 = sd32                      # exact int32 ids: the sharded path uses them as they are
     del X, Y
 
     out_bufs = (torch.empty(8, dtype=torch.float64, device=dev), torch.empty(Bl, D, device=dev),
@@ -230,8 +264,8 @@ def run_ours(a):
     def step_device():
         if world == 1:
             return ops.critic_loss_fwd_bwd(Xd, Yd, Wd, sd32, a.estimator, a.precision, inv_tau, True, out=out_bufs)
-        out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xd, Yd, Wd, sd64, a.estimator, a.precision, inv_tau, True)
-        return out["loss"], dX, dY, dW
+        # check_guard=False: no host read inside the timed region (the guard count is checked once after it)
+        return mdist.sharded_critic_loss_fwd_bwd(Xd, Yd, Wd, sd32, a.estimator, a.precision, inv_tau, True, check_guard=False)
 
     def sync_all():
         if world > 1:
@@ -278,8 +312,17 @@ def run_ours(a):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_per_step = total_ms / a.steps
     value = B * B / (ms_per_step * 1e-3)
-    loss_val = float(last[0][0].item()) if world == 1 else float(last[0].item())
-    guard_rows = float(last[0][7].item()) if world == 1 else None
+    if world == 1:
+        loss_val, guard_rows = float(last[0][0].item()), float(last[0][7].item())
+    else:
+        loss_val = float(last[0]["loss"].item())
+        guard_rows = float(last[0]["guard"].item()) if "guard" in last[0] else 0.0
+    # a tripped guard means the timed steps went through the exact repeat (N = 1) or are not valid (N > 1): say so loudly
+    sym = a.estimator == "infonce_sym"
+    path = "row+column statistics pass + gradient pass (exact references)" if sym else "single pass, sampled softmax references"
+    if guard_rows != 0.0 and not sym:
+        path += (" -> guard tripped: the exact repeat ran inside every timed step" if world == 1 else
+                 " -> guard tripped and NOT acted on (check_guard=False in the timed loop): INVALID NUMBER")
 
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     e2e = None
@@ -309,6 +352,8 @@ def run_ours(a):
                 x, y = Xh.to(dev, non_blocking=True), Yh.to(dev, non_blocking=True)
                 w = Wh.to(dev, non_blocking=True) if bilinear else None
                 s = sh.to(dev, non_blocking=True)
+                # the public call with its default guard handling: the host reads the merged guard count as soon as the
+                # score tiles are done and would repeat the step on the exact path
                 out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(x, y, w, s, a.estimator, a.precision, inv_tau, True)
                 dXh.copy_(dX, non_blocking=True); dYh.copy_(dY, non_blocking=True)
                 if bilinear:
@@ -323,6 +368,48 @@ def run_ours(a):
                "d2h_bytes_per_step": world * (2 * n_bd + (n_dd if bilinear else 0) + 64),
                "api": "mi_critic_loss_fwd_bwd_host (C ABI, pinned fp32 host buffers)" if world == 1 else
                       "mi_b200.dist.sharded_critic_loss_fwd_bwd on pinned host shards"}
+
+    # ---- variants (N = 1): the other estimators / precisions, BASELINE config 2, numerically hostile inputs
+    variants = []
+    if world == 1 and not a.no_variants:
+        pk_v = peaks()
+
+        def run_variant(name, Xv, Yv, Wv, sv, est, prec, itau, steps=5):
+            Bv, Dv = Xv.shape
+            bufs = (torch.empty(8, dtype=torch.float64, device=dev), torch.empty(Bv, Dv, device=dev),
+                    torch.empty(Bv, Dv, device=dev), None if Wv is None else torch.empty(Dv, Dv, device=dev))
+            fn = lambda: ops.critic_loss_fwd_bwd(Xv, Yv, Wv, sv, est, prec, itau, True, out=bufs)
+            for _ in range(3):
+                fn()
+            t_ms, _, _, r = timed(fn, steps)
+            t_ms /= steps
+            fa_v = f_alg(Bv, Dv, Wv is not None)
+            lo = r[0].cpu()
+            variants.append({"name": name, "B": Bv, "D": Dv, "critic": "dot" if Wv is None else "bilinear", "estimator": est,
+                             "precision": prec, "ms_per_step": t_ms, "pairs_per_s": Bv * Bv / (t_ms * 1e-3),
+                             "f_alg_tflops": fa_v / (t_ms * 1e-3) / 1e12,
+                             "frac_of_sustained_peak": fa_v / (t_ms * 1e-3) / 1e12 / pk_v["sustained"],
+                             "frac_of_burst_peak": fa_v / (t_ms * 1e-3) / 1e12 / pk_v["burst"],
+                             "loss": float(lo[0]), "guard_rows": float(lo[7]),
+                             "path": ("exact repeat (guard tripped)" if float(lo[7]) != 0.0 else
+                                      ("statistics + gradient pass" if est == "infonce_sym" else "single pass"))})
+
+        run_variant("config3 symmetric InfoNCE, fast", Xd, Yd, Wd, sd32, "infonce_sym", "fast", inv_tau)
+        run_variant("config3 symmetric InfoNCE, strict", Xd, Yd, Wd, sd32, "infonce_sym", "strict", inv_tau, steps=3)
+        run_variant("DV, strict (fp32-accumulate mode)", Xd, Yd, Wd, sd32, "dv", "strict", inv_tau, steps=3)
+        run_variant("row InfoNCE, fast", Xd, Yd, Wd, sd32, "infonce_row", "fast", inv_tau)
+        # numerically hostile inputs at the full size (VERDICT r1 #1c): must stay on the single pass, guard clear
+        if bilinear:
+            run_variant("stress: scores x 8 (nearly one-hot softmax)", Xd, Yd, (8.0 * Wd.float()).bfloat16(), sd32, "dv", "fast", inv_tau)
+            gw = torch.Generator().manual_seed(11)
+            Wn = (torch.eye(D) + 0.1 * torch.randn(D, D, generator=gw) / math.sqrt(D)).to(dev).bfloat16()
+            run_variant("stress: unnormalised embeddings, W = I + noise, inv_tau = 1", Xd, Yd, Wn, sd32, "dv", "fast", 1.0)
+            run_variant("stress: unnormalised embeddings, row InfoNCE", Xd, Yd, Wn, sd32, "infonce_row", "fast", 1.0)
+        # BASELINE config 2: bilinear + InfoNCE, B = 4096, D = 768
+        X2, Y2, s2, W2 = synthetic.synthetic_embeddings(4096, 768, seed=2, dup_frac=0.05, bilinear=True)
+        X2, Y2, W2, s2 = X2.to(dev).bfloat16(), Y2.to(dev).bfloat16(), W2.to(dev).bfloat16(), s2.to(torch.int32).to(dev)
+        run_variant("config2 bilinear + InfoNCE (reference form)", X2, Y2, W2, s2, "infonce", "fast", 1.0, steps=20)
+        run_variant("config2 bilinear + symmetric InfoNCE", X2, Y2, W2, s2, "infonce_sym", "fast", 1.0, steps=20)
 
     launches_t = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
@@ -341,20 +428,19 @@ def run_ours(a):
         if (c["global_batch"], c["dim"], c["critic"], c["estimator"], c["precision"], c["n_gpus"]) == \
                 (B, D, a.critic, a.estimator, a.precision, world):
             traffic = tj["bytes_per_step"]
-    f_alg = 6.0 * B * B * D + (6.0 * B * D * D if bilinear else 0.0)
-    sym = a.estimator == "infonce_sym"
+    fa = f_alg(B, D, bilinear)
     strict = a.precision == "strict"
-    # executed tensor flops: statistics pass(es) 2 B^2 D each, one score recompute 2 B^2 D, two dS x operand
-    # contractions 2 B^2 D each; strict mode adds the hi/lo segments of T and of the dS panel
-    # (the single-pass path — every estimator but the symmetric one — computes the scores once: no statistics pass)
-    n_stats = 2 if sym else 0
+    # executed tensor flops: the single pass computes the scores once (+ the ~1 % column sample of the references);
+    # the symmetric estimator adds ONE combined row+column statistics pass (2 B^2 D); two dS x operand contractions
+    # 2 B^2 D each; strict mode adds the hi/lo segments of T and of the dS panel
+    n_stats = 1 if sym else 0
     if strict:
         s_mult = 2.0 if bilinear else 1.0
-        f_exec = (n_stats * s_mult + 2 * s_mult + 2 * 2 + 2 * (3 if (bilinear or not sym) else 2)) * float(B) * B * D
+        f_exec = (n_stats * s_mult + s_mult + 2 * (3 if (bilinear or not sym) else 2)) * 2.0 * float(B) * B * D
     else:
-        f_exec = (n_stats + 2 + 4) * float(B) * B * D
+        f_exec = (n_stats + 1 + 2) * 2.0 * float(B) * B * D
     f_exec += (6.0 * B * D * D if bilinear else 0.0)
-    ach = f_alg / (ms_per_step * 1e-3) / 1e12 / world           # per GPU
+    ach = fa / (ms_per_step * 1e-3) / 1e12 / world           # per GPU
     kinds = ["score_stats", "ds_panel", "gemm"]
     by_kernel = {k: {"ms_per_step": ms[i] / a.steps, "launches_per_step": cnt[i] / a.steps} for i, k in enumerate(kinds)}
     line = {
@@ -364,14 +450,15 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "global_batch": B, "dim": D, "critic": a.critic,
                    "estimator": a.estimator, "precision": a.precision, "parallelism": f"row-sharded x{world}",
                    "l2": "inputs (2 x %d MB bf16 + >1 GB dS panel per pass) exceed the 126 MB L2; no flush needed" % (B * D * 2 >> 20),
-                   "loss": loss_val, "guard_rows": guard_rows},
+                   "loss": loss_val, "guard_rows": guard_rows, "path": path},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
                      "frac": ach / pk["sustained"], "traffic": traffic,
                      "traffic_note": "DRAM bytes per step summed over the step's launches (ncu capture in profiles/), "
-                                     "algorithmic bytes 0.54e9: the path is tensor-bound, the bf16 dS panel staging is the extra traffic",
+                                     "algorithmic bytes 0.54e9: the path is tensor-bound; the bf16 dS panel is STREAMED THROUGH HBM "
+                                     "panel by panel (SURVEY 7.3-d) - that staging is the extra traffic",
                      "peak_kind": "sustained bf16 (kernel timed inside a long step), " + pk["source"],
                      "frac_of_burst_peak": ach / pk["burst"], "burst_peak": pk["burst"],
-                     "algorithmic_flops_per_step": f_alg, "executed_flops_per_step": f_exec,
+                     "algorithmic_flops_per_step": fa, "executed_flops_per_step": f_exec,
                      "executed_tflops": f_exec / (ms_per_step * 1e-3) / 1e12 / world,
                      "kernel": "tile_engine_kernel (all launches of one step; per-kind CUDA-event times in by_kernel)",
                      "by_kernel": by_kernel},
@@ -379,9 +466,12 @@ def run_ours(a):
     }
     if e2e:
         line["e2e"] = e2e
+    if variants:
+        line["variants"] = variants
     if world == 1 and not a.no_cpu_baseline:
         cb = time_cpu(a, 3, 1, budget_s=25.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"]["config1"] = time_cpu_config1()
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

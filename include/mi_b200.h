@@ -132,7 +132,8 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
  * include_diag = 1 adds the positive pair.  stride = 1 samples every column: the references are then the exact row
  * log-sum-exps and the pass cannot leave the safe window.  stride = 0 picks mi_ref_sample_stride(Bq, n_cols, D) (about
  * mi_set_ref_sample_columns() columns per row, default 2048, i.e. ~1 % of the step at B = 65536).  Also returned:
- * diag_out[q] = the positive-pair score S[q, q_offset + q], lambda_out[0] = max_q ref[q] (may be NULL).
+ * diag_out[q] = the positive-pair score S[q, q_offset + q], lambda_out[0] = the largest sample log-sum-exp (may be NULL).
+ * Sampled references (stride > 1) are lifted 48 nats above the sample's log-sum-exp: the true value can only lie above it.
  *
  * mi_score_single_pass: the same tiles give the row sums (=> row_out / scal_out exactly as mi_score_stats; for
  * include_diag = 1 the sums include the positive pair) and
@@ -140,7 +141,7 @@ int mi_score_grad(const void* Q, int64_t ldq, int q_split, const void* K, int64_
  * with wrow = e^{ref - lambda[0]} (include_diag = 0; lambda = ONE constant near the largest reference, the same on every
  * rank whose ok_raw is summed) or inv_bg / rowsum (include_diag = 1; lambda unused, may be NULL).
  * Any reference is mathematically valid.  flag_out (and scal_out[6]) count the rows whose reference left the numerically
- * safe window (row sum outside [1e-30, 1e30], or ref - lambda > 60): must be 0, else repeat with stride = 1 references.
+ * safe window (row sum outside [1e-30, 1e30], or ref - lambda > 80): must be 0, else repeat with stride = 1 references.
  * The gradients follow from mi_single_finalize_q / _k once the (global) log-sum-exp is known:
  *   Oq = alpha (c_q oq_raw - gamma Kdiag),  c_q = e^{ref_q - lse} (dv_like) or wrow_q
  *   Ok = alpha (kappa ok_raw - gamma Qdiag), kappa = e^{lambda - lse} (dv_like) or 1     (in place) */

@@ -99,7 +99,7 @@ __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
 template <int kCG, class Epi, bool kAMN, bool kBMN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const Sched sc, const typename Epi::Params ep) {
+                   const Sched sc, const __grid_constant__ typename Epi::Params ep) {
   using C = Cfg<kCG>;
   if (sc.run_if != nullptr && *sc.run_if == 0) return;      // grid-uniform: both CTAs of a pair leave together
   extern __shared__ uint8_t smem_raw[];
@@ -400,12 +400,113 @@ struct EpiStats {
   }
 };
 
+// ---- row AND column statistics from one score computation (symmetric InfoNCE: both softmax directions).
+//      Rows: the lane-local online (max, sum-exp) of EpiStats.  Columns: each warp transposes its 32 x 32 chunk through
+//      2 KB of shared memory, 16 columns at a time (conflict-free: 16 B groups XOR-swizzled by the row), so that a lane
+//      holds 16 rows of ONE column and max / sum-exp are lane-local again; the two row halves meet in one shuffle.
+//      Output: colpart[row block of 32][column] = log2-sum-exp2 of the column over those 32 rows (-inf if all excluded),
+//      merged over the row blocks by a small kernel.  S itself is never stored.
+struct EpiStatsRC {
+  static constexpr int kEpiSmemBytes = kNumEpiWarps * 2048;
+  struct Params {
+    MaskInfo mask;
+    int q_rows, k_cols;
+    float scale;           // S = scale * acc, scale > 0
+    float4* part;          // [n_split][4][rows_padded]  {max (log2 units), sum, 0, 0}
+    int rows_padded;
+    float* colpart;        // [rows_padded / 32][col_pitch]
+    long long col_pitch;
+  };
+  struct State { uint8_t* stage_smem; MaskState ms; float m, s; };
+
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+  static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
+    st.m = neg_inf(); st.s = 0.f;
+    mask_begin(p.mask, st.ms, row, p.q_rows);
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0,
+                                               uint32_t (&v)[32]) {
+    const float c2 = p.scale * kLog2e;
+    const int lane = (int)(threadIdx.x & 31);
+    uint32_t mk = chunk_mask(p.mask, st.ms, col0, p.k_cols);
+    if (row >= p.q_rows) mk = 0xffffffffu;             // rows beyond the matrix (zero-filled by TMA) take no part
+    if (mk != 0u) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) if ((mk >> c) & 1u) v[c] = 0xff800000u;   // -inf
+    }
+    // ---- rows: lane-local online softmax statistics (as EpiStats)
+    float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+    for (int c = 4; c < 32; c += 4) {
+      m0 = fmaxf(m0, __uint_as_float(v[c])); m1 = fmaxf(m1, __uint_as_float(v[c + 1]));
+      m2 = fmaxf(m2, __uint_as_float(v[c + 2])); m3 = fmaxf(m3, __uint_as_float(v[c + 3]));
+    }
+    const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c2;
+    const float m_new = fmaxf(st.m, cm);
+    if (m_new > neg_inf()) {
+      float s0 = st.s * ptx::ex2(st.m - m_new), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        s0 += ptx::ex2(fmaf(__uint_as_float(v[c]), c2, -m_new));
+        s1 += ptx::ex2(fmaf(__uint_as_float(v[c + 1]), c2, -m_new));
+        s2 += ptx::ex2(fmaf(__uint_as_float(v[c + 2]), c2, -m_new));
+        s3 += ptx::ex2(fmaf(__uint_as_float(v[c + 3]), c2, -m_new));
+      }
+      st.s = (s0 + s1) + (s2 + s3); st.m = m_new;
+    }
+    // ---- columns: transpose 16 columns at a time.  Element (r, c) of the half lives at word
+    //      r * 16 + 4 * ((c >> 2) ^ ((r >> 1) & 3)) + (c & 3); lane (cc = lane & 15, rh = lane >> 4) reads rows 2t + rh.
+    float* sm = reinterpret_cast<float*>(st.stage_smem);
+    const int sw = (lane >> 1) & 3;
+    const int cc = lane & 15, rh = lane >> 4;
+    const int rb = (row - lane) >> 5;                  // 32-row block of this warp
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(sm + lane * 16 + 4 * (g ^ sw)) =
+            make_uint4(v[16 * h + 4 * g], v[16 * h + 4 * g + 1], v[16 * h + 4 * g + 2], v[16 * h + 4 * g + 3]);
+      __syncwarp();
+      float x[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) x[t] = sm[(2 * t + rh) * 16 + 4 * ((cc >> 2) ^ (t & 3)) + (cc & 3)];
+      __syncwarp();
+      float a0 = fmaxf(x[0], x[1]), a1 = fmaxf(x[2], x[3]), a2 = fmaxf(x[4], x[5]), a3 = fmaxf(x[6], x[7]);
+      a0 = fmaxf(a0, fmaxf(x[8], x[9])); a1 = fmaxf(a1, fmaxf(x[10], x[11]));
+      a2 = fmaxf(a2, fmaxf(x[12], x[13])); a3 = fmaxf(a3, fmaxf(x[14], x[15]));
+      const float mh = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * c2;          // this half's column max (log2 units)
+      const float mo = __shfl_xor_sync(0xffffffffu, mh, 16);
+      const float mc = fmaxf(mh, mo);                                      // column max over the warp's 32 rows
+      float s0 = 0.f, s1 = 0.f;
+      if (mc > neg_inf()) {
+#pragma unroll
+        for (int t = 0; t < 16; t += 2) {
+          s0 += ptx::ex2(fmaf(x[t], c2, -mc));
+          s1 += ptx::ex2(fmaf(x[t + 1], c2, -mc));
+        }
+      }
+      float sc = s0 + s1;
+      sc += __shfl_xor_sync(0xffffffffu, sc, 16);
+      if (rh == 0) {
+        const float l2 = (mc > neg_inf() && sc > 0.f) ? mc + __log2f(sc) : neg_inf();
+        p.colpart[(size_t)rb * p.col_pitch + col0 + 16 * h + cc] = l2;
+      }
+    }
+  }
+  static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit& un, int row, int colq) {
+    p.part[((size_t)un.s * kColQuarters + colq) * p.rows_padded + row] = make_float4(st.m, st.s, 0.f, 0.f);
+  }
+};
+
 // ---- dS panel: P[row, col] = incl * ( wq e^{S - refq[row]} + wk e^{S - refk[col]} ), bf16 (hi [+ lo])
-// Each epilogue warp stages its 32 rows x 32 columns (2 KB, XOR-swizzled 16 B chunks) in shared memory
-// and writes them out as 64 B row segments (8 rows per warp store) instead of 16 B per row.
+// Each epilogue warp stages its 32 rows x 32 columns (2 KB, 16 B chunks XOR-swizzled by the row = TMA SWIZZLE_64B) in
+// shared memory and ONE lane hands the tile to the TMA engine (cp.async.bulk.tensor store): no per-thread global stores,
+// no address arithmetic, rows beyond the panel clipped by the tensor map.
 struct EpiPStore {
   static constexpr int kEpiSmemBytes = kNumEpiWarps * 2048;
   struct Params {
+    alignas(64) CUtensorMap tmap_p;   // the panel [q_rows, pitch] bf16, box 32 x 32, SWIZZLE_64B
     MaskInfo mask;
     int q_rows, k_cols;
     long long q_offset;
@@ -416,9 +517,7 @@ struct EpiPStore {
     const float* refk2;     // [n_ntile*256] (padded) column reference, log2 units, weight folded in
     int use_k;
     int include_diag;       // 1: the positive pair is part of the softmax (InfoNCE), 0: negatives only (DV)
-    __nv_bfloat16* P;       // [q_rows, pitch]
-    __nv_bfloat16* P_lo;    // residual panel (strict mode) or nullptr
-    long long pitch;
+    int lo_col0;            // strict mode: the residual panel starts at this column of the same rows (0: none)
     // single-pass mode: refq is a per-row UPPER BOUND of the scores, so P <= 1 needs no running max; the
     // row sums of P (fp32, before rounding) are the statistics: sum_part[n_split][4][rows_padded]
     float* sum_part;
@@ -427,34 +526,31 @@ struct EpiPStore {
   struct State { uint8_t* stage_smem; MaskState ms; float rq2; float s; };
 
   static __device__ __forceinline__ void init(const Params&, State&) {}
-  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {
+    if ((threadIdx.x & 31) == 0) ptx::tma_store_wait_all();          // this lane issued the warp's stores
+  }
   static __device__ __forceinline__ void unit_begin(const Params& p, State& st, const Unit&, int row, int) {
     st.s = 0.f;
     mask_begin(p.mask, st.ms, row, p.q_rows);
     const float r = (p.use_q && row < p.q_rows) ? __ldg(p.refq + row) : 0.f;
     st.rq2 = (r - p.ln_wq) * kLog2e;
   }
-  // stage this thread's 32 packed bf16 (16 words = 4 x 16 B) into its row of the warp's 32 x 64 B tile,
-  // then the warp writes the tile to global memory: lane -> (row = 8*it + lane/4, 16 B chunk = lane%4)
-  static __device__ __forceinline__ void stage_and_flush(uint8_t* smem, int lane, const uint32_t (&w)[16],
-                                                         __nv_bfloat16* dst_row0, long long pitch, int rows_valid) {
+  // stage this thread's 32 packed bf16 (16 words = 4 x 16 B) into its row of the warp's 32 x 64 B tile (the TMA
+  // SWIZZLE_64B pattern: 16 B chunk index ^= (row >> 1) & 3), then lane 0 issues the tile store at (col, row0)
+  static __device__ __forceinline__ void stage_and_store(const Params& p, uint8_t* smem, int lane, const uint32_t (&w)[16],
+                                                         int col, int row0) {
+    if (lane == 0) ptx::tma_store_wait_read();         // the previous store of this warp has drained the buffer
+    __syncwarp();
     const int sw = (lane >> 1) & 3;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       *reinterpret_cast<uint4*>(smem + lane * 64 + ((g ^ sw) * 16)) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+    ptx::fence_proxy_async_smem();
     __syncwarp();
-    uint4 val[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = it * 8 + (lane >> 2), ch = lane & 3;
-      val[it] = *reinterpret_cast<const uint4*>(smem + r * 64 + ((ch ^ ((r >> 1) & 3)) * 16));
+    if (lane == 0 && row0 < p.q_rows) {
+      ptx::tma_store_2d(&p.tmap_p, ptx::smem_u32(smem), col, row0);
+      ptx::tma_store_commit();
     }
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = it * 8 + (lane >> 2), ch = lane & 3;
-      if (r < rows_valid) ptx::st_global_cs(dst_row0 + (size_t)r * pitch + ch * 8, val[it]);
-    }
-    __syncwarp();
   }
   static __device__ __forceinline__ void chunk(const Params& p, State& st, const Unit&, int row, int col0,
                                                uint32_t (&v)[32]) {
@@ -502,15 +598,14 @@ struct EpiPStore {
 #pragma unroll
     for (int c = 0; c < 16; ++c) hi[c] = ptx::pack_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
     const int row0 = row - lane;                       // first row of this warp
-    const int rows_valid = p.q_rows - row0;
-    stage_and_flush(st.stage_smem, lane, hi, p.P + (size_t)row0 * p.pitch + col0, p.pitch, rows_valid);
-    if (p.P_lo != nullptr) {                           // strict mode: residual panel
+    stage_and_store(p, st.stage_smem, lane, hi, col0, row0);
+    if (p.lo_col0 > 0) {                               // strict mode: residual panel, lo_col0 columns to the right
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const float h0 = __uint_as_float(hi[c] << 16), h1 = __uint_as_float(hi[c] & 0xffff0000u);
         hi[c] = ptx::pack_bf16(__uint_as_float(v[2 * c]) - h0, __uint_as_float(v[2 * c + 1]) - h1);
       }
-      stage_and_flush(st.stage_smem, lane, hi, p.P_lo + (size_t)row0 * p.pitch + col0, p.pitch, rows_valid);
+      stage_and_store(p, st.stage_smem, lane, hi, col0 + p.lo_col0, row0);
     }
   }
   static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit& un, int row, int colq) {

@@ -141,6 +141,26 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long rows, long long k_exten
   return MI_OK;
 }
 
+// bf16 matrix [rows, cols] with row pitch ld (elements) as a STORE target: box 32 x 32, 64 B swizzle (the staging layout
+// of EpiPStore); rows / columns beyond the matrix are clipped by the TMA engine.
+int make_tmap_store32(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { std::snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled unavailable"); return MI_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0 || rows <= 0 || cols <= 0) return MI_ERR_BAD_ARG;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled (store) failed with %d", static_cast<int>(r));
+    return MI_ERR_CUDA;
+  }
+  return MI_OK;
+}
+
 // ------------------------------------------------------------------------------------ engine launch
 struct MapSpec {          // a 2-D bf16 tensor map: `rows` x `k_extent` elements, row pitch ld
   const void* ptr; long long rows, k_extent, ld;
@@ -198,6 +218,7 @@ int launch_engine_cg(const MapSpec& a, const MapSpec& b, const Sched& sc, const 
 }
 
 template <> struct EpiKind<mi::EpiStats> { static constexpr int value = 0; };
+template <> struct EpiKind<mi::EpiStatsRC> { static constexpr int value = 0; };
 template <> struct EpiKind<mi::EpiPStore> { static constexpr int value = 1; };
 template <> struct EpiKind<mi::EpiStore> { static constexpr int value = 2; };
 template <> struct EpiKind<mi::EpiMlpFwd> { static constexpr int value = 0; };   // (profiling buckets: score-like / panel-like)
@@ -378,8 +399,9 @@ __global__ void row_norm_kernel(const __nv_bfloat16* __restrict__ A, long long l
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) norm[row] = sqrtf(acc);
 }
-// one block: out[0] = max_i in[i] (NaN entries are ignored by fmaxf; all-NaN / empty gives -inf)
-__global__ void max_reduce_kernel(const float* __restrict__ in, long long n, float* __restrict__ out, const int* __restrict__ run_if) {
+// one block: out[0] = max_i in[i] - offset (NaN entries are ignored by fmaxf; all-NaN / empty gives -inf)
+__global__ void max_reduce_kernel(const float* __restrict__ in, long long n, float* __restrict__ out, float offset,
+                                  const int* __restrict__ run_if) {
   MI_PRED(run_if);
   __shared__ float sh[32];
   float m = mi::neg_inf();
@@ -387,7 +409,7 @@ __global__ void max_reduce_kernel(const float* __restrict__ in, long long n, flo
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x == 0) { float g = mi::neg_inf(); for (int i = 0; i < (int)(blockDim.x >> 5); ++i) g = fmaxf(g, sh[i]); out[0] = g; }
+  if (threadIdx.x == 0) { float g = mi::neg_inf(); for (int i = 0; i < (int)(blockDim.x >> 5); ++i) g = fmaxf(g, sh[i]); out[0] = g - offset; }
 }
 
 // The single pass writes P~ = incl e^{S - ref_q} BEFORE the exact row statistics are known, so it needs a per-row reference
@@ -452,7 +474,7 @@ __global__ void sum_merge_kernel(const float* __restrict__ part, int n_part, int
     lse_all = hi + log1pf(expf(lo - hi));
     const float d = r - lambda[0];
     wrow[row] = expf(d);                                             // e^{ref - lambda}; e^{lambda - LSE} is applied at the end
-    bad = bad || !(d <= 60.f);                                       // lambda far below this row's reference (or NaN)
+    bad = bad || !(d <= 80.f);                                       // lambda far below this row's reference (or NaN)
   }
   if (bad) atomicAdd(flag, 1);
   row_out[row] = make_float4(lse_neg, cnt, diag, lse_all);
@@ -462,8 +484,8 @@ __global__ void scale_rows_kernel(const __nv_bfloat16* __restrict__ in, long lon
                                   const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo,
                                   long long ld_out, long long R, long long C, const int* __restrict__ run_if) {
   MI_PRED(run_if);
-  const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
-  if (idx >= R * C) return;
+  for (long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; idx < R * C;
+       idx += (long long)gridDim.x * blockDim.x * 8) {
   const long long r = idx / C, c = idx - r * C;         // C % 8 == 0: the 8 elements share a row
   const uint4 hv = *reinterpret_cast<const uint4*>(in + r * ld_in + c);
   const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
@@ -488,6 +510,7 @@ __global__ void scale_rows_kernel(const __nv_bfloat16* __restrict__ in, long lon
       l[j] = ptx::pack_bf16(v[2 * j] - __uint_as_float(h[j] << 16), v[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
     *reinterpret_cast<uint4*>(out_lo + r * ld_out + c) = make_uint4(l[0], l[1], l[2], l[3]);
   }
+  }
 }
 // Oq[i,:] = alpha (c_i Oraw[i,:] - gamma Kdiag[i,:]),  c_i = e^{ref_i - LSE} (DV) or wrow_i (row InfoNCE).  8 elements / thread
 __global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, long long rows, const float* __restrict__ ref,
@@ -496,8 +519,8 @@ __global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, lo
                                   float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ out_lo, long long ld16,
                                   const int* __restrict__ run_if) {
   MI_PRED(run_if);
-  const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
-  if (idx >= rows * D) return;
+  for (long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; idx < rows * D;
+       idx += (long long)gridDim.x * blockDim.x * 8) {
   const long long i = idx / D, d = idx - i * D;          // D % 8 == 0
   const float c = dv_like ? expf(ref[i] - lse[0]) : wrow[i];
   const uint4 kv = *reinterpret_cast<const uint4*>(kdiag + i * ldk + d);
@@ -532,6 +555,7 @@ __global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, lo
         l[j] = ptx::pack_bf16(o[2 * j] - __uint_as_float(h[j] << 16), o[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
       *reinterpret_cast<uint4*>(out_lo + i * ld16 + d) = make_uint4(l[0], l[1], l[2], l[3]);
     }
+  }
   }
 }
 // Ok[k,:] = alpha (kappa Ok[k,:] - gamma [0 <= k-q_offset < Bq] Q[k-q_offset,:]),  kappa = e^{lambda - LSE} (DV) or 1
@@ -573,6 +597,39 @@ __global__ void stats_merge_kernel(const float4* __restrict__ part, int n_part, 
   row_out[row] = make_float4(lse_neg, cnt, diag, lse_all);
 }
 
+// columns of the square score matrix: merge the per-32-row-block partial log2-sum-exp2 values (EpiStatsRC) of column j
+// -> col_out[j] = {lse_neg, n_neg, diag, lse_all} (the layout of row_out).  block = 32 columns x 8 row-block slices.
+__global__ void col_merge_kernel(const float* __restrict__ colpart, int n_rb, long long pitch, int k_cols,
+                                 const int* __restrict__ n_same, int q_rows, const float* __restrict__ diag_in,
+                                 float4* __restrict__ col_out) {
+  __shared__ float shm[8][33], shs[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float m = mi::neg_inf(), s = 0.f;
+  if (col < k_cols) {
+    for (int rb = threadIdx.y; rb < n_rb; rb += 8) {
+      const float x = colpart[(size_t)rb * pitch + col];
+      if (x > mi::neg_inf()) {
+        const float mn = fmaxf(m, x);
+        s = s * exp2f(m - mn) + exp2f(x - mn);       // (m = -inf, s = 0 on the first hit: 0 * 0 + 1)
+        m = mn;
+      }
+    }
+  }
+  shm[threadIdx.y][threadIdx.x] = m; shs[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || col >= k_cols) return;
+  float gm = mi::neg_inf();
+  for (int y = 0; y < 8; ++y) gm = fmaxf(gm, shm[y][threadIdx.x]);
+  float gs = 0.f;
+  for (int y = 0; y < 8; ++y) if (shs[y][threadIdx.x] > 0.f) gs += shs[y][threadIdx.x] * exp2f(shm[y][threadIdx.x] - gm);
+  const float diag = diag_in[col];
+  const float cnt = static_cast<float>(q_rows - n_same[col]);
+  const float lse_neg = (cnt > 0.f && gs > 0.f) ? (gm + log2f(gs)) * mi::kLn2 : mi::neg_inf();
+  const float hi = fmaxf(lse_neg, diag), lo = fminf(lse_neg, diag);
+  const float lse_all = hi + log1pf(expf(lo - hi));
+  col_out[col] = make_float4(lse_neg, cnt, diag, lse_all);
+}
+
 // one block: scal = {max lse_neg, sum exp(lse_neg - max), sum n_neg, sum diag, sum (lse_all - diag), #rows w/o neg, 0, 0}
 __global__ void stats_reduce_kernel(const float4* __restrict__ row_out, int q_rows, double* __restrict__ scal,
                                     const int* __restrict__ run_if) {
@@ -607,6 +664,63 @@ __global__ void stats_reduce_kernel(const float4* __restrict__ row_out, int q_ro
     for (int k = 0; k < 5; ++k) for (int i = 0; i < nw; ++i) t[k] += sh[k][i];
     scal[0] = g; scal[1] = t[0]; scal[2] = t[1]; scal[3] = t[2]; scal[4] = t[3]; scal[5] = t[4]; scal[6] = 0; scal[7] = 0;
   }
+}
+// the same reduction over kRedBlocks blocks: each block reduces its slice relative to its own maximum, the last block to
+// finish (atomic ticket) merges the slices and resets the ticket.  red = {double part[kRedBlocks][8]; unsigned ticket} (zeroed once).
+constexpr int kRedBlocks = 64;
+struct RedScratch { double* part; unsigned* ticket; };
+__global__ void stats_reduce_mb_kernel(const float4* __restrict__ row_out, int q_rows, double* __restrict__ scal,
+                                       double* __restrict__ part, unsigned* __restrict__ ticket, const int* __restrict__ run_if) {
+  MI_PRED(run_if);
+  __shared__ double sh[5][8];
+  __shared__ float shm[8];
+  __shared__ float bmax;
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;     // 256 threads
+  const int per = (q_rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(q_rows, r0 + per);
+  float m = mi::neg_inf();
+  for (int r = r0 + tid; r < r1; r += blockDim.x) m = fmaxf(m, row_out[r].x);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) shm[w] = m;
+  __syncthreads();
+  if (tid == 0) { float g = mi::neg_inf(); for (int i = 0; i < nw; ++i) g = fmaxf(g, shm[i]); bmax = g; }
+  __syncthreads();
+  const float g = bmax;
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int r = r0 + tid; r < r1; r += blockDim.x) {
+    const float4 v = row_out[r];
+    if (v.x > mi::neg_inf()) acc[0] += exp((double)v.x - (double)g);
+    acc[1] += v.y; acc[2] += v.z; acc[3] += (double)v.w - (double)v.z;
+    if (!(v.y > 0.f)) acc[4] += 1.0;
+  }
+  for (int k = 0; k < 5; ++k) {
+    double a = acc[k];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) sh[k][w] = a;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double t[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k < 5; ++k) for (int i = 0; i < nw; ++i) t[k] += sh[k][i];
+    double* p = part + blockIdx.x * 8;
+    p[0] = g; p[1] = t[0]; p[2] = t[1]; p[3] = t[2]; p[4] = t[3]; p[5] = t[4];
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || tid != 0) return;
+  __threadfence();
+  double gm = -INFINITY;
+  for (unsigned b = 0; b < gridDim.x; ++b) gm = fmax(gm, part[b * 8]);
+  double s = 0, t[4] = {0, 0, 0, 0};
+  for (unsigned b = 0; b < gridDim.x; ++b) {
+    const double* v = part + b * 8;
+    if (isfinite(v[0])) s += v[1] * exp(v[0] - gm);
+    for (int k = 0; k < 4; ++k) t[k] += v[2 + k];
+  }
+  scal[0] = gm; scal[1] = s; scal[2] = t[0]; scal[3] = t[1]; scal[4] = t[2]; scal[5] = t[3]; scal[6] = 0; scal[7] = 0;
+  *ticket = 0u;
 }
 // scal[6] = number of rows whose single-pass reference left the safe window (travels with the rank's scalars)
 __global__ void flag_to_scal_kernel(const int* __restrict__ flag, double* __restrict__ scal, const int* __restrict__ run_if) {
@@ -692,6 +806,11 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int n_par
 }
 
 inline unsigned blocks_for(long long n, int t) { return static_cast<unsigned>(cdiv(n, t)); }
+// grid of a grid-stride elementwise kernel: enough blocks to fill the machine, few enough that a predicated-off launch is cheap
+inline unsigned blocks_capped(long long n, int t) {
+  const long long want = cdiv(n, t), cap = 16LL * num_sms();
+  return static_cast<unsigned>(want < cap ? (want < 1 ? 1 : want) : cap);
+}
 
 // ------------------------------------------------------------------------------------ stages
 // A bf16 operand [rows, D]; split == 2 means a hi/lo pair stored as [hi | lo] in one row, lo starting
@@ -874,6 +993,22 @@ int build_mask(const MaskBuf& b, const int* sid_q, const int* sid_k, long long B
   return MI_OK;
 }
 
+RedScratch take_red(Bump& ws) {
+  RedScratch r;
+  r.part = ws.take<double>(kRedBlocks * 8);
+  r.ticket = ws.take<unsigned>(1);
+  return r;
+}
+// {max, sum-exp, sums} of the per-row statistics -> scal[8]; the ticket is zeroed here (stream ordered), the kernel resets it
+int reduce_rows(const float* row_out, long long rows, double* scal, const RedScratch& red, cudaStream_t stream) {
+  MI_CUDA(cudaMemsetAsync(red.ticket, 0, sizeof(unsigned), stream));
+  const int nb = rows >= 8192 ? kRedBlocks : 1;
+  stats_reduce_mb_kernel<<<nb, 256, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(rows), scal, red.part,
+                                                 red.ticket, t_run_if);
+  MI_LAUNCH_CHECK("stats_reduce_mb_kernel");
+  return MI_OK;
+}
+
 int stats_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
                long long q_offset, long long Bq, long long Bk, long long D, float scale,
                float* row_out, double* scal_out, Bump& ws, cudaStream_t stream) {
@@ -889,6 +1024,7 @@ int stats_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
   float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * mi::kColQuarters * rows_padded);
   float* diag = ws.take<float>(Bq);
+  const RedScratch red = take_red(ws);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
   if (!Q.p || !K.p || !sid_q || !sid_k || !row_out || !scal_out || !(scale > 0.f)) return MI_ERR_BAD_ARG;
@@ -905,14 +1041,59 @@ int stats_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   stats_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(Bq),
                                                               mb.n_same, static_cast<int>(Bk), diag, reinterpret_cast<float4*>(row_out));
   MI_LAUNCH_CHECK("stats_merge_kernel");
-  stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out, t_run_if);
-  MI_LAUNCH_CHECK("stats_reduce_kernel");
+  MI_TRY(reduce_rows(row_out, Bq, scal_out, red, stream));
   return MI_OK;
 }
 
-// Sampled references sit kRefMargin nats above the sample's log-sum-exp (see ref_merge_kernel): a row stays inside the
-// safe window while its true log-sum-exp is within [-45, +93] nats of what the sample saw.
-constexpr float kRefMargin = 24.f;
+// Row AND column statistics of the SQUARE score matrix S = scale Q K^T (same study ids on both sides) from ONE score
+// computation (EpiStatsRC) — the symmetric estimator's statistics for 2 B^2 D instead of 4 B^2 D.
+int stats_rc_impl(const Opnd& Q, const Opnd& K, const int* sid, long long B, long long D, float scale,
+                  float* row_out, double* scal_row, float* col_out, double* scal_col, Bump& ws, cudaStream_t stream) {
+  if (B <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
+  Sched sc;
+  sc.n_mblk = static_cast<int>(cdiv(B, rows_per_mblk()));
+  sc.n_ntile = static_cast<int>(cdiv(B, mi::TILE_N));
+  sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
+  sc.n_ksplit = 1; sc.order = 0;
+  MI_TRY(score_segments(sc, Q, K, D));
+  const long long k_pad = static_cast<long long>(sc.n_ntile) * mi::TILE_N;
+  const int rows_padded = sc.n_mblk * rows_per_mblk();
+  const int n_rb = rows_padded / 32;
+  const MaskBuf mb = take_mask(ws, B, k_pad, B);
+  float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * mi::kColQuarters * rows_padded);
+  float* diag = ws.take<float>(B);
+  float* colpart = ws.take<float>(static_cast<size_t>(n_rb) * k_pad);
+  const RedScratch red = take_red(ws);
+  if (!ws.ok()) return MI_ERR_WORKSPACE;
+  if (ws.dry) return MI_OK;
+  if (!Q.p || !K.p || !sid || !row_out || !scal_row || !col_out || !scal_col || !(scale > 0.f)) return MI_ERR_BAD_ARG;
+  MI_TRY(build_mask(mb, sid, sid, B, B, k_pad, stream));
+  diag_kernel<<<blocks_for(B * 32, 256), 256, 0, stream>>>(Q.p, Q.ld, Q.split, K.p, K.ld, K.split, 0, B, D,
+                                                            round_up(D, kSplitAlign), scale, diag, t_run_if);
+  MI_LAUNCH_CHECK("diag_kernel");
+  mi::EpiStatsRC::Params ep;
+  ep.mask = mi::MaskInfo{mb.excl, mb.n_same, sid, mb.sidk_pad};
+  ep.q_rows = static_cast<int>(B); ep.k_cols = static_cast<int>(B);
+  ep.scale = scale; ep.part = part; ep.rows_padded = rows_padded;
+  ep.colpart = colpart; ep.col_pitch = k_pad;
+  MI_TRY(launch_engine<mi::EpiStatsRC>(MapSpec{Q.p, B, opnd_k_extent(Q, D), Q.ld}, MapSpec{K.p, B, opnd_k_extent(K, D), K.ld},
+                                       sc, ep, stream));
+  stats_merge_kernel<<<blocks_for(B, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(B),
+                                                             mb.n_same, static_cast<int>(B), diag, reinterpret_cast<float4*>(row_out));
+  MI_LAUNCH_CHECK("stats_merge_kernel");
+  MI_TRY(reduce_rows(row_out, B, scal_row, red, stream));
+  col_merge_kernel<<<static_cast<unsigned>(cdiv(B, 32)), dim3(32, 8), 0, stream>>>(colpart, n_rb, k_pad, static_cast<int>(B), mb.n_same,
+                                                                                    static_cast<int>(B), diag, reinterpret_cast<float4*>(col_out));
+  MI_LAUNCH_CHECK("col_merge_kernel");
+  MI_TRY(reduce_rows(col_out, B, scal_col, red, stream));
+  return MI_OK;
+}
+
+// Sampled references sit kRefMargin nats above the sample's log-sum-exp (see ref_merge_kernel).  The sample is a subset of
+// the row's columns, so the row's true log-sum-exp can only lie ABOVE the sample's: with the margin a row stays inside the
+// safe window while its true log-sum-exp is up to ~117 nats above what the sample saw (row sum <= 1e30), and entries more
+// than 87 - 48 = 39 nats below the row's log-sum-exp (relative weight < 1e-17) flush to zero.
+constexpr float kRefMargin = 48.f;
 
 // Column sample of the single pass's references: stride such that about g_ref_sample_cols columns are scored per row;
 // 1 (every column: exact references, the pass can never leave the safe window) when the sample would not be cheaper
@@ -970,7 +1151,8 @@ int ref_sample_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* s
                                                             diag_out, include_diag, stride > 1 ? kRefMargin : 0.f, ref_out, pr);
   MI_LAUNCH_CHECK("ref_merge_kernel");
   if (lam_out != nullptr) {
-    max_reduce_kernel<<<1, 1024, 0, stream>>>(ref_out, Bq, lam_out, pr);
+    // lambda = the largest SAMPLE log-sum-exp (the margin taken out again): e^{S - lambda} is then centred on the global scale
+    max_reduce_kernel<<<1, 1024, 0, stream>>>(ref_out, Bq, lam_out, stride > 1 ? kRefMargin : 0.f, pr);
     MI_LAUNCH_CHECK("max_reduce_kernel");
   }
   return MI_OK;
@@ -1046,7 +1228,8 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
     ep.q_offset = q_offset + r0; ep.scale = scale;
     ep.refq = use_q ? refq + r0 : nullptr; ep.ln_wq = use_q ? logf(wq) : 0.f; ep.use_q = use_q ? 1 : 0;
     ep.refk2 = refk2; ep.use_k = use_k ? 1 : 0; ep.include_diag = include_diag;
-    ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
+    MI_TRY(make_tmap_store32(&ep.tmap_p, P, rows, pitch, pitch));
+    ep.lo_col0 = strict ? static_cast<int>(k_pad) : 0;
     ep.sum_part = nullptr; ep.rows_padded = 0;
     MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
                                         MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
@@ -1154,6 +1337,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   // (x3: the first panel may be written by up to three launches — own columns first, the rest once K has arrived)
   const size_t part_slices = static_cast<size_t>(max_split > 64 ? 64 : max_split) * mi::kColQuarters;
   float* part = ws.take<float>(3 * part_slices * panel_rows);
+  const RedScratch red = take_red(ws);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
   if (!Q.p || !K.p || !sid_q || !sid_k || !ref || !diag || !row_out || !oq_raw || !wrow || !flag_out || !(scale > 0.f) ||
@@ -1194,7 +1378,8 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
       ep.q_offset = q_offset + r0; ep.scale = scale;
       ep.refq = ref + r0; ep.ln_wq = 0.f; ep.use_q = 1;
       ep.refk2 = nullptr; ep.use_k = 0; ep.include_diag = include_diag;
-      ep.P = P; ep.P_lo = strict ? P + k_pad : nullptr; ep.pitch = pitch;
+      MI_TRY(make_tmap_store32(&ep.tmap_p, P, rows, pitch, pitch));
+      ep.lo_col0 = strict ? static_cast<int>(k_pad) : 0;
       ep.sum_part = part + static_cast<size_t>(n_part) * rows_padded; ep.rows_padded = rows_padded;
       MI_TRY(launch_engine<mi::EpiPStore>(MapSpec{Qe.p + r0 * Qe.ld, rows, opnd_k_extent(Qe, D), Qe.ld},
                                           MapSpec{Ke.p, Bk, opnd_k_extent(Ke, D), Ke.ld}, sc, ep, stream));
@@ -1217,8 +1402,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
     if (scal_out != nullptr && r0 + panel_rows >= Bq) {
       // every row's statistics are final once the last panel's sums are merged: reduce them NOW (before the two
       // contractions of this panel) so a caller can exchange the scalars of the loss while the GEMMs still run
-      stats_reduce_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(Bq), scal_out, pr);
-      MI_LAUNCH_CHECK("stats_reduce_kernel");
+      MI_TRY(reduce_rows(row_out, Bq, scal_out, red, stream));
       flag_to_scal_kernel<<<1, 1, 0, stream>>>(flag_out, scal_out, pr);
       MI_LAUNCH_CHECK("flag_to_scal_kernel");
       if (ev_after_scal != nullptr) MI_CUDA(cudaEventRecord(ev_after_scal, stream));
@@ -1231,7 +1415,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
     Bump none(nullptr, 0, false);
     // (2) Ok_raw += P~^T (w Q)[panel]: contraction over the panel rows, P~ read MN-major
     if (ok_raw) {
-      scale_rows_kernel<<<blocks_for(rows * D / 8, 256), 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qs,
+      scale_rows_kernel<<<blocks_capped(rows * D / 8, 256), 256, 0, stream>>>(Q.p + r0 * Q.ld, Q.ld, Q.split, Dp, wrow + r0, Qs,
                                                                           strict ? Qs + Dp : nullptr, ld_qs, rows, D, pr);
       MI_LAUNCH_CHECK("scale_rows_kernel");
       GemmArgs g;
@@ -1403,7 +1587,7 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
         MI_LAUNCH_CHECK("loss_finalize_kernel");
       }
       // dT = inv_tau (c G~ Y - Y/B): fp32 (dot critic: this is dX) or the bf16 (hi/lo) operand of the dX / dW GEMMs
-      finalize_q_kernel<<<blocks_for(B * D / 8, 256), 256, 0, stream>>>(oq_raw, D, B, ref_r, sp_wrow, lse_f, dv_like ? 1 : 0, inv_tau, gam,
+      finalize_q_kernel<<<blocks_capped(B * D / 8, 256), 256, 0, stream>>>(oq_raw, D, B, ref_r, sp_wrow, lse_f, dv_like ? 1 : 0, inv_tau, gam,
                                                                         Y, D, 1, Dp, bilinear ? nullptr : dX, bilinear ? dT16 : nullptr,
                                                                         (bilinear && tsplit == 2) ? dT16 + Dp : nullptr, ldT, t_run_if);
       MI_LAUNCH_CHECK("finalize_q_kernel");
@@ -1428,9 +1612,12 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     }
   }
   if (!single || ws.dry) {        // statistics pass(es) + gradient pass with exact references (planning covers both paths)
-    MI_TRY(stats_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
+    if (sym) {      // rows and columns from one score computation
+      MI_TRY(stats_rc_impl(To, Yo, sid, B, D, inv_tau, rows_r, scal_r, rows_c, scal_c, ws, stream));
+    } else {
+      MI_TRY(stats_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
+    }
     ws.release(mk);
-    if (sym) { MI_TRY(stats_impl(Yo, To, sid, sid, 0, B, B, D, inv_tau, rows_c, scal_c, ws, stream)); ws.release(mk); }
     if (!ws.dry) {
       loss_finalize_kernel<<<1, 32, 0, stream>>>(scal_r, scal_c, B, estimator, loss_out, lse_f, nullptr, nullptr);
       MI_LAUNCH_CHECK("loss_finalize_kernel");
@@ -1487,6 +1674,11 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
       if (tsplit == 2) { g.k_blocks = 2 * kb; g.b_noff[1] = static_cast<int>(Dp); }
       const long long tiles = cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N);
       long long ks = cdiv(num_pairs(), tiles);
+      // The batch is the contraction dimension: B / 16 accumulating MMAs per output element.  The tensor core's fp32
+      // accumulation of such a long, heavily cancelling sum (dW is tiny against the sum of its terms' magnitudes) loses
+      // ~1e-3 of the result at B = 65536 with a few hundred K blocks per accumulator (measured: tests/test_gpu_parity.py
+      // full-size case); strict mode therefore cuts the chains to <= 16 K blocks and sums the partials in a separate pass.
+      if (strict) ks = std::max<long long>(ks, cdiv(g.k_blocks, 16));
       if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
       if (ks < 1) ks = 1;
       g.ksplit = static_cast<int>(ks);
@@ -1704,7 +1896,7 @@ int mi_row_norm_max(const void* A, int64_t lda, int a_split, int64_t rows, int64
   row_norm_kernel<<<blocks_for(rows * 32, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda, a_split == 2 ? 2 : 1,
                                                                    round_up(D, kSplitAlign), rows, D, norm_out);
   MI_LAUNCH_CHECK("row_norm_kernel");
-  max_reduce_kernel<<<1, 1024, 0, stream>>>(norm_out, rows, max_out, nullptr);
+  max_reduce_kernel<<<1, 1024, 0, stream>>>(norm_out, rows, max_out, 0.f, nullptr);
   MI_LAUNCH_CHECK("max_reduce_kernel");
   return MI_OK;
 }
@@ -1749,7 +1941,7 @@ int mi_single_finalize_q(const float* oq_raw, int64_t rows, int64_t D, const flo
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long long Dp = round_up(D, kSplitAlign);
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
-  finalize_q_kernel<<<blocks_for(rows * D / 8, 256), 256, 0, stream>>>(oq_raw, D, rows, ref, wrow, lse, dv_like, alpha, gamma,
+  finalize_q_kernel<<<blocks_capped(rows * D / 8, 256), 256, 0, stream>>>(oq_raw, D, rows, ref, wrow, lse, dv_like, alpha, gamma,
                                                                        static_cast<const __nv_bfloat16*>(kdiag), ldk, k_split == 2 ? 2 : 1, Dp,
                                                                        out_f32, ob, (ob && out_split == 2) ? ob + Dp : nullptr, ld16, nullptr);
   MI_LAUNCH_CHECK("finalize_q_kernel");

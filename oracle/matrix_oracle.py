@@ -57,6 +57,24 @@ def create_mi_pairs(X: torch.Tensor, Y: torch.Tensor, study_id: Sequence) -> tor
     return torch.cat((pos, neg), 0)
 
 
+def create_mi_pairs_catloop(X: torch.Tensor, Y: torch.Tensor, study_id: Sequence) -> torch.Tensor:
+    """main_utils.py:80-110 AS THE REFERENCE EXECUTES IT: the pair tensor grows by one ``torch.cat`` of the whole tensor per
+    negative pair (main_utils.py:106-108), i.e. O(B^2) Python iterations and O(B^4 D) bytes copied.  Same result as
+    ``create_mi_pairs`` above (tests prove it); kept so that ``bench.py`` can time BASELINE config 1 the way the reference
+    spends its time (>= 87 % of the reference's step is this loop)."""
+    B = len(study_id)
+    pairs = torch.cat((X, Y), 1)                                   # :93 the B matched rows
+    for gap in range(B - 1):                                       # :99
+        for i in range(B):                                         # :100
+            j = i + gap + 1
+            if j >= B:
+                j -= B
+            if study_id[i] != study_id[j]:                         # :105
+                row = torch.cat((X[i], Y[j])).reshape(1, -1)       # :106-107
+                pairs = torch.cat((pairs, row), 0)                 # :108 re-copies everything built so far
+    return pairs
+
+
 def dv_bound_loss(logits: torch.Tensor, pos_size: int) -> torch.Tensor:
     """mi_critics.py:3-12.  ``log N_neg`` is evaluated in float32 on the host
     (mi_critics.py:10: ``torch.log(torch.tensor(n).float())``) — mirrored."""
@@ -205,13 +223,14 @@ def critic_loss(X, Y, study_id, W=None, inv_tau: float = 1.0, estimator: str = "
 
 
 def critic_loss_pair_form(X, Y, study_id, W=None, inv_tau: float = 1.0, estimator: str = "dv",
-                          dtype=torch.float64):
+                          dtype=torch.float64, catloop: bool = False):
     """The reference's three-call sequence (main_utils.py:220-226) with the
-    separable critic in the discriminator slot, differentiated by autograd."""
+    separable critic in the discriminator slot, differentiated by autograd.
+    ``catloop``: build the pair tensor with the reference's own growing-``torch.cat`` loop."""
     X = X.detach().to("cpu", dtype).requires_grad_(True)
     Y = Y.detach().to("cpu", dtype).requires_grad_(True)
     Wd = None if W is None else W.detach().to("cpu", dtype).requires_grad_(True)
-    rows = create_mi_pairs(X, Y, list(study_id))
+    rows = (create_mi_pairs_catloop if catloop else create_mi_pairs)(X, Y, list(study_id))
     logits = pair_logits_separable(rows, Wd, inv_tau)
     fn = {"dv": dv_bound_loss, "infonce": infonce_bound_loss}[estimator]
     loss = fn(logits, len(study_id))

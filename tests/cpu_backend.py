@@ -82,9 +82,9 @@ def score_ref_sample(Q, K, sid_q, sid_k, q_offset, scale, include_diag, col0=0, 
     lse = torch.logsumexp(torch.where(M[:, cols], S[:, cols], torch.full_like(S[:, cols], float("-inf"))), 1)
     diag = S[i, j]
     ref = torch.logaddexp(lse, diag) if include_diag else torch.where(torch.isfinite(lse), lse, diag)
-    if stride > 1:
-        ref = ref + 24.0                                  # kRefMargin of the library
-    return {"ref": ref, "diag": diag, "lam": ref.max().reshape(1), "stride": stride}
+    margin = 48.0 if stride > 1 else 0.0                   # kRefMargin of the library
+    ref = ref + margin
+    return {"ref": ref, "diag": diag, "lam": (ref.max() - margin).reshape(1), "stride": stride}
 
 
 def score_single_pass(Q, K, sid_q, sid_k, q_offset, scale, include_diag, precision, inv_bg, ref, lam, diag, want_k=True,
@@ -108,7 +108,7 @@ def score_single_pass(Q, K, sid_q, sid_k, q_offset, scale, include_diag, precisi
         lse_all = torch.logaddexp(lse_neg, diag.double())
         d = ref - lam.double().reshape(())
         wrow = torch.exp(d)
-        bad = bad | ~(d <= 60.0)
+        bad = bad | ~(d <= 80.0)
     rows = torch.stack([lse_neg, n_neg, diag.double(), lse_all], 1)
     fin = torch.isfinite(lse_neg)
     m = lse_neg[fin].max() if fin.any() else torch.tensor(float("-inf"), dtype=torch.float64)

@@ -251,3 +251,14 @@ def test_merge_scalars_matches_single_block():
     out = mdist.merge_scalars(torch.stack(parts))
     assert abs(float(out["lse_neg"]) - float(torch.logsumexp(lse, 0))) < 1e-12
     assert float(out["n_neg"]) == 40 and float(out["diag_sum"]) == 4
+
+
+def test_package_synthetic_generator_equals_the_oracles():
+    """bench.py / examples use mi_b200.synthetic (the product never imports oracle/); the tests use the oracle's copy."""
+    from mi_b200 import synthetic
+    from oracle import matrix_oracle as mo
+    for bil in (False, True):
+        a = synthetic.synthetic_embeddings(96, 40, seed=5, dup_frac=0.1, bilinear=bil)
+        b = mo.synthetic_embeddings(96, 40, seed=5, dup_frac=0.1, bilinear=bil)
+        for x, y in zip(a, b):
+            assert (x is None and y is None) or torch.equal(x, y)

@@ -180,3 +180,13 @@ def test_chunked_oracle_equals_matrix_oracle(est, critic):
     for k in ("dX", "dY") + (("dW",) if critic == "bilinear" else ()):
         err = float((got[k].double() - ref[k]).abs().max() / ref[k].abs().max())
         assert err < 2e-5, (k, err)                       # fp32 matmuls against the fp64 matrix form
+
+
+def test_catloop_pair_construction_equals_vectorised():
+    """The reference's growing-torch.cat pair construction (timed by bench.py for BASELINE config 1) == the oracle's gather."""
+    X, Y, sid, _ = mo.synthetic_embeddings(12, 8, seed=3, dup_frac=0.3, bilinear=False)
+    ids = [str(int(s)) for s in sid]
+    assert torch.equal(mo.create_mi_pairs_catloop(X, Y, ids), mo.create_mi_pairs(X, Y, ids))
+    a = mo.critic_loss_pair_form(X, Y, ids, None, 0.3, "dv", catloop=True)
+    b = mo.critic_loss_pair_form(X, Y, ids, None, 0.3, "dv")
+    assert torch.equal(a["loss"], b["loss"]) and torch.allclose(a["dX"], b["dX"], rtol=0, atol=1e-15)
