@@ -522,7 +522,7 @@ __global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, lo
   for (long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; idx < rows * D;
        idx += (long long)gridDim.x * blockDim.x * 8) {
   const long long i = idx / D, d = idx - i * D;          // D % 8 == 0
-  const float c = dv_like ? expf(ref[i] - lse[0]) : wrow[i];
+  const float c = dv_like ? expf(ref[i] - lse[0]) : (wrow != nullptr ? wrow[i] : 1.f);
   const uint4 kv = *reinterpret_cast<const uint4*>(kdiag + i * ldk + d);
   const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
   float kd[8];
@@ -1171,6 +1171,14 @@ long long panel_mblks(long long Bq, long long Bk, long long D, int precision) {
   return mb;
 }
 
+// The tensor core adds into its fp32 accumulator with truncation, not round-to-nearest: a chain of n accumulating MMAs
+// carries a systematic relative bias of ~n * 2^-25 (measured at B = 65536: 12288 MMAs per output element of the
+// dS x Y contraction in strict mode left a 2e-4 bias in dT, which the batch-coherent sum dW = X^T dT amplified to 4e-3).
+// Strict ("fp32-accumulate") mode therefore cuts every long contraction into chains of at most kStrictChainBlocks K blocks
+// (split-K: partial tiles summed by a separate fp32 round-to-nearest pass).  Fast mode keeps one chain (bound 1e-2).
+constexpr int kStrictChainBlocks = 128;
+inline int strict_ksplit(int k_blocks) { return static_cast<int>(cdiv(k_blocks, kStrictChainBlocks)); }
+
 struct GradOut {            // fp32 and/or bf16 (split == 2: [hi | lo] rows) destination
   float* f32 = nullptr; long long ld = 0;
   __nv_bfloat16* bf16 = nullptr; long long ld16 = 0; int split = 1;
@@ -1200,6 +1208,11 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
   const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
   float* refk2 = ws.take<float>(k_pad);
   bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
+  // strict: the Oq contraction runs as short split-K chains into a raw fp32 panel, finished by an elementwise pass
+  const int oq_ksplit = strict ? strict_ksplit(kp * (k_hl ? 3 : 2)) : 1;
+  const size_t kpart_elems = oq_ksplit > 1 ? static_cast<size_t>(oq_ksplit) * panel_rows * round_up(D, 4) : 0;
+  float* kpart = oq_ksplit > 1 ? ws.take<float>(kpart_elems) : nullptr;
+  float* oq_rawp = oq_ksplit > 1 ? ws.take<float>(static_cast<size_t>(panel_rows) * D) : nullptr;
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
   if (!Q.p || !K.p || !sid_q || !sid_k || (!oq.f32 && !oq.bf16 && !ok)) return MI_ERR_BAD_ARG;
@@ -1271,6 +1284,19 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
         g.k_blocks = 2 * kp; g.a_seg[1] = kp;
         if (k_hl) { g.k_blocks = 3 * kp; g.b_noff[2] = static_cast<int>(Dp); }
       }
+      if (oq_ksplit > 1) {
+        g.ksplit = oq_ksplit;
+        g.out_f32 = oq_rawp; g.ld_out = D;
+        Bump kws(kpart, kpart_elems * sizeof(float), false);
+        const int st = run_gemm(g, kws, stream);
+        t_reserve_sms = 0;
+        MI_TRY(st);
+        bf* o16 = oq.bf16 ? oq.bf16 + r0 * oq.ld16 : nullptr;
+        finalize_q_kernel<<<blocks_capped(rows * D / 8, 256), 256, 0, stream>>>(
+            oq_rawp, D, rows, nullptr, nullptr, nullptr, 0, alpha, gamma, K.p + (q_offset + r0) * K.ld, K.ld, k_hl ? 2 : 1, Dp,
+            oq.f32 ? oq.f32 + r0 * oq.ld : nullptr, o16, (o16 && oq.split == 2) ? o16 + Dp : nullptr, oq.ld16, t_run_if);
+        MI_LAUNCH_CHECK("finalize_q_kernel");
+      } else {
       g.alpha = alpha; g.gamma = gamma;
       if (gamma != 0.f) {                            // - gamma K[q_offset + q]
         g.sub = K.p + (q_offset + r0) * K.ld; g.ld_sub = K.ld;
@@ -1282,6 +1308,7 @@ int grad_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
       const int st = run_gemm(g, none, stream);
       t_reserve_sms = 0;
       MI_TRY(st);
+      }
     }
   }
   return MI_OK;
@@ -1338,6 +1365,9 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   const size_t part_slices = static_cast<size_t>(max_split > 64 ? 64 : max_split) * mi::kColQuarters;
   float* part = ws.take<float>(3 * part_slices * panel_rows);
   const RedScratch red = take_red(ws);
+  const int oq_ksplit = strict ? strict_ksplit(kp * (k_hl ? 3 : 2)) : 1;     // see kStrictChainBlocks
+  const size_t kpart_elems = oq_ksplit > 1 ? static_cast<size_t>(oq_ksplit) * panel_rows * round_up(D, 4) : 0;
+  float* kpart = oq_ksplit > 1 ? ws.take<float>(kpart_elems) : nullptr;
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
   if (!Q.p || !K.p || !sid_q || !sid_k || !ref || !diag || !row_out || !oq_raw || !wrow || !flag_out || !(scale > 0.f) ||
@@ -1454,7 +1484,9 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
         if (k_hl) { g.k_blocks = 3 * kp; g.b_noff[2] = static_cast<int>(Dp); }
       }
       g.out_f32 = oq_raw + r0 * D; g.ld_out = D;
-      const int st = run_gemm(g, none, stream);
+      g.ksplit = oq_ksplit;
+      Bump kws(kpart, kpart_elems * sizeof(float), false);
+      const int st = run_gemm(g, oq_ksplit > 1 ? kws : none, stream);
       t_reserve_sms = 0;
       MI_TRY(st);
     }
