@@ -241,6 +241,12 @@ def run_ours(a):
     from mi_b200 import dist as mdist
     lib = _lib.load()
 
+    # the clock sampler starts HERE, seconds before the timed region: nvidia-smi's own start-up (NVML attaching to every GPU
+    # of the box) stalls the GPUs for ~100 ms once — measured as a one-step spike when it was started right before the timing
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get('MI_BENCH_NOSMI'):
+        sampler.start()
+
     B, D = a.batch, a.dim
     assert B % world == 0
     Bl = B // world
@@ -265,7 +271,8 @@ def run_ours(a):
         if world == 1:
             return ops.critic_loss_fwd_bwd(Xd, Yd, Wd, sd32, a.estimator, a.precision, inv_tau, True, out=out_bufs)
         # check_guard=False: no host read inside the timed region (the guard count is checked once after it)
-        return mdist.sharded_critic_loss_fwd_bwd(Xd, Yd, Wd, sd32, a.estimator, a.precision, inv_tau, True, check_guard=False)
+        return mdist.sharded_critic_loss_fwd_bwd(Xd, Yd, Wd, sd32, a.estimator, a.precision, inv_tau, True,
+                                                 check_guard=bool(os.environ.get("MI_BENCH_CHECK_GUARD")))
 
     def sync_all():
         if world > 1:
@@ -296,10 +303,6 @@ def run_ours(a):
     for _ in range(max(3, a.warmup)):
         step_device()
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0 and not os.environ.get('MI_BENCH_NOSMI'):
-        sampler.start()
-        time.sleep(0.25)
     lib.mi_set_profiling(0 if os.environ.get('MI_BENCH_NOPROF') else 1)
     ms = (ctypes.c_double * 3)()
     cnt = (ctypes.c_int64 * 3)()

@@ -82,6 +82,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--seq", type=int, default=128)
     ap.add_argument("--bert-layers", type=int, default=12)
+    ap.add_argument("--throughput-steps", type=int, default=10,
+                    help="after the instrumented steps: this many steps WITHOUT any host synchronisation inside the step "
+                         "(the loss of step n is read while step n+1 runs: deferred logging instead of main_utils.py:233's "
+                         "per-step .item())")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -137,10 +141,41 @@ def main():
         if rank == 0:
             print(f"step {step}: loss {lv:.5f}  step {1e3 * (t3 - t0):.1f} ms  (encoders fwd {1e3 * (t1 - t0):.1f}, "
                   f"critic+loss fwd(+fused bwd) {1e3 * (t2 - t1):.2f})", flush=True)
+    # ---- throughput: the same step with NO host synchronisation inside it (the reference's three per-step syncs —
+    # mi_critics.py:10 H2D of log N, main_utils.py:233 loss.item(), and the adapter's optional no-negatives check — are gone;
+    # the sharded critic's only host read is its guard count, which waits for the score tiles, not for the step)
+    tput = None
+    if a.throughput_steps > 0:
+        critic.check_negatives = False
+        img = torch.rand(B, 1, 256, 256, generator=g).to(dev)
+        ids = torch.randint(1000, 30000, (B, a.seq), generator=g).to(dev)
+        mask, seg = torch.ones_like(ids), torch.zeros_like(ids)
+        study = torch.arange(B) + rank * B
+        study_list = study.tolist()
+        pending, logged = None, []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for step in range(a.throughput_steps):
+            img_opt.zero_grad(); txt_opt.zero_grad(); mi_opt.zero_grad()
+            emb_img, emb_txt = img_enc(img), txt_enc(ids, mask, seg)
+            if world > 1:
+                loss = mi_b200.sharded_mi_loss(emb_img, emb_txt, critic, study, a.estimator)
+            elif a.critic == "fused":
+                loss = mi_critic(critic(mi_b200.create_mi_pairs(emb_img, emb_txt, study_list, dev)), B, dev)
+            else:
+                loss = mi_critic(critic(mi_b200.create_mi_pairs_tensor(emb_img, emb_txt, study_list, dev)), B, dev)
+            loss.sum().backward()
+            mi_opt.step(); img_opt.step(); txt_opt.step(); sched.step()
+            if pending is not None:
+                logged.append(float(pending))            # the PREVIOUS step's loss: already on its way, no stall
+            pending = loss.detach().sum().to("cpu", non_blocking=True)
+        torch.cuda.synchronize()
+        tput = (time.perf_counter() - t0) / a.throughput_steps
     if rank == 0:
         print(f"RESULT critic={a.critic} world={world} batch/gpu={B} global_pairs={(B * world) ** 2} "
               f"step_ms={1e3 * sum(times) / len(times):.1f} critic_ms={1e3 * sum(crit_times) / len(crit_times):.2f} "
-              f"samples/s={B * world * len(times) / sum(times):.0f}", flush=True)
+              f"samples/s={B * world * len(times) / sum(times):.0f}"
+              + ("" if tput is None else f"  | no-sync loop: step_ms={1e3 * tput:.1f} samples/s={B * world / tput:.0f}"), flush=True)
 
 
 if __name__ == "__main__":

@@ -558,22 +558,36 @@ __global__ void finalize_q_kernel(const float* __restrict__ raw, long long D, lo
   }
   }
 }
-// Ok[k,:] = alpha (kappa Ok[k,:] - gamma [0 <= k-q_offset < Bq] Q[k-q_offset,:]),  kappa = e^{lambda - LSE} (DV) or 1
+// Ok[k,:] = alpha (kappa Ok[k,:] - gamma [0 <= k-q_offset < Bq] Q[k-q_offset,:]),  kappa = e^{lambda - LSE} (DV) or 1.  8 elements / thread
 __global__ void finalize_k_kernel(float* __restrict__ ok, long long D, long long Bk, const float* __restrict__ lambda,
                                   const float* __restrict__ lse, int dv_like, float alpha, float gamma,
                                   const __nv_bfloat16* __restrict__ Q, long long ldq, int q_split, long long Dp,
                                   long long q_offset, long long Bq) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= Bk * D) return;
-  const long long k = idx / D, d = idx - k * D;
   const float kappa = dv_like ? expf(lambda[0] - lse[0]) : 1.f;
-  float qd = 0.f;
-  const long long q = k - q_offset;
-  if (q >= 0 && q < Bq) {
-    qd = __bfloat162float(Q[q * ldq + d]);
-    if (q_split == 2) qd += __bfloat162float(Q[q * ldq + Dp + d]);
+  for (long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; idx < Bk * D;
+       idx += (long long)gridDim.x * blockDim.x * 8) {
+    const long long k = idx / D, d = idx - k * D;          // D % 8 == 0
+    float qd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long q = k - q_offset;
+    if (q >= 0 && q < Bq) {
+      const uint4 hv = *reinterpret_cast<const uint4*>(Q + q * ldq + d);
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { qd[2 * j] = __uint_as_float(hw[j] << 16); qd[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u); }
+      if (q_split == 2) {
+        const uint4 lv = *reinterpret_cast<const uint4*>(Q + q * ldq + Dp + d);
+        const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { qd[2 * j] += __uint_as_float(lw[j] << 16); qd[2 * j + 1] += __uint_as_float(lw[j] & 0xffff0000u); }
+      }
+    }
+    float4 a = *reinterpret_cast<const float4*>(ok + idx), b = *reinterpret_cast<const float4*>(ok + idx + 4);
+    a.x = alpha * (kappa * a.x - gamma * qd[0]); a.y = alpha * (kappa * a.y - gamma * qd[1]);
+    a.z = alpha * (kappa * a.z - gamma * qd[2]); a.w = alpha * (kappa * a.w - gamma * qd[3]);
+    b.x = alpha * (kappa * b.x - gamma * qd[4]); b.y = alpha * (kappa * b.y - gamma * qd[5]);
+    b.z = alpha * (kappa * b.z - gamma * qd[6]); b.w = alpha * (kappa * b.w - gamma * qd[7]);
+    *reinterpret_cast<float4*>(ok + idx) = a; *reinterpret_cast<float4*>(ok + idx + 4) = b;
   }
-  ok[idx] = alpha * (kappa * ok[idx] - gamma * qd);
 }
 
 // merge the (split, half) partials of one row -> {lse_neg, n_neg, diag, lse_all}
@@ -1984,7 +1998,8 @@ int mi_single_finalize_k(float* ok, int64_t rows, int64_t D, const float* lambda
   MI_TRY(device_check());
   if (!ok || !qdiag || rows <= 0 || D <= 0 || (dv_like && (!lse || !lambda))) return MI_ERR_BAD_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  finalize_k_kernel<<<blocks_for(rows * D, 256), 256, 0, stream>>>(ok, D, rows, lambda, lse, dv_like, alpha, gamma,
+  if ((D % 8) != 0) return MI_ERR_BAD_ARG;
+  finalize_k_kernel<<<blocks_capped(rows * D / 8, 256), 256, 0, stream>>>(ok, D, rows, lambda, lse, dv_like, alpha, gamma,
                                                                    static_cast<const __nv_bfloat16*>(qdiag), ldq, q_split == 2 ? 2 : 1,
                                                                    round_up(D, kSplitAlign), 0, rows);
   MI_LAUNCH_CHECK("finalize_k_kernel");

@@ -114,14 +114,10 @@ def _reduce_scatter_rows(part, Bl, off, world, group, nccl, ev):
         recv = torch.empty_like(part)
         with torch.cuda.stream(side):
             work = dist.all_to_all_single(recv, part, group=group, async_op=True)
-        part.record_stream(side)
-        recv.record_stream(side)
         return _A2ASum(recv.view(world, Bl, part.shape[1])), work
     out = torch.empty((Bl, part.shape[1]), dtype=part.dtype, device=part.device)
     with torch.cuda.stream(side):
         work = dist.reduce_scatter_tensor(out, part, op=dist.ReduceOp.SUM, group=group, async_op=True)
-    part.record_stream(side)
-    out.record_stream(side)
     return out, work
 
 
@@ -180,11 +176,11 @@ def _single_pass_step(backend, T_local, Xb, Yb, Wb, Y_all, sid_loc, sid_all, off
                 gh = _guard_buffer(scal.device)
                 gh.copy_(out["guard"].reshape(1), non_blocking=True)
             ev_m.record(side)
-        main = torch.cuda.current_stream()
-        scal.record_stream(side)
-        scal_all.record_stream(side)
-        for t in list(out.values()):          # allocated on the side stream, consumed on the compute stream
-            t.record_stream(main)
+        # (no record_stream on the large buffers of this module: the compute stream waits for every side-stream / NCCL
+        #  consumer of them before the call returns, so handing them back to the caching allocator is stream ordered — and
+        #  the allocator reuses the same blocks step after step instead of growing)
+        for t in list(out.values()):          # a few scalars allocated under the side stream's context and consumed on the
+            t.record_stream(torch.cuda.current_stream())      # compute stream, which outlives the side stream's use
         if check_guard:
             ev_m.synchronize()
             if float(gh[0]) != 0.0:
@@ -275,8 +271,9 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
             lam = lam.clone()
             dist.all_reduce(lam, op=dist.ReduceOp.MAX, group=group)
     Y_all, ev_y = Yb, None
-    # (experiment knob, off by default: correct on NCCL — scripts/dist_check.py)
-    own_first = nccl and single and os.environ.get("MI_OWN_COLUMNS_FIRST", "0") == "1"
+    # the rank's own column block is scored under the all-gather of the other ranks' text embeddings (MI_OWN_COLUMNS_FIRST=0
+    # switches this off for A/B runs)
+    own_first = nccl and single and os.environ.get("MI_OWN_COLUMNS_FIRST", "1") == "1"
     if world > 1:
         Y_all = torch.empty((Bg, D), dtype=Yb.dtype, device=Yb.device)
         if own_first:
@@ -294,7 +291,6 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
                 y_work.wait()
                 ev_y = torch.cuda.Event()
                 ev_y.record(side)
-            Y_all.record_stream(side)
         else:
             y_work.wait()
     T_all = _gather_mat(T_local, world, group) if sym else None

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import mi_b200  # noqa
 from mi_b200 import dist as mdist
-from oracle import matrix_oracle as mo
+from mi_b200 import synthetic as mo
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 1024

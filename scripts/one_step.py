@@ -10,9 +10,6 @@ sys.path.insert(0, ROOT)
 import mi_b200  # noqa
 from mi_b200 import ops, _lib
 
-if os.environ.get("MI_MN") == "0":      # A/B: transposed K-major copies instead of MN-major operand reads
-    _lib.load().mi_set_mn_operands(0)
-
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 est = sys.argv[3] if len(sys.argv) > 3 else "dv"
