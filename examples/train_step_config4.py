@@ -153,6 +153,7 @@ def main():
         study = torch.arange(B) + rank * B
         study_list = study.tolist()
         pending, logged = None, []
+        loss_pin = [torch.zeros(1).pin_memory() for _ in range(2)]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for step in range(a.throughput_steps):
@@ -166,9 +167,13 @@ def main():
                 loss = mi_critic(critic(mi_b200.create_mi_pairs_tensor(emb_img, emb_txt, study_list, dev)), B, dev)
             loss.sum().backward()
             mi_opt.step(); img_opt.step(); txt_opt.step(); sched.step()
-            if pending is not None:
-                logged.append(float(pending))            # the PREVIOUS step's loss: already on its way, no stall
-            pending = loss.detach().sum().to("cpu", non_blocking=True)
+            if pending is not None:                      # the PREVIOUS step's loss: (nearly) there already, no stall of this step
+                pending[1].synchronize()
+                logged.append(float(pending[0]))
+            slot = loss_pin[step & 1]
+            slot.copy_(loss.detach().reshape(-1)[:1], non_blocking=True)
+            ev = torch.cuda.Event(); ev.record()
+            pending = (slot, ev)
         torch.cuda.synchronize()
         tput = (time.perf_counter() - t0) / a.throughput_steps
     if rank == 0:

@@ -38,7 +38,9 @@ enum mi_status {
   MI_ERR_WORKSPACE = -2,      /* workspace too small: call the matching *_workspace_bytes */
   MI_ERR_CUDA = -3,           /* a CUDA runtime / driver call failed (see mi_last_cuda_error) */
   MI_ERR_NO_DEVICE = -4,      /* no sm_100 device: there is NO CPU fallback */
-  MI_ERR_NO_NEGATIVES = -5    /* reported by the host layer when N_neg == 0 (reference yields nan/-inf) */
+  MI_ERR_NO_NEGATIVES = -5,   /* reported by the host layer when N_neg == 0 (reference yields nan/-inf) */
+  MI_GUARD_TRIPPED = 1        /* mi_sharded_critic_loss_fwd_bwd only: the sampled references left the safe window on some rank
+                                 (every rank returns this together); the outputs are NOT valid — repeat on the exact path */
 };
 
 enum mi_critic { MI_CRITIC_DOT = 0, MI_CRITIC_BILINEAR = 1 };
@@ -151,6 +153,7 @@ int mi_score_ref_sample(const void* Q, int64_t ldq, int q_split, const void* K, 
                         const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
                         int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag,
                         int64_t col0, int64_t n_cols, int64_t stride,
+                        int subset /* 1: K holds only PART of the row's columns (a rank's own block): margin even at stride 1 */,
                         float* ref_out /*[Bq]*/, float* diag_out /*[Bq]*/, float* lambda_out /*[1] or NULL*/,
                         void* workspace, size_t workspace_bytes, mi_stream_t stream);
 size_t mi_score_single_pass_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision);
@@ -211,6 +214,30 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
                                 int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
                                 double* loss_out_host, float* dX_host, float* dY_host, float* dW_host,
                                 void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream);
+
+/* ---- the whole path, batch-sharded over the GPUs of one node --------------------------------------- */
+
+/* One host call per step and rank: rank r passes its row shard (X_local, Y_local [B_local, D] bf16, sid_local int32; all ranks
+ * the same B_local) and receives the GLOBAL-batch loss (loss_out fp64[8], device, identical on every rank) and the gradients
+ * of its rows (dX, dY fp32 [B_local, D]) plus dW (fp32 [D, D], already summed over ranks).  Estimators DV / INFONCE_REF /
+ * INFONCE_ROW (the symmetric one is orchestrated on the host side, mi_b200/dist.py).  Inside: all-gather of the ids and of Y
+ * (in place, the own column block is scored while the others arrive), references from a sample of the OWN column block and
+ * an all-reduce(max) of lambda, the single pass, all-gather of the 8 loss scalars, reduce-scatter of the dY contributions
+ * under the dT contraction, all-reduce of dW under the dX GEMM — NCCL called directly on `nccl_comm` (an ncclComm_t, e.g.
+ * torch.distributed's ProcessGroupNCCL._comm_ptr()) from ONE internal communication stream per context; libnccl.so.2 is
+ * resolved from the running process.  check_guard = 1: the host waits (an event, not a stream) until the merged guard count
+ * is known — right after the score tiles — and returns MI_GUARD_TRIPPED on every rank when it is non-zero; 0: never
+ * synchronises, the count is left in loss_out[7].  A context is bound to one device / communicator and serves one call at a
+ * time; the collectives it issues must not interleave with other collectives on the same communicator from other threads. */
+typedef struct mi_dist_ctx mi_dist_ctx;
+int mi_dist_ctx_create(void* nccl_comm, mi_dist_ctx** out);
+void mi_dist_ctx_destroy(mi_dist_ctx* ctx);
+int mi_dist_ctx_info(const mi_dist_ctx* ctx, int* rank, int* world);
+size_t mi_sharded_critic_workspace_bytes(int64_t B_local, int world, int64_t D, int critic, int estimator, int precision);
+int mi_sharded_critic_loss_fwd_bwd(mi_dist_ctx* ctx, const void* X_local, const void* Y_local, const void* W, const int32_t* sid_local,
+                                   int64_t B_local, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                                   double* loss_out, float* dX, float* dY, float* dW,
+                                   void* workspace, size_t workspace_bytes, int check_guard, mi_stream_t stream);
 
 /* ---- the reference's own critic: make_mlp(2D, [H1, H2]) on every pair ---------------- */
 

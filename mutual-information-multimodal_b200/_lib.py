@@ -40,7 +40,7 @@ PROTOTYPES = {
     "mi_score_ref_sample_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_i64]),
     "mi_ref_sample_stride": (c_i64, [c_i64, c_i64, c_i64]),
     "mi_score_ref_sample": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
-                                    c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+                                    c_int, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mi_score_single_pass_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "mi_row_norm_max": (c_int, [c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "mi_score_single_pass": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
@@ -53,6 +53,12 @@ PROTOTYPES = {
     "mi_critic_workspace_bytes": (c_sz, [c_i64, c_i64, c_int, c_int, c_int, c_int]),
     "mi_critic_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "mi_dist_ctx_create": (c_int, [c_vp, c_vp]),
+    "mi_dist_ctx_destroy": (None, [c_vp]),
+    "mi_dist_ctx_info": (c_int, [c_vp, c_vp, c_vp]),
+    "mi_sharded_critic_workspace_bytes": (c_sz, [c_i64, c_int, c_i64, c_int, c_int, c_int]),
+    "mi_sharded_critic_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32,
+                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_vp]),
     "mi_mlp_critic_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_i64, c_int]),
     "mi_mlp_critic_loss_fwd_bwd": (c_int, [c_vp] * 9 + [c_i64, c_i64, c_i64, c_i64, c_int, c_int] + [c_vp] * 10 + [c_vp, c_sz, c_vp]),
     "mi_gdv_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),

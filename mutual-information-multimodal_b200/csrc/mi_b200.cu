@@ -1123,12 +1123,16 @@ long long ref_stride_auto(long long Bq, long long ncols, long long D) {
 
 // Per-row softmax references of the single pass (see ref_merge_kernel) from the columns c0 + s * stride, s in [0, ns),
 // ns = ceil(nc / stride), of K — one statistics launch over a strided view of K (a TMA map whose row pitch is
-// stride * ld; no gather).  Also: diag_out[q] = the positive-pair score S[q, q_offset + q]; lam_out[0] = max_q ref_out[q].
+// stride * ld; no gather).  `margin` lifts the references above the sample's log-sum-exp (kRefMargin whenever the sampled
+// columns are a proper subset of the row's columns, 0 when they are all of them).  Also: diag_out[q] = the positive-pair
+// score S[q, q_offset + q]; lam_out[0] = max_q ref_out[q] - margin.
 int ref_sample_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k, long long q_offset,
                     long long Bq, long long Bk, long long D, float scale, int include_diag,
-                    long long c0, long long nc, long long stride,
-                    float* ref_out, float* diag_out, float* lam_out, Bump& ws, cudaStream_t stream) {
+                    long long c0, long long nc, long long stride, float margin,
+                    float* ref_out, float* diag_out, float* lam_out, Bump& ws, cudaStream_t stream,
+                    const MaskBuf* shared_mask = nullptr /* stride 1 over all columns: a mask the caller has built already */) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0 || stride < 1 || c0 < 0 || nc <= 0 || c0 + nc > Bk) return MI_ERR_BAD_ARG;
+  if (shared_mask != nullptr && (stride != 1 || c0 != 0 || nc != Bk)) return MI_ERR_BAD_ARG;
   const long long ns = cdiv(nc, stride);
   Sched sc;
   sc.n_mblk = static_cast<int>(cdiv(Bq, rows_per_mblk()));
@@ -1138,7 +1142,7 @@ int ref_sample_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* s
   MI_TRY(score_segments(sc, Q, K, D));
   const long long k_pad = static_cast<long long>(sc.n_ntile) * mi::TILE_N;
   const int rows_padded = sc.n_mblk * rows_per_mblk();
-  const MaskBuf mb = take_mask(ws, Bq, k_pad, ns);
+  const MaskBuf mb = shared_mask != nullptr ? *shared_mask : take_mask(ws, Bq, k_pad, ns);
   int* sid_s = ws.take<int>(ns);
   float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * mi::kColQuarters * rows_padded);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
@@ -1151,7 +1155,7 @@ int ref_sample_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* s
     MI_LAUNCH_CHECK("gather_int_kernel");
     sid_cols = sid_s;
   }
-  MI_TRY(build_mask(mb, sid_q, sid_cols, Bq, ns, k_pad, stream));
+  if (shared_mask == nullptr) MI_TRY(build_mask(mb, sid_q, sid_cols, Bq, ns, k_pad, stream));
   diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Q.p, Q.ld, Q.split, K.p, K.ld, K.split, q_offset, Bq, D,
                                                              round_up(D, kSplitAlign), scale, diag_out, pr);
   MI_LAUNCH_CHECK("diag_kernel");
@@ -1162,11 +1166,11 @@ int ref_sample_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* s
   MI_TRY(launch_engine<mi::EpiStats>(MapSpec{Q.p, Bq, opnd_k_extent(Q, D), Q.ld},
                                      MapSpec{K.p + c0 * K.ld, ns, opnd_k_extent(K, D), K.ld * stride}, sc, ep, stream));
   ref_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(Bq),
-                                                            diag_out, include_diag, stride > 1 ? kRefMargin : 0.f, ref_out, pr);
+                                                            diag_out, include_diag, margin, ref_out, pr);
   MI_LAUNCH_CHECK("ref_merge_kernel");
   if (lam_out != nullptr) {
     // lambda = the largest SAMPLE log-sum-exp (the margin taken out again): e^{S - lambda} is then centred on the global scale
-    max_reduce_kernel<<<1, 1024, 0, stream>>>(ref_out, Bq, lam_out, stride > 1 ? kRefMargin : 0.f, pr);
+    max_reduce_kernel<<<1, 1024, 0, stream>>>(ref_out, Bq, lam_out, margin, pr);
     MI_LAUNCH_CHECK("max_reduce_kernel");
   }
   return MI_OK;
@@ -1358,7 +1362,10 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                      float* row_out, float* oq_raw, float* ok_raw, float* wrow, int* flag_out, Bump& ws, cudaStream_t stream,
                      cudaEvent_t ev_after_k = nullptr, double* scal_out = nullptr, cudaEvent_t ev_after_scal = nullptr,
                      cudaEvent_t ev_k_ready = nullptr, const struct SingleFin* fin = nullptr,
-                     const struct PanelFeed* feed = nullptr, bool k_local_valid = false) {
+                     const struct PanelFeed* feed = nullptr, bool k_local_valid = false,
+                     const MaskBuf* shared_mask = nullptr /* the negatives mask of (sid_q, sid_k), built by the caller */,
+                     cudaEvent_t ev_lambda = nullptr /* lambda (an all-reduce in flight) is valid once this event fires: waited for
+                                                        right before the first row-sum merge, after the score tiles are enqueued */) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
   const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
@@ -1371,7 +1378,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
   const long long mb_panel = panel_mblks(Bq, Bk, D, precision & 1);
   const long long panel_rows = mb_panel * rows_per_mblk();
   const int max_split = n_ntile;
-  const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
+  const MaskBuf mb = shared_mask != nullptr ? *shared_mask : take_mask(ws, Bq, k_pad, Bk);
   const long long ld_qs = strict ? 2 * Dp : D;               // w Q [panel_rows, hi | lo]
   bf* Qs = ok_raw || ws.dry ? ws.take<bf>(static_cast<size_t>(panel_rows) * ld_qs) : nullptr;
   bf* P = ws.take<bf>(static_cast<size_t>(panel_rows) * pitch);
@@ -1389,7 +1396,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
     return MI_ERR_BAD_ARG;
   const int* pr = t_run_if;
 
-  MI_TRY(build_mask(mb, sid_q, sid_k, Bq, Bk, k_pad, stream));
+  if (shared_mask == nullptr) MI_TRY(build_mask(mb, sid_q, sid_k, Bq, Bk, k_pad, stream));
   const Opnd Qe{Q.p, Q.ld, strict ? Q.split : 1}, Ke{K.p, K.ld, strict ? K.split : 1};
   // from here on the K rows are read: wait for the caller's "K complete" event (the all-gather of the text embeddings).
   // When the caller vouches for this rank's own rows (k_local_valid) the wait moves further down: the score tiles of the
@@ -1438,6 +1445,7 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
     } else {
       MI_TRY(score_tiles(0, n_ntile));
     }
+    if (ev_lambda != nullptr && r0 == 0) MI_CUDA(cudaStreamWaitEvent(stream, ev_lambda, 0));
     sum_merge_kernel<<<blocks_for(rows, 128), 128, 0, stream>>>(part, n_part, rows_padded, static_cast<int>(rows),
                                                                 ref + r0, lambda, mb.n_same + r0, static_cast<int>(Bk), diag + r0,
                                                                 include_diag, inv_bg, reinterpret_cast<float4*>(row_out) + r0,
@@ -1560,6 +1568,10 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   double* sp_guard = single ? ws.take<double>(1) : nullptr;
   float* sp_oq = (single && (bilinear || !dX)) ? ws.take<float>(static_cast<size_t>(B) * D) : nullptr;   // dot: dX doubles as the raw buffer
   float* sp_ok = (single && !dY) ? ws.take<float>(static_cast<size_t>(B) * D) : nullptr;
+  // the negatives mask of the whole batch: built ONCE per call and shared by the exact reference pass and the single pass(es)
+  const long long k_pad_all = cdiv(B, mi::TILE_N) * mi::TILE_N;
+  MaskBuf all_mask{};
+  if (single) all_mask = take_mask(ws, B, k_pad_all, B);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (!ws.dry && (!X || !Y || !sid || !loss_out || (bilinear && !W))) return MI_ERR_BAD_ARG;
 
@@ -1598,6 +1610,7 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
     const long long panel_rows = panel_mblks(B, B, D, precision & 1) * rows_per_mblk();
     // one complete pass: references (column sample of the given stride) -> score tiles / statistics / both contractions
     // -> loss and dT.  `flag` counts the rows that tripped the guard of THIS pass.
+    if (!ws.dry) MI_TRY(build_mask(all_mask, sid, sid, B, B, k_pad_all, stream));
     auto run_pass = [&](long long stride, int* flag, bool feed_x) -> int {
       if (!ws.dry) MI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
       PanelFeed feed;
@@ -1607,22 +1620,23 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
           if (bilinear) MI_TRY(project(r0, rows, none));
           const Opnd Tp{To.p + r0 * To.ld, To.ld, To.split};
           const size_t m2 = ws.mark();
-          MI_TRY(ref_sample_impl(Tp, Yo, sid + r0, sid, r0, rows, B, D, inv_tau, incl, 0, B, stride,
+          MI_TRY(ref_sample_impl(Tp, Yo, sid + r0, sid, r0, rows, B, D, inv_tau, incl, 0, B, stride, stride > 1 ? kRefMargin : 0.f,
                                  ref_r + r0, sp_diag + r0, r0 == 0 ? sp_lambda : nullptr, ws, stream));
           ws.release(m2);
           return MI_OK;
         };
       } else {
-        MI_TRY(ref_sample_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, 0, B, stride, ref_r, sp_diag, sp_lambda, ws, stream));
+        MI_TRY(ref_sample_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, 0, B, stride, stride > 1 ? kRefMargin : 0.f,
+                               ref_r, sp_diag, sp_lambda, ws, stream, stride == 1 ? &all_mask : nullptr));
         ws.release(mk);
       }
       MI_TRY(single_pass_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, incl, precision, gam, ref_r, sp_lambda, sp_diag,
                               rows_r, oq_raw, ok_raw, sp_wrow, flag, ws, stream,
                               fused_k ? ev_dy_final : nullptr, scal_r, nullptr, nullptr, fused_k ? &fin : nullptr,
-                              feed_x ? &feed : nullptr));
+                              feed_x ? &feed : nullptr, false, &all_mask));
       if (ws.dry) {                      // the per-panel reference sample of the streamed form lives on top of the pass
         const size_t m2 = ws.mark();
-        MI_TRY(ref_sample_impl(To, Yo, sid, sid, 0, panel_rows < B ? panel_rows : B, B, D, inv_tau, incl, 0, B, stride,
+        MI_TRY(ref_sample_impl(To, Yo, sid, sid, 0, panel_rows < B ? panel_rows : B, B, D, inv_tau, incl, 0, B, stride, 0.f,
                                ref_r, sp_diag, sp_lambda, ws, stream));
         ws.release(m2);
       }
@@ -1773,6 +1787,8 @@ int copy_side(CopySide* out) {
 
 }  // namespace
 
+#include "sharded.cuh"      // the batch-sharded step with its NCCL collectives as one host call
+
 // ======================================================================================== C ABI
 extern "C" {
 
@@ -1784,6 +1800,7 @@ const char* mi_status_string(int status) {
     case MI_ERR_CUDA: return "CUDA error";
     case MI_ERR_NO_DEVICE: return "no sm_100 (Blackwell) device: this library has no CPU fallback";
     case MI_ERR_NO_NEGATIVES: return "no negative pairs (all study ids equal)";
+    case MI_GUARD_TRIPPED: return "single-pass guard tripped: results are not valid, repeat the step with exact references";
     default: return "unknown status";
   }
 }
@@ -1907,23 +1924,24 @@ size_t mi_score_ref_sample_workspace_bytes(int64_t Bq, int64_t n_cols, int64_t D
   Bump ws(nullptr, 0, true);
   if (stride < 1) stride = ref_stride_auto(Bq, n_cols, D);
   // planned for a hi/lo Q (the larger K loop does not change the workspace, only the mask / partial buffers matter)
-  if (ref_sample_impl(Opnd{nullptr, D, 1}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, n_cols, D, 1.f, 0, 0, n_cols, stride,
+  if (ref_sample_impl(Opnd{nullptr, D, 1}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, n_cols, D, 1.f, 0, 0, n_cols, stride, 0.f,
                       nullptr, nullptr, nullptr, ws, nullptr) != MI_OK) return 0;
   return ws.peak + 256;
 }
 int mi_score_ref_sample(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
                         const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
                         int64_t Bq, int64_t Bk, int64_t D, float scale, int include_diag,
-                        int64_t col0, int64_t n_cols, int64_t stride,
+                        int64_t col0, int64_t n_cols, int64_t stride, int subset,
                         float* ref_out, float* diag_out, float* lambda_out,
                         void* workspace, size_t workspace_bytes, mi_stream_t stream_) {
   MI_TRY(device_check());
   if (q_offset < 0 || q_offset + Bq > Bk) return MI_ERR_BAD_ARG;
   if (stride < 1) stride = ref_stride_auto(Bq, n_cols, D);
+  const float margin = (stride > 1 || subset != 0) ? kRefMargin : 0.f;
   Bump ws(workspace, workspace_bytes, false);
   return ref_sample_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
                          Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
-                         sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, col0, n_cols, stride,
+                         sid_q, sid_k, q_offset, Bq, Bk, D, scale, include_diag, col0, n_cols, stride, margin,
                          ref_out, diag_out, lambda_out, ws, reinterpret_cast<cudaStream_t>(stream_));
 }
 int64_t mi_ref_sample_stride(int64_t Bq, int64_t n_cols, int64_t D) { return ref_stride_auto(Bq, n_cols, D); }
@@ -2145,6 +2163,57 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
 #undef MI_HOST_CUDA
 #undef MI_HOST_TRY
   return MI_OK;
+}
+
+int mi_dist_ctx_create(void* nccl_comm, mi_dist_ctx** out) {
+  MI_TRY(device_check());
+  if (!nccl_comm || !out) return MI_ERR_BAD_ARG;
+  const NcclApi& nc = nccl_api();
+  if (!nc.ok) { std::snprintf(g_cuda_err, sizeof(g_cuda_err), "libnccl.so.2 not found in the process"); return MI_ERR_CUDA; }
+  mi_dist_ctx* c = new mi_dist_ctx();
+  c->comm = nccl_comm;
+  MI_NCCL(nc.comm_count(nccl_comm, &c->world));
+  MI_NCCL(nc.comm_rank(nccl_comm, &c->rank));
+  MI_CUDA(cudaGetDevice(&c->device));
+  MI_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  cudaEvent_t* evs[] = {&c->ev_in, &c->ev_lamloc, &c->ev_sid, &c->ev_y, &c->ev_lam, &c->ev_s, &c->ev_k, &c->ev_m, &c->ev_rs,
+                        &c->ev_dwg, &c->ev_dw, &c->ev_drain};
+  for (cudaEvent_t* e : evs) MI_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  MI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->guard_host), sizeof(double), cudaHostAllocDefault));
+  c->guard_host[0] = 0.0;
+  *out = c;
+  return MI_OK;
+}
+void mi_dist_ctx_destroy(mi_dist_ctx* c) {
+  if (!c) return;
+  (void)cudaStreamSynchronize(c->comm_stream);
+  cudaEvent_t evs[] = {c->ev_in, c->ev_lamloc, c->ev_sid, c->ev_y, c->ev_lam, c->ev_s, c->ev_k, c->ev_m, c->ev_rs, c->ev_dwg, c->ev_dw,
+                       c->ev_drain};
+  for (cudaEvent_t e : evs) (void)cudaEventDestroy(e);
+  (void)cudaStreamDestroy(c->comm_stream);
+  (void)cudaFreeHost(c->guard_host);
+  delete c;
+}
+int mi_dist_ctx_info(const mi_dist_ctx* c, int* rank, int* world) {
+  if (!c || !rank || !world) return MI_ERR_BAD_ARG;
+  *rank = c->rank; *world = c->world;
+  return MI_OK;
+}
+size_t mi_sharded_critic_workspace_bytes(int64_t B_local, int world, int64_t D, int critic, int estimator, int precision) {
+  Bump ws(nullptr, 0, true);
+  if (sharded_impl(nullptr, world, 0, nullptr, nullptr, nullptr, nullptr, B_local, D, critic, estimator, precision, 1.f, nullptr, nullptr,
+                   nullptr, nullptr, ws, 0, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_sharded_critic_loss_fwd_bwd(mi_dist_ctx* ctx, const void* X_local, const void* Y_local, const void* W, const int32_t* sid_local,
+                                   int64_t B_local, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                                   double* loss_out, float* dX, float* dY, float* dW,
+                                   void* workspace, size_t workspace_bytes, int check_guard, mi_stream_t stream) {
+  MI_TRY(device_check());
+  if (!ctx) return MI_ERR_BAD_ARG;
+  Bump ws(workspace, workspace_bytes, false);
+  return sharded_impl(ctx, ctx->world, ctx->rank, X_local, Y_local, W, sid_local, B_local, D, critic, estimator, precision, inv_tau,
+                      loss_out, dX, dY, dW, ws, check_guard, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t mi_mlp_critic_workspace_bytes(int64_t B, int64_t D, int64_t H1, int64_t H2, int precision) {

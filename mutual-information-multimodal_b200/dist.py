@@ -251,6 +251,18 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
     # ---- the exchange step
     nccl = world > 1 and dist.get_backend(group) != "gloo"
     single = need_grads and not sym and not two_pass
+    if (nccl and single and sid_local.dtype == torch.int32 and hasattr(backend, "sharded_step")
+            and os.environ.get("MI_SHARDED_IMPL", "c") != "python"):
+        # the whole step, collectives included, as ONE library call (csrc/sharded.cuh): no per-op host overhead
+        st, lo, dX, dY, dW = backend.sharded_step(Xb, Yb, Wb, sid_local, estimator, precision, inv_tau, group=group,
+                                                  check_guard=check_guard)
+        if st == 0:
+            return ({"loss": lo[0], "pos_mean": lo[1], "lse_neg": lo[2], "n_neg": lo[3], "loss_row": lo[4],
+                     "rows_without_negatives": lo[6], "guard": lo[7]}, dX, dY, dW)
+        out, dX, dY, dW = sharded_critic_loss_fwd_bwd(X_local, Y_local, W, sid_local, estimator, precision, inv_tau,
+                                                       need_grads, group, backend, two_pass=True)      # guard tripped on every rank
+        out["guard"] = torch.ones((), dtype=torch.float64, device=out["loss"].device)
+        return out, dX, dY, dW
     T_local = backend.gemm(Xb, Wb, b_t=True, out_dtype=torch.bfloat16, out_split=strict) if bilinear else Xb   # X W, W in place
     smp = lam = None
     sid_all = None
@@ -258,7 +270,7 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         # softmax references of this rank's rows from a sample of its OWN column block (needs nothing from the other ranks,
         # so it runs before / under the all-gather of the text embeddings); lambda = the largest reference of ALL ranks
         sid_own = sid_local if sid_local.dtype == torch.int32 else dense_labels(sid_local.to(torch.int64))
-        smp = backend.score_ref_sample(T_local, Yb, sid_own, sid_own, 0, inv_tau, not dv_like)
+        smp = backend.score_ref_sample(T_local, Yb, sid_own, sid_own, 0, inv_tau, not dv_like, subset=world > 1)
         lam = smp["lam"]
         if world > 1 and sid_local.dtype == torch.int32:
             # ONE small all-gather carries the study ids and lambda (raw float bits); it goes first, so the mask pre-pass

@@ -280,9 +280,11 @@ def set_ref_sample_columns(n: int) -> None:
 
 
 def score_ref_sample(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float, include_diag: bool,
-                     col0: int = 0, n_cols: Optional[int] = None, stride: int = 0) -> dict:
+                     col0: int = 0, n_cols: Optional[int] = None, stride: int = 0, subset: bool = False) -> dict:
     """mi_score_ref_sample: per-row softmax references of the single pass from a strided column sample
-    (``stride`` = 1: every column, exact; 0: the library's choice).  Returns {"ref" [Bq], "diag" [Bq], "lam" [1], "stride"}."""
+    (``stride`` = 1: every column of K; 0: the library's choice).  ``subset``: K holds only part of the row's columns (a
+    rank's own block), so the references keep their safety margin even at stride 1.
+    Returns {"ref" [Bq], "diag" [Bq], "lam" [1], "stride"}."""
     _need_cuda(Q, K, sid_q, sid_k)
     lib = _lib.load()
     Qt, ldq, qsp, D = _opnd(Q)
@@ -298,7 +300,7 @@ def score_ref_sample(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float, 
     r = {"ref": torch.empty(Bq, **f32), "diag": torch.empty(Bq, **f32), "lam": torch.empty(1, **f32), "stride": stride}
     ws = workspace(lib.mi_score_ref_sample_workspace_bytes(Bq, n_cols, D, stride), dev)
     _check(lib.mi_score_ref_sample(_ptr(Qt), ldq, qsp, _ptr(Kt), ldk, ksp, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D,
-                                   scale, int(include_diag), col0, n_cols, stride, _ptr(r["ref"]), _ptr(r["diag"]), _ptr(r["lam"]),
+                                   scale, int(include_diag), col0, n_cols, stride, int(subset), _ptr(r["ref"]), _ptr(r["diag"]), _ptr(r["lam"]),
                                    _ptr(ws), ws.numel(), _stream()), "mi_score_ref_sample")
     return r
 
@@ -415,6 +417,63 @@ def critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, W: Optional[torch.Tens
                                       _ptr(loss), _ptr(dX), _ptr(dY), _ptr(dW), _ptr(ws), ws.numel(), _stream()),
            "mi_critic_loss_fwd_bwd")
     return loss, dX, dY, dW
+
+
+GUARD_TRIPPED = 1
+_dist_ctx = {}
+
+
+def dist_context(group=None):
+    """The library-side context of the batch-sharded step (mi_dist_ctx) for a torch.distributed NCCL process group: it
+    borrows the group's own ncclComm_t (ProcessGroupNCCL._comm_ptr()) — no second communicator.  Cached per group."""
+    import torch.distributed as tdist
+    pg = tdist.distributed_c10d._get_default_group() if group is None else group
+    backend = pg._get_backend(torch.device("cuda", torch.cuda.current_device()))
+    key = id(backend)
+    if key not in _dist_ctx:
+        try:
+            comm = backend._comm_ptr()
+        except Exception:                                     # communicator not created yet (lazy init): one collective forces it
+            tdist.all_reduce(torch.zeros(1, device=f"cuda:{torch.cuda.current_device()}"), group=group)
+            comm = backend._comm_ptr()
+        ctx = C.c_void_p()
+        _check(_lib.load().mi_dist_ctx_create(C.c_void_p(comm), C.byref(ctx)), "mi_dist_ctx_create")
+        rank, world = C.c_int(), C.c_int()
+        _check(_lib.load().mi_dist_ctx_info(ctx, C.byref(rank), C.byref(world)), "mi_dist_ctx_info")
+        _dist_ctx[key] = (ctx, rank.value, world.value, backend)      # (keeps the backend alive as long as the context)
+    return _dist_ctx[key]
+
+
+def sharded_step(X_local: torch.Tensor, Y_local: torch.Tensor, W: Optional[torch.Tensor], sid_local: torch.Tensor,
+                 estimator: str, precision: str, inv_tau: float, group=None, check_guard: bool = True):
+    """mi_sharded_critic_loss_fwd_bwd: the whole batch-sharded step (collectives included) as one library call.
+    Returns (status, loss_out fp64[8], dX, dY, dW); status GUARD_TRIPPED (on every rank alike) means the outputs are not
+    valid and the step must be repeated on the exact path."""
+    _need_cuda(X_local, Y_local, W, sid_local)
+    lib = _lib.load()
+    ctx, rank, world, _ = dist_context(group)
+    X, Y = as_bf16(X_local), as_bf16(Y_local)
+    Wb = None if W is None else as_bf16(W)
+    if sid_local.dtype != torch.int32:
+        raise MIError("sharded_step needs exact int32 study ids (equal ids <=> equal values on every rank)")
+    sid = sid_local.contiguous()
+    Bl, D = X.shape
+    critic = 1 if Wb is not None else 0
+    est, prec = ESTIMATOR[estimator], PRECISION[precision]
+    dev = X.device
+    loss = torch.empty(8, dtype=torch.float64, device=dev)
+    dX = torch.empty((Bl, D), dtype=torch.float32, device=dev)
+    dY = torch.empty((Bl, D), dtype=torch.float32, device=dev)
+    dW = torch.empty((D, D), dtype=torch.float32, device=dev) if Wb is not None else None
+    nbytes = lib.mi_sharded_critic_workspace_bytes(Bl, world, D, critic, est, prec)
+    if nbytes == 0:
+        raise MIError("mi_sharded_critic_workspace_bytes: unsupported configuration")
+    ws = workspace(nbytes, dev)
+    st = lib.mi_sharded_critic_loss_fwd_bwd(ctx, _ptr(X), _ptr(Y), _ptr(Wb), _ptr(sid), Bl, D, critic, est, prec, inv_tau,
+                                            _ptr(loss), _ptr(dX), _ptr(dY), _ptr(dW), _ptr(ws), ws.numel(), int(check_guard), _stream())
+    if st not in (0, GUARD_TRIPPED):
+        _check(st, "mi_sharded_critic_loss_fwd_bwd")
+    return st, loss, dX, dY, dW
 
 
 class GraphedCriticStep:

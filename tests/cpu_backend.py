@@ -74,7 +74,7 @@ def row_norm_max(A):
 REF_STRIDE = 1      # tests set this to exercise the sampled references (the library picks its own stride)
 
 
-def score_ref_sample(Q, K, sid_q, sid_k, q_offset, scale, include_diag, col0=0, n_cols=None, stride=0):
+def score_ref_sample(Q, K, sid_q, sid_k, q_offset, scale, include_diag, col0=0, n_cols=None, stride=0, subset=False):
     S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)
     n_cols = K.shape[0] - col0 if n_cols is None else n_cols
     stride = REF_STRIDE if stride < 1 else stride
@@ -82,7 +82,7 @@ def score_ref_sample(Q, K, sid_q, sid_k, q_offset, scale, include_diag, col0=0, 
     lse = torch.logsumexp(torch.where(M[:, cols], S[:, cols], torch.full_like(S[:, cols], float("-inf"))), 1)
     diag = S[i, j]
     ref = torch.logaddexp(lse, diag) if include_diag else torch.where(torch.isfinite(lse), lse, diag)
-    margin = 48.0 if stride > 1 else 0.0                   # kRefMargin of the library
+    margin = 48.0 if (stride > 1 or subset) else 0.0       # kRefMargin of the library
     ref = ref + margin
     return {"ref": ref, "diag": diag, "lam": (ref.max() - margin).reshape(1), "stride": stride}
 

@@ -524,7 +524,12 @@ def _nccl_worker(rank, world, port, ret):
         X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=11, dup_frac=0.05, bilinear=True)
         Bl = B // world
         sl = slice(rank * Bl, (rank + 1) * Bl)
-        for est, planted in (("dv", False), ("infonce_row", False), ("infonce_sym", False), ("dv", True)):
+        cases = [(est, planted, impl) for impl in ("c", "python")
+                 for est, planted in (("dv", False), ("infonce_row", False), ("infonce_sym", False), ("dv", True))]
+        for est, planted, impl in cases:
+            # "c": the whole step as ONE library call that issues its own NCCL collectives (csrc/sharded.cuh);
+            # "python": the same step orchestrated op by op through torch.distributed (mi_b200/dist.py)
+            os.environ["MI_SHARDED_IMPL"] = impl
             Xb, Yb, Wb = X.bfloat16(), Y.bfloat16(), W.bfloat16()
             if planted:                                      # guard trip on rank 0 only: both ranks must take the exact path
                 ops.set_ref_sample_columns(64)
@@ -536,8 +541,8 @@ def _nccl_worker(rank, world, port, ret):
             torch.cuda.synchronize()
             ops.set_ref_sample_columns(2048)
             r = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
-            errs[(est, planted)] = [abs(float(out["loss"]) - float(full[0][0])) / abs(float(full[0][0])), r(dX, full[1][sl]),
-                                    r(dY, full[2][sl]), r(dW, full[3]), float(out.get("guard", 0.0))]
+            errs[(est, planted, impl)] = [abs(float(out["loss"]) - float(full[0][0])) / abs(float(full[0][0])), r(dX, full[1][sl]),
+                                          r(dY, full[2][sl]), r(dW, full[3]), float(out.get("guard", 0.0))]
         ret[rank] = errs
     finally:
         dist.destroy_process_group()
@@ -557,9 +562,9 @@ def test_sharded_path_nccl_2gpu_equals_single_gpu(env):
     mp.spawn(_nccl_worker, args=(2, port, ret), nprocs=2, join=True)
     assert len(ret) == 2
     for rank in range(2):
-        for (est, planted), e in ret[rank].items():
-            assert e[0] < 1e-5 and max(e[1:4]) < 1e-4, (rank, est, planted, e)
-            assert (e[4] != 0.0) == planted, (rank, est, planted, e)
+        for (est, planted, impl), e in ret[rank].items():
+            assert e[0] < 1e-5 and max(e[1:4]) < 1e-4, (rank, est, planted, impl, e)
+            assert (e[4] != 0.0) == planted, (rank, est, planted, impl, e)
 
 
 def test_cuda_graph_replay_equals_direct_call(env):
