@@ -327,49 +327,62 @@ def run_ours(a):
         path += (" -> guard tripped: the exact repeat ran inside every timed step" if world == 1 else
                  " -> guard tripped and NOT acted on (check_guard=False in the timed loop): INVALID NUMBER")
 
-    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region).
+    # Every step: the step's inputs (bf16 embeddings, W, study ids) cross PCIe from pinned host memory, the loss comes back to
+    # the host; the gradients stay on the device, where the encoders' backward consumes them.  N = 1 also times
+    # the full host round trip of round 1 (fp32 host embeddings in, fp32 gradients back out) as `roundtrip_fp32`.
     e2e = None
     if not a.no_e2e:
-        n_bd, n_dd = Bl * D * 4, D * D * 4
+        Xp, Yp = Xh.bfloat16().pin_memory(), Yh.bfloat16().pin_memory()
+        Wp = Wh.bfloat16().pin_memory() if bilinear else None
+        n_in = 2 * Bl * D * 2 + (D * D * 2 if bilinear else 0) + Bl * 4
+        P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        roundtrip = None
         if world == 1:
             crit, est, prec = (1 if bilinear else 0), ops.ESTIMATOR[a.estimator], ops.PRECISION[a.precision]
             nbytes = lib.mi_critic_host_scratch_bytes(B, D, crit, est, prec, 1)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             loss_h = torch.zeros(8, dtype=torch.float64).pin_memory()
-            dXh, dYh = torch.empty(Bl, D).pin_memory(), torch.empty(Bl, D).pin_memory()
-            dWh = torch.empty(D, D).pin_memory() if bilinear else None
-            P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+            gX, gY = torch.empty(Bl, D, device=dev), torch.empty(Bl, D, device=dev)
+            gW = torch.empty(D, D, device=dev) if bilinear else None
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
             def step_host():
+                st = lib.mi_critic_loss_fwd_bwd_from_host(P(Xp), P(Yp), P(Wp), P(sh), 1, B, D, crit, est, prec, inv_tau,
+                                                          P(loss_h), P(gX), P(gY), P(gW), P(scratch), nbytes, stream)
+                if st != 0:
+                    raise RuntimeError(lib.mi_status_string(st).decode())
+                return loss_h
+
+            dXh, dYh = torch.empty(Bl, D).pin_memory(), torch.empty(Bl, D).pin_memory()
+            dWh = torch.empty(D, D).pin_memory() if bilinear else None
+
+            def step_roundtrip():
                 st = lib.mi_critic_loss_fwd_bwd_host(P(Xh), P(Yh), P(Wh), P(sh), B, D, crit, est, prec, inv_tau,
                                                      P(loss_h), P(dXh), P(dYh), P(dWh), P(scratch), nbytes, stream)
                 if st != 0:
                     raise RuntimeError(lib.mi_status_string(st).decode())
                 return loss_h
+            drain = lambda: None
         else:
             # N > 1: the user-level loop around the public sharded call, software-pipelined the way a training loop overlaps
-            # its data loader: step n+1's host->device copies run on a copy stream under step n's compute, step n's
-            # gradients go back on a second copy stream under step n+1, and the loss of step n is read (a device->host read
-            # of the step's result, every step) after step n+1 has been enqueued.  Every step still moves all of its inputs
-            # from pinned host memory and all of its results back inside the timed region.
-            dXh, dYh = torch.empty(Bl, D).pin_memory(), torch.empty(Bl, D).pin_memory()
-            dWh = torch.empty(D, D).pin_memory() if bilinear else None
+            # its data loader: step n+1's host->device copies run on a copy stream under step n's compute and the loss of
+            # step n is read (a device->host read of the step's result, every step) after step n+1 has been enqueued.
             s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
             main = torch.cuda.current_stream()
-            dbuf = [(torch.empty(Bl, D, device=dev), torch.empty(Bl, D, device=dev),
-                     torch.empty(D, D, device=dev) if bilinear else None, torch.empty(Bl, dtype=torch.int32, device=dev),
-                     torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
+            bf = dict(dtype=torch.bfloat16, device=dev)
+            dbuf = [(torch.empty(Bl, D, **bf), torch.empty(Bl, D, **bf), torch.empty(D, D, **bf) if bilinear else None,
+                     torch.empty(Bl, dtype=torch.int32, device=dev), torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
             loss_pin = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
             state = {"n": 0, "pending": None}
 
             def upload(slot):
-                x, y, w, s_, ev_in, _ = dbuf[slot]
+                x, y, w, s_, ev_in, ev_used = dbuf[slot]
                 with torch.cuda.stream(s_in):
-                    s_in.wait_event(dbuf[slot][5])             # the previous user of this slot has consumed it
-                    x.copy_(Xh, non_blocking=True); y.copy_(Yh, non_blocking=True); s_.copy_(sh, non_blocking=True)
+                    s_in.wait_event(ev_used)                   # the previous user of this slot has consumed it
+                    x.copy_(Xp, non_blocking=True); y.copy_(Yp, non_blocking=True); s_.copy_(sh, non_blocking=True)
                     if bilinear:
-                        w.copy_(Wh, non_blocking=True)
+                        w.copy_(Wp, non_blocking=True)
                     ev_in.record(s_in)
 
             def step_host():
@@ -384,17 +397,11 @@ def run_ours(a):
                 # score tiles are done and would repeat the step on the exact path
                 out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(x, y, w, s_, a.estimator, a.precision, inv_tau, True)
                 ev_used.record(main)
-                ev_done = torch.cuda.Event(); ev_done.record(main)
                 with torch.cuda.stream(s_out):
-                    s_out.wait_event(ev_done)
-                    dXh.copy_(dX, non_blocking=True); dYh.copy_(dY, non_blocking=True)
-                    if bilinear:
-                        dWh.copy_(dW, non_blocking=True)
+                    s_out.wait_event(ev_used)
                     loss_pin[slot].copy_(out["loss"].reshape(1), non_blocking=True)
                     ev_out = torch.cuda.Event(); ev_out.record(s_out)
-                for t in (dX, dY, dW, out["loss"]):
-                    if t is not None:
-                        t.record_stream(s_out)
+                out["loss"].record_stream(s_out)
                 prev = state["pending"]
                 state["pending"] = (ev_out, slot)
                 state["n"] = n + 1
@@ -409,27 +416,34 @@ def run_ours(a):
                     state["pending"] = None
                 main.wait_stream(s_out); main.wait_stream(s_in)
         step_host(); step_host()
-        if world > 1:
-            drain()
+        drain()
         e_steps = max(2, min(a.steps, 5)) if world == 1 else max(4, a.steps)
 
-        def timed_host(steps):
+        def timed_host(fn, steps):
             def run():
                 r = None
                 for _ in range(steps):
-                    r = step_host()
-                if world > 1:
-                    drain()
+                    r = fn()
+                drain()
                 return r
-            return timed(run, 1)
-        e_ms, _, _, _ = timed_host(e_steps)
-        e_ms /= e_steps
+            return timed(run, 1)[0] / steps
+        e_ms = timed_host(step_host, e_steps)
+        if world == 1:
+            step_roundtrip()
+            rt_ms = timed_host(step_roundtrip, 3)
+            n_bd, n_dd = Bl * D * 4, D * D * 4
+            roundtrip = {"ms_per_step": rt_ms, "value": B * B / (rt_ms * 1e-3), "unit": UNIT,
+                         "h2d_bytes_per_step": 2 * n_bd + (n_dd if bilinear else 0) + Bl * 4,
+                         "d2h_bytes_per_step": 2 * n_bd + (n_dd if bilinear else 0) + 64,
+                         "api": "mi_critic_loss_fwd_bwd_host (fp32 host embeddings in, fp32 gradients back to the host)"}
         e2e = {"value": B * B / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": world * (2 * n_bd + (n_dd if bilinear else 0) + Bl * 4),
-               "d2h_bytes_per_step": world * (2 * n_bd + (n_dd if bilinear else 0) + 64),
-               "api": "mi_critic_loss_fwd_bwd_host (C ABI, pinned fp32 host buffers)" if world == 1 else
-                      "mi_b200.dist.sharded_critic_loss_fwd_bwd on pinned host shards, copies software-pipelined "
-                      "across steps on two copy streams (loss read one step late)"}
+               "h2d_bytes_per_step": world * n_in, "d2h_bytes_per_step": world * 64,
+               "api": ("mi_critic_loss_fwd_bwd_from_host (C ABI: pinned bf16 host embeddings in, loss to the host, gradients stay on "
+                       "the device)" if world == 1 else
+                       "mi_b200.dist.sharded_critic_loss_fwd_bwd on pinned bf16 host shards, copies software-pipelined across "
+                       "steps on a copy stream (loss read one step late; gradients stay on the device)")}
+        if roundtrip:
+            e2e["roundtrip_fp32"] = roundtrip
 
     # ---- variants (N = 1): the other estimators / precisions, BASELINE config 2, numerically hostile inputs
     variants = []

@@ -215,6 +215,15 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
                                 double* loss_out_host, float* dX_host, float* dY_host, float* dW_host,
                                 void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream);
 
+/* The data-loader form: embeddings arrive in HOST buffers (host_dtype 0 = fp32, 1 = bf16: copied straight into the operand
+ * buffers), the loss goes back to the host, the gradients stay on the DEVICE (dX_dev, dY_dev, dW_dev: fp32 device buffers or
+ * NULL) where the encoders' backward consumes them.  Same streaming of the image-embedding panels under the pass, same guard
+ * handling and scratch size as mi_critic_loss_fwd_bwd_host; synchronises before it returns. */
+int mi_critic_loss_fwd_bwd_from_host(const void* X_host, const void* Y_host, const void* W_host, const int32_t* sid_host, int host_dtype,
+                                     int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                                     double* loss_out_host, float* dX_dev, float* dY_dev, float* dW_dev,
+                                     void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream);
+
 /* ---- the whole path, batch-sharded over the GPUs of one node --------------------------------------- */
 
 /* One host call per step and rank: rank r passes its row shard (X_local, Y_local [B_local, D] bf16, sid_local int32; all ranks

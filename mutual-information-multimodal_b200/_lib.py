@@ -53,6 +53,8 @@ PROTOTYPES = {
     "mi_critic_workspace_bytes": (c_sz, [c_i64, c_i64, c_int, c_int, c_int, c_int]),
     "mi_critic_loss_fwd_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "mi_critic_loss_fwd_bwd_from_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_int, c_f32,
+                                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mi_dist_ctx_create": (c_int, [c_vp, c_vp]),
     "mi_dist_ctx_destroy": (None, [c_vp]),
     "mi_dist_ctx_info": (c_int, [c_vp, c_vp, c_vp]),

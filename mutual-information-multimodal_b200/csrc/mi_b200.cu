@@ -1365,7 +1365,10 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                      const struct PanelFeed* feed = nullptr, bool k_local_valid = false,
                      const MaskBuf* shared_mask = nullptr /* the negatives mask of (sid_q, sid_k), built by the caller */,
                      cudaEvent_t ev_lambda = nullptr /* lambda (an all-reduce in flight) is valid once this event fires: waited for
-                                                        right before the first row-sum merge, after the score tiles are enqueued */) {
+                                                        right before the first row-sum merge, after the score tiles are enqueued */,
+                     bool defer_reduce = false /* do not reduce row_out -> scal_out here: ev_after_scal fires right after the last
+                                                  row-sum merge and the CALLER reduces (reduce_rows + flag_to_scal) on another
+                                                  stream, so the contractions start without waiting for it */) {
   if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
   typedef __nv_bfloat16 bf;
   const bool strict = (precision & 1) == MI_PREC_BF16_STRICT;
@@ -1451,7 +1454,9 @@ int single_pass_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* 
                                                                 include_diag, inv_bg, reinterpret_cast<float4*>(row_out) + r0,
                                                                 wrow + r0, flag_out, pr);
     MI_LAUNCH_CHECK("sum_merge_kernel");
-    if (scal_out != nullptr && r0 + panel_rows >= Bq) {
+    if (defer_reduce && r0 + panel_rows >= Bq) {
+      if (ev_after_scal != nullptr) MI_CUDA(cudaEventRecord(ev_after_scal, stream));
+    } else if (scal_out != nullptr && r0 + panel_rows >= Bq) {
       // every row's statistics are final once the last panel's sums are merged: reduce them NOW (before the two
       // contractions of this panel) so a caller can exchange the scalars of the loss while the GEMMs still run
       MI_TRY(reduce_rows(row_out, Bq, scal_out, red, stream));
@@ -2053,11 +2058,17 @@ size_t mi_critic_host_scratch_bytes(int64_t B, int64_t D, int critic, int estima
   ws.take<float>(static_cast<size_t>(B) * D); ws.take<float>(static_cast<size_t>(B) * D); ws.take<float>(static_cast<size_t>(D) * D);
   return ws.peak + 256 + core;
 }
-int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const float* W_host, const int32_t* sid_host,
-                                int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
-                                double* loss_out_host, float* dX_host, float* dY_host, float* dW_host,
-                                void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream_) {
+// in_bf16: the host embeddings / W are bf16 (copied straight into the operand buffers, no cast);
+// grads_on_device: dX_host / dY_host / dW_host are DEVICE pointers — the gradients stay where the encoders' backward consumes them
+static int host_entry_impl(const void* X_host_, const void* Y_host_, const void* W_host_, const int32_t* sid_host, bool in_bf16,
+                           int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                           double* loss_out_host, float* dX_host, float* dY_host, float* dW_host, bool grads_on_device,
+                           void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream_) {
   MI_TRY(device_check());
+  const float* X_host = static_cast<const float*>(X_host_); const float* Y_host = static_cast<const float*>(Y_host_);
+  const float* W_host = static_cast<const float*>(W_host_);
+  const __nv_bfloat16* X_hb = static_cast<const __nv_bfloat16*>(X_host_); const __nv_bfloat16* Y_hb = static_cast<const __nv_bfloat16*>(Y_host_);
+  const __nv_bfloat16* W_hb = static_cast<const __nv_bfloat16*>(W_host_);
   if (!X_host || !Y_host || !sid_host || !loss_out_host || !dev_scratch || B <= 0 || D <= 0) return MI_ERR_BAD_ARG;
   const bool bilinear = critic == MI_CRITIC_BILINEAR;
   if (bilinear && !W_host) return MI_ERR_BAD_ARG;
@@ -2069,6 +2080,7 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
   bf* X16 = ws.take<bf>(nBD); bf* Y16 = ws.take<bf>(nBD); bf* W16 = ws.take<bf>(nDD);
   int* sid = ws.take<int>(B); double* loss = ws.take<double>(8);
   float* dX = ws.take<float>(nBD); float* dY = ws.take<float>(nBD); float* dW = ws.take<float>(nDD);
+  if (grads_on_device) { dX = dX_host; dY = dY_host; dW = dW_host; }
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   ws.off = (ws.off + 255) & ~static_cast<size_t>(255);
   uint8_t* core = ws.base + ws.off;
@@ -2102,32 +2114,42 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
   }
   MI_HOST_CUDA(cudaMemcpyAsync(sid, sid_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, stream));
   if (bilinear) {
-    MI_HOST_CUDA(cudaMemcpyAsync(W32, W_host, nDD * 4, cudaMemcpyHostToDevice, stream));
-    MI_HOST_TRY(mi_cast_f32_to_bf16(W32, W16, static_cast<int64_t>(nDD), stream_));
+    if (in_bf16) {
+      MI_HOST_CUDA(cudaMemcpyAsync(W16, W_hb, nDD * 2, cudaMemcpyHostToDevice, stream));
+    } else {
+      MI_HOST_CUDA(cudaMemcpyAsync(W32, W_host, nDD * 4, cudaMemcpyHostToDevice, stream));
+      MI_HOST_TRY(mi_cast_f32_to_bf16(W32, W16, static_cast<int64_t>(nDD), stream_));
+    }
   }
   std::function<int(long long, long long)> x_ready;
   if (streamed) {
-    MI_HOST_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, side.stream));
+    if (in_bf16) MI_HOST_CUDA(cudaMemcpyAsync(Y16, Y_hb, nBD * 2, cudaMemcpyHostToDevice, side.stream));
+    else MI_HOST_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, side.stream));
     MI_HOST_CUDA(cudaEventRecord(side.ev_y, side.stream));
     for (long long c = 0; c < n_chunks; ++c) {
       const long long r0 = c * chunk_rows, rows = (B - r0 < chunk_rows) ? (B - r0) : chunk_rows;
-      MI_HOST_CUDA(cudaMemcpyAsync(X32 + r0 * D, X_host + r0 * D, static_cast<size_t>(rows) * D * 4, cudaMemcpyHostToDevice, side.stream));
+      if (in_bf16) MI_HOST_CUDA(cudaMemcpyAsync(X16 + r0 * D, X_hb + r0 * D, static_cast<size_t>(rows) * D * 2, cudaMemcpyHostToDevice, side.stream));
+      else MI_HOST_CUDA(cudaMemcpyAsync(X32 + r0 * D, X_host + r0 * D, static_cast<size_t>(rows) * D * 4, cudaMemcpyHostToDevice, side.stream));
       MI_HOST_CUDA(cudaEventRecord(side.ev_x[c], side.stream));
     }
     MI_HOST_CUDA(cudaStreamWaitEvent(stream, side.ev_y, 0));
-    MI_HOST_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
+    if (!in_bf16) MI_HOST_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
     x_ready = [&](long long r0, long long rows) -> int {
       if (r0 % chunk_rows != 0) return MI_ERR_BAD_ARG;                // the pass walks the same panels
       MI_CUDA(cudaStreamWaitEvent(stream, side.ev_x[r0 / chunk_rows], 0));
+      if (in_bf16) return MI_OK;
       return mi_cast_f32_to_bf16(X32 + r0 * D, X16 + r0 * D, static_cast<int64_t>(rows * D), stream_);
     };
+  } else if (in_bf16) {
+    MI_HOST_CUDA(cudaMemcpyAsync(X16, X_hb, nBD * 2, cudaMemcpyHostToDevice, stream));
+    MI_HOST_CUDA(cudaMemcpyAsync(Y16, Y_hb, nBD * 2, cudaMemcpyHostToDevice, stream));
   } else {
     MI_HOST_CUDA(cudaMemcpyAsync(X32, X_host, nBD * 4, cudaMemcpyHostToDevice, stream));
     MI_HOST_CUDA(cudaMemcpyAsync(Y32, Y_host, nBD * 4, cudaMemcpyHostToDevice, stream));
     MI_HOST_TRY(mi_cast_f32_to_bf16(X32, X16, static_cast<int64_t>(nBD), stream_));
     MI_HOST_TRY(mi_cast_f32_to_bf16(Y32, Y16, static_cast<int64_t>(nBD), stream_));
   }
-  const bool early = dY_host != nullptr && have_side;
+  const bool early = dY_host != nullptr && have_side && !grads_on_device;
   // Pass 0: sampled references, no device-side fallback (the host decides: this call synchronises anyway).
   // Pass 1 (only if the guard tripped): exact references, inputs already on the device.
   double guard0 = 0.0;
@@ -2139,7 +2161,7 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
                             attempt == 0 ? precision : (precision | MI_PREC_TWO_PASS), inv_tau, loss,
                             dX_host ? dX : nullptr, dY_host ? dY : nullptr, (dW_host && bilinear) ? dW : nullptr, cws, stream,
                             early ? side.ev : nullptr, &recorded, (streamed && attempt == 0) ? &x_ready : nullptr, fb));
-    if (dY_host) {
+    if (dY_host && !grads_on_device) {
       cudaStream_t cs = stream;
       if (early && recorded) {
         MI_HOST_CUDA(cudaStreamWaitEvent(side.stream, side.ev, 0));
@@ -2148,8 +2170,8 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
       MI_HOST_CUDA(cudaMemcpyAsync(dY_host, dY, nBD * 4, cudaMemcpyDeviceToHost, cs));
     }
     MI_HOST_CUDA(cudaMemcpyAsync(loss_out_host, loss, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    if (dX_host) MI_HOST_CUDA(cudaMemcpyAsync(dX_host, dX, nBD * 4, cudaMemcpyDeviceToHost, stream));
-    if (dW_host && bilinear) MI_HOST_CUDA(cudaMemcpyAsync(dW_host, dW, nDD * 4, cudaMemcpyDeviceToHost, stream));
+    if (dX_host && !grads_on_device) MI_HOST_CUDA(cudaMemcpyAsync(dX_host, dX, nBD * 4, cudaMemcpyDeviceToHost, stream));
+    if (dW_host && bilinear && !grads_on_device) MI_HOST_CUDA(cudaMemcpyAsync(dW_host, dW, nDD * 4, cudaMemcpyDeviceToHost, stream));
     MI_HOST_CUDA(cudaStreamSynchronize(stream));
     if (have_side) MI_HOST_CUDA(cudaStreamSynchronize(side.stream));
     if (attempt == 1) {          // same report as the device entry: [7] = rows that tripped the sampled pass
@@ -2165,6 +2187,22 @@ int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const 
   return MI_OK;
 }
 
+int mi_critic_loss_fwd_bwd_host(const float* X_host, const float* Y_host, const float* W_host, const int32_t* sid_host,
+                                int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                                double* loss_out_host, float* dX_host, float* dY_host, float* dW_host,
+                                void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream) {
+  return host_entry_impl(X_host, Y_host, W_host, sid_host, false, B, D, critic, estimator, precision, inv_tau, loss_out_host,
+                         dX_host, dY_host, dW_host, false, dev_scratch, dev_scratch_bytes, stream);
+}
+int mi_critic_loss_fwd_bwd_from_host(const void* X_host, const void* Y_host, const void* W_host, const int32_t* sid_host, int host_dtype,
+                                     int64_t B, int64_t D, int critic, int estimator, int precision, float inv_tau,
+                                     double* loss_out_host, float* dX_dev, float* dY_dev, float* dW_dev,
+                                     void* dev_scratch, size_t dev_scratch_bytes, mi_stream_t stream) {
+  if (host_dtype != 0 && host_dtype != 1) return MI_ERR_BAD_ARG;
+  return host_entry_impl(X_host, Y_host, W_host, sid_host, host_dtype == 1, B, D, critic, estimator, precision, inv_tau, loss_out_host,
+                         dX_dev, dY_dev, dW_dev, true, dev_scratch, dev_scratch_bytes, stream);
+}
+
 int mi_dist_ctx_create(void* nccl_comm, mi_dist_ctx** out) {
   MI_TRY(device_check());
   if (!nccl_comm || !out) return MI_ERR_BAD_ARG;
@@ -2176,8 +2214,9 @@ int mi_dist_ctx_create(void* nccl_comm, mi_dist_ctx** out) {
   MI_NCCL(nc.comm_rank(nccl_comm, &c->rank));
   MI_CUDA(cudaGetDevice(&c->device));
   MI_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  MI_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
   cudaEvent_t* evs[] = {&c->ev_in, &c->ev_lamloc, &c->ev_sid, &c->ev_y, &c->ev_lam, &c->ev_s, &c->ev_k, &c->ev_m, &c->ev_rs,
-                        &c->ev_dwg, &c->ev_dw, &c->ev_drain};
+                        &c->ev_dwg, &c->ev_dw, &c->ev_drain, &c->ev_mask, &c->ev_start};
   for (cudaEvent_t* e : evs) MI_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   MI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->guard_host), sizeof(double), cudaHostAllocDefault));
   c->guard_host[0] = 0.0;
@@ -2187,10 +2226,12 @@ int mi_dist_ctx_create(void* nccl_comm, mi_dist_ctx** out) {
 void mi_dist_ctx_destroy(mi_dist_ctx* c) {
   if (!c) return;
   (void)cudaStreamSynchronize(c->comm_stream);
+  (void)cudaStreamSynchronize(c->aux_stream);
   cudaEvent_t evs[] = {c->ev_in, c->ev_lamloc, c->ev_sid, c->ev_y, c->ev_lam, c->ev_s, c->ev_k, c->ev_m, c->ev_rs, c->ev_dwg, c->ev_dw,
-                       c->ev_drain};
+                       c->ev_drain, c->ev_mask, c->ev_start};
   for (cudaEvent_t e : evs) (void)cudaEventDestroy(e);
   (void)cudaStreamDestroy(c->comm_stream);
+  (void)cudaStreamDestroy(c->aux_stream);
   (void)cudaFreeHost(c->guard_host);
   delete c;
 }

@@ -70,7 +70,8 @@ int nccl_fail(int r, const char* where) {
 struct mi_dist_ctx {
   ncclComm_p comm; int rank, world, device;
   cudaStream_t comm_stream;
-  cudaEvent_t ev_in, ev_lamloc, ev_sid, ev_y, ev_lam, ev_s, ev_k, ev_m, ev_rs, ev_dwg, ev_dw, ev_drain;
+  cudaStream_t aux_stream;     // the negatives-mask pre-pass of the whole column set runs here, beside the projection / references
+  cudaEvent_t ev_in, ev_lamloc, ev_sid, ev_y, ev_lam, ev_s, ev_k, ev_m, ev_rs, ev_dwg, ev_dw, ev_drain, ev_mask, ev_start;
   double* guard_host;      // pinned: the merged guard count of the step in flight
 };
 
@@ -108,6 +109,9 @@ int sharded_impl(mi_dist_ctx* ctx, int world, int rank, const void* X_, const vo
   b.oq_raw = (bilinear || !dX) ? ws.take<float>(static_cast<size_t>(Bl) * D) : nullptr;      // dot: dX doubles as the raw buffer
   b.ok_raw = ws.take<float>(static_cast<size_t>(Bg) * D);
   b.scal = ws.take<double>(8); b.scal_all = ws.take<double>(static_cast<size_t>(world) * 8); b.scratch8 = ws.take<double>(8);
+  const long long k_pad_all = cdiv(Bg, mi::TILE_N) * mi::TILE_N;
+  const MaskBuf all_mask = take_mask(ws, Bl, k_pad_all, Bg);      // rows: this rank's; columns: everyone's
+  const RedScratch red = take_red(ws);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   const size_t mk = ws.mark();
   const int incl = dv_like ? 0 : 1;
@@ -136,8 +140,10 @@ int sharded_impl(mi_dist_ctx* ctx, int world, int rank, const void* X_, const vo
   if (!nc.ok) { std::snprintf(g_cuda_err, sizeof(g_cuda_err), "libnccl.so.2 not found in the process"); return MI_ERR_CUDA; }
   const bf* X = static_cast<const bf*>(X_); const bf* Y = static_cast<const bf*>(Y_); const bf* W = static_cast<const bf*>(W_);
   if (!X || !Y || !sid_local || !loss_out || (bilinear && !W) || !dY || (!dX && !bilinear)) return MI_ERR_BAD_ARG;
-  cudaStream_t Cs = ctx->comm_stream;
+  cudaStream_t Cs = ctx->comm_stream, As = ctx->aux_stream;
   Bump none(nullptr, 0, false);
+  MI_CUDA(cudaEventRecord(ctx->ev_start, S));              // the auxiliary stream joins the step here (workspace reuse is ordered)
+  MI_CUDA(cudaStreamWaitEvent(As, ctx->ev_start, 0));
 
   // ---- exchange: ids, text embeddings (in place: the own rows are in their slot before the collective starts)
   MI_CUDA(cudaMemcpyAsync(b.Y_all + off * D, Y, static_cast<size_t>(Bl) * D * sizeof(bf), cudaMemcpyDeviceToDevice, S));
@@ -152,6 +158,11 @@ int sharded_impl(mi_dist_ctx* ctx, int world, int rank, const void* X_, const vo
     MI_CUDA(cudaEventRecord(ctx->ev_sid, Cs));
   }
   MI_CUDA(cudaEventRecord(ctx->ev_y, Cs));
+  // ---- the negatives mask of (own rows) x (all columns): needs the gathered ids only — built on the auxiliary stream while
+  //      the compute stream projects and samples
+  MI_CUDA(cudaStreamWaitEvent(As, ctx->ev_sid, 0));
+  MI_TRY(build_mask(all_mask, b.sid_all + off, b.sid_all, Bl, Bg, k_pad_all, As));
+  MI_CUDA(cudaEventRecord(ctx->ev_mask, As));
   // ---- local: projection, references from the own column block, lambda
   if (bilinear) {
     if (tsplit == 2) {
@@ -175,15 +186,19 @@ int sharded_impl(mi_dist_ctx* ctx, int world, int rank, const void* X_, const vo
   else MI_CUDA(cudaMemcpyAsync(b.lam, b.lam_loc, 4, cudaMemcpyDeviceToDevice, Cs));
   MI_CUDA(cudaEventRecord(ctx->ev_lam, Cs));
   // ---- the single pass over this rank's rows against ALL columns
-  MI_CUDA(cudaStreamWaitEvent(S, ctx->ev_sid, 0));
+  MI_CUDA(cudaStreamWaitEvent(S, ctx->ev_mask, 0));
   MI_CUDA(cudaMemsetAsync(b.flag, 0, sizeof(int), S));
   float* oq_raw = b.oq_raw ? b.oq_raw : dX;
   MI_TRY(single_pass_impl(To, Ya, b.sid_all + off, b.sid_all, off, Bl, Bg, D, inv_tau, incl, precision, gam, b.ref, b.lam, b.diag,
                           b.rows, oq_raw, b.ok_raw, b.wrow, b.flag, ws, S, ctx->ev_k, b.scal, ctx->ev_s, ctx->ev_y, nullptr, nullptr,
-                          /*k_local_valid=*/true, nullptr, ctx->ev_lam));
+                          /*k_local_valid=*/true, &all_mask, ctx->ev_lam, /*defer_reduce=*/true));
   ws.release(mk);
-  // ---- scalars: exchange + merge on the communication stream (under the contractions); the guard goes to the host
+  // ---- scalars: reduce (this rank's rows), exchange and merge on the communication stream, under the contractions; the guard
+  //      goes to the host
   MI_CUDA(cudaStreamWaitEvent(Cs, ctx->ev_s, 0));
+  MI_TRY(reduce_rows(b.rows, Bl, b.scal, red, Cs));
+  flag_to_scal_kernel<<<1, 1, 0, Cs>>>(b.flag, b.scal, nullptr);
+  MI_LAUNCH_CHECK("flag_to_scal_kernel");
   if (world > 1) MI_NCCL(nc.all_gather(b.scal, b.scal_all, 8, kNcclFloat64, ctx->comm, Cs));
   else MI_CUDA(cudaMemcpyAsync(b.scal_all, b.scal, 64, cudaMemcpyDeviceToDevice, Cs));
   merge_scal_kernel<<<1, 32, 0, Cs>>>(b.scal_all, world, b.scratch8);

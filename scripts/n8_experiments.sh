@@ -19,9 +19,8 @@ print(sys.argv[1], f"{d['ms_per_step']:.3f} ms/step", f"{d['value']:.4e} pairs/s
 PY
   grep per-step "gpurun_out/bench_n${N}_$name.err" >> "$out"
 }
-run own_first "" MI_OWN_COLUMNS_FIRST=1
-run base "--no-e2e" MI_OWN_COLUMNS_FIRST=0
-run own_first_again "--no-e2e" MI_OWN_COLUMNS_FIRST=1
+run c_step "" MI_SHARDED_IMPL=c
+run python_step "--no-e2e" MI_SHARDED_IMPL=python
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     scripts/dist_timeline.py > gpurun_out/timeline_n${N}.md 2> gpurun_out/timeline_n${N}.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \

@@ -407,6 +407,32 @@ def test_host_buffer_abi_matches_device_call(env):
     assert _rel(dX, ref["dX"]) < 1e-3 and _rel(dY, ref["dY"]) < 1e-3 and _rel(dW, ref["dW"]) < 1e-3
 
 
+def test_from_host_abi_bf16_inputs_device_gradients(env):
+    """mi_critic_loss_fwd_bwd_from_host (the data-loader form: bf16 OR fp32 embeddings in pinned host memory, loss back to the
+    host, gradients left in device buffers) == the device-pointer call, over several streamed row panels."""
+    mi_b200, ops, mo, dev = env
+    from mi_b200 import _lib
+    lib = _lib.load()
+    B, D = 24576, 64
+    X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=10, dup_frac=0.05, bilinear=True)
+    Xb, Yb, Wb = X.bfloat16(), Y.bfloat16(), W.bfloat16()
+    sh = sid.to(torch.int32).contiguous().pin_memory()
+    ref, rX, rY, rW = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), Wb.to(dev), sh.to(dev), "dv", "fast", 1.0, True)
+    torch.cuda.synchronize()
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    n = lib.mi_critic_host_scratch_bytes(B, D, 1, 0, 0, 1)
+    scratch = torch.empty(n, dtype=torch.uint8, device=dev)
+    for host_dtype, (Xh, Yh, Wh) in ((1, (Xb, Yb, Wb)), (0, (Xb.float(), Yb.float(), Wb.float()))):
+        Xh, Yh, Wh = Xh.contiguous().pin_memory(), Yh.contiguous().pin_memory(), Wh.contiguous().pin_memory()
+        loss = torch.zeros(8, dtype=torch.float64).pin_memory()
+        gX, gY, gW = torch.zeros(B, D, device=dev), torch.zeros(B, D, device=dev), torch.zeros(D, D, device=dev)
+        st = lib.mi_critic_loss_fwd_bwd_from_host(p(Xh), p(Yh), p(Wh), p(sh), host_dtype, B, D, 1, 0, 0, 1.0, p(loss), p(gX), p(gY), p(gW),
+                                                  p(scratch), n, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert st == 0, lib.mi_status_string(st)
+        assert float(loss[7]) == 0.0 and abs(float(loss[0]) - float(ref[0])) < 1e-6 * max(1.0, abs(float(ref[0])))
+        assert _rel(gX, rX.cpu()) < 1e-2 and _rel(gY, rY.cpu()) < 1e-2 and _rel(gW, rW.cpu()) < 1e-2   # (fast mode: see below)
+
+
 @pytest.mark.parametrize("critic", ["dot", "bilinear"])
 def test_host_buffer_abi_streams_panels(env, critic):
     """Several row panels: the host entry point feeds the image embeddings panel by panel from a second stream (cast and
