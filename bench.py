@@ -486,6 +486,18 @@ def run_ours(a):
         X2, Y2, W2, s2 = X2.to(dev).bfloat16(), Y2.to(dev).bfloat16(), W2.to(dev).bfloat16(), s2.to(torch.int32).to(dev)
         run_variant("config2 bilinear + InfoNCE (reference form)", X2, Y2, W2, s2, "infonce", "fast", 1.0, steps=20)
         run_variant("config2 bilinear + symmetric InfoNCE", X2, Y2, W2, s2, "infonce_sym", "fast", 1.0, steps=20)
+        # the same step replayed from a CUDA graph (ops.GraphedCriticStep): at this size the direct call is host-launch bound
+        gstep = ops.GraphedCriticStep(4096, 768, bilinear=True, estimator="infonce", precision="fast", inv_tau=1.0, device=dev)
+        for _ in range(3):
+            gstep(X2, Y2, W2, s2)
+        g_ms, _, _, gr = timed(lambda: gstep(X2, Y2, W2, s2), 20)
+        g_ms /= 20
+        variants.append({"name": "config2 bilinear + InfoNCE, CUDA-graph replay (incl. the copies into the graph's static inputs)",
+                         "B": 4096, "D": 768, "critic": "bilinear", "estimator": "infonce", "precision": "fast", "ms_per_step": g_ms,
+                         "pairs_per_s": 4096 * 4096 / (g_ms * 1e-3), "f_alg_tflops": f_alg(4096, 768, True) / (g_ms * 1e-3) / 1e12,
+                         "frac_of_sustained_peak": f_alg(4096, 768, True) / (g_ms * 1e-3) / 1e12 / pk_v["sustained"],
+                         "frac_of_burst_peak": f_alg(4096, 768, True) / (g_ms * 1e-3) / 1e12 / pk_v["burst"],
+                         "loss": float(gr[0][0]), "guard_rows": float(gr[0][7]), "path": "single pass (exact references), graph replay"})
 
     launches_t = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
