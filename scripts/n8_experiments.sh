@@ -20,7 +20,6 @@ PY
   grep per-step "gpurun_out/bench_n${N}_$name.err" >> "$out"
 }
 run c_step "" MI_SHARDED_IMPL=c
-run python_step "--no-e2e" MI_SHARDED_IMPL=python
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     scripts/dist_timeline.py > gpurun_out/timeline_n${N}.md 2> gpurun_out/timeline_n${N}.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
