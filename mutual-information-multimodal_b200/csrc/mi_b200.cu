@@ -1016,7 +1016,7 @@ RedScratch take_red(Bump& ws) {
 // {max, sum-exp, sums} of the per-row statistics -> scal[8]; the ticket is zeroed here (stream ordered), the kernel resets it
 int reduce_rows(const float* row_out, long long rows, double* scal, const RedScratch& red, cudaStream_t stream) {
   MI_CUDA(cudaMemsetAsync(red.ticket, 0, sizeof(unsigned), stream));
-  const int nb = rows >= 8192 ? kRedBlocks : 1;
+  const int nb = static_cast<int>(std::min<long long>(kRedBlocks, std::max<long long>(1, rows / 2048)));
   stats_reduce_mb_kernel<<<nb, 256, 0, stream>>>(reinterpret_cast<const float4*>(row_out), static_cast<int>(rows), scal, red.part,
                                                  red.ticket, t_run_if);
   MI_LAUNCH_CHECK("stats_reduce_mb_kernel");

@@ -111,7 +111,6 @@ int sharded_impl(mi_dist_ctx* ctx, int world, int rank, const void* X_, const vo
   b.scal = ws.take<double>(8); b.scal_all = ws.take<double>(static_cast<size_t>(world) * 8); b.scratch8 = ws.take<double>(8);
   const long long k_pad_all = cdiv(Bg, mi::TILE_N) * mi::TILE_N;
   const MaskBuf all_mask = take_mask(ws, Bl, k_pad_all, Bg);      // rows: this rank's; columns: everyone's
-  const RedScratch red = take_red(ws);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   const size_t mk = ws.mark();
   const int incl = dv_like ? 0 : 1;
@@ -191,14 +190,13 @@ int sharded_impl(mi_dist_ctx* ctx, int world, int rank, const void* X_, const vo
   float* oq_raw = b.oq_raw ? b.oq_raw : dX;
   MI_TRY(single_pass_impl(To, Ya, b.sid_all + off, b.sid_all, off, Bl, Bg, D, inv_tau, incl, precision, gam, b.ref, b.lam, b.diag,
                           b.rows, oq_raw, b.ok_raw, b.wrow, b.flag, ws, S, ctx->ev_k, b.scal, ctx->ev_s, ctx->ev_y, nullptr, nullptr,
-                          /*k_local_valid=*/true, &all_mask, ctx->ev_lam, /*defer_reduce=*/true));
+                          /*k_local_valid=*/true, &all_mask, ctx->ev_lam));
   ws.release(mk);
-  // ---- scalars: reduce (this rank's rows), exchange and merge on the communication stream, under the contractions; the guard
-  //      goes to the host
+  // ---- scalars: exchange and merge on the communication stream, under the contractions; the guard goes to the host.
+  //      (The rows are reduced inside the pass, on the compute stream, BEFORE the dY contraction is launched: the engine's
+  //      persistent grid takes every SM, so a collective that is not already running when it starts waits for it to end —
+  //      measured: deferring the reduction to this stream delayed the scalar all-gather by the whole contraction.)
   MI_CUDA(cudaStreamWaitEvent(Cs, ctx->ev_s, 0));
-  MI_TRY(reduce_rows(b.rows, Bl, b.scal, red, Cs));
-  flag_to_scal_kernel<<<1, 1, 0, Cs>>>(b.flag, b.scal, nullptr);
-  MI_LAUNCH_CHECK("flag_to_scal_kernel");
   if (world > 1) MI_NCCL(nc.all_gather(b.scal, b.scal_all, 8, kNcclFloat64, ctx->comm, Cs));
   else MI_CUDA(cudaMemcpyAsync(b.scal_all, b.scal, 64, cudaMemcpyDeviceToDevice, Cs));
   merge_scal_kernel<<<1, 32, 0, Cs>>>(b.scal_all, world, b.scratch8);
