@@ -6,6 +6,7 @@ path runs in libmi_b200.so.  All functions raise ``MIError`` on failure — ther
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple, Union
 
 import torch
@@ -452,6 +453,8 @@ def sharded_step(X_local: torch.Tensor, Y_local: torch.Tensor, W: Optional[torch
     _need_cuda(X_local, Y_local, W, sid_local)
     lib = _lib.load()
     ctx, rank, world, _ = dist_context(group)
+    if "MI_RS_RESERVE_SMS" in os.environ:       # (experiment knob) SMs the dT contraction leaves to the overlapped reduce-scatter
+        lib.mi_set_overlap_reserve_sms(int(os.environ["MI_RS_RESERVE_SMS"]))
     X, Y = as_bf16(X_local), as_bf16(Y_local)
     Wb = None if W is None else as_bf16(W)
     if sid_local.dtype != torch.int32:

@@ -16,4 +16,7 @@ Parity status
   reference (its critic is a concat-MLP, its "infonce" is DV + log N): for those
   the oracle is PARITY UNPINNED by the reference; it is anchored to it only
   through the DV path (same score matrix, same mask, same pair ordering).
+* ``oracle.chunked_oracle`` (the same matrix form with the scores formed 4096 rows at a time, so that it runs at
+  B = 65536 on whatever device the inputs live on) is pinned to ``oracle.matrix_oracle`` by
+  ``tests/test_oracle.py::test_chunked_oracle_equals_matrix_oracle``.
 """
