@@ -291,6 +291,28 @@ def test_single_pass_guard_falls_back_inside_the_library(env, est):
         ops.set_ref_sample_columns(2048)
 
 
+def test_guard_fallback_over_several_panels(env):
+    """The predicated exact repeat when the step spans several row panels (B = 20480 at D = 64: three panels) — checked against
+    the chunked oracle on the device (the CPU matrix form would need ~20 GB here)."""
+    mi_b200, ops, mo, dev = env
+    from oracle import chunked_oracle as co
+    B, D, inv_tau = 20480, 64, 0.125
+    ops.set_ref_sample_columns(256)
+    try:
+        Xb, Yb, sid = _guard_case(mo, B, D, 13, True)
+        Xd, Yd, sd = Xb.bfloat16().to(dev), Yb.bfloat16().to(dev), sid.to(dev)
+        for est in ("dv", "infonce_row"):
+            ref = co.critic_loss_chunked(Xd.float(), Yd.float(), sd, None, inv_tau, est, chunk=4096)
+            out, dX, dY, _ = ops.critic_loss_fwd_bwd(Xd, Yd, None, sd, est, "strict", inv_tau, True)
+            torch.cuda.synchronize()
+            assert float(out[7]) >= 1.0
+            _loss_ok(out[0].item(), ref, 1e-4)
+            rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+            assert rel(dX, ref["dX"]) < 1e-3 and rel(dY, ref["dY"]) < 1e-3, (est, rel(dX, ref["dX"]), rel(dY, ref["dY"]))
+    finally:
+        ops.set_ref_sample_columns(2048)
+
+
 def test_sampled_references_on_hostile_scales(env):
     """The cases the round-1 Cauchy-Schwarz bound could not handle stay on the single pass with a
     clear guard: (a) a huge-norm image row orthogonal to every text embedding (bound ~1e3 above its scores), (b) scores
@@ -550,9 +572,10 @@ def _nccl_worker(rank, world, port, ret):
         X, Y, sid, W = mo.synthetic_embeddings(B, D, seed=11, dup_frac=0.05, bilinear=True)
         Bl = B // world
         sl = slice(rank * Bl, (rank + 1) * Bl)
-        cases = [(est, planted, impl) for impl in ("c", "python")
+        cases = [(est, planted, impl, "strict") for impl in ("c", "python")
                  for est, planted in (("dv", False), ("infonce_row", False), ("infonce_sym", False), ("dv", True))]
-        for est, planted, impl in cases:
+        cases += [("dv", False, "c", "fast"), ("infonce_row", False, "c", "fast")]        # the benchmark's mode
+        for est, planted, impl, prec in cases:
             # "c": the whole step as ONE library call that issues its own NCCL collectives (csrc/sharded.cuh);
             # "python": the same step orchestrated op by op through torch.distributed (mi_b200/dist.py)
             os.environ["MI_SHARDED_IMPL"] = impl
@@ -560,14 +583,14 @@ def _nccl_worker(rank, world, port, ret):
             if planted:                                      # guard trip on rank 0 only: both ranks must take the exact path
                 ops.set_ref_sample_columns(64)
                 Xb = Xb.clone(); Yb = Yb.clone(); Yb[7] = -Yb[5]; Xb[7] = (80.0 * Yb[5].float()).bfloat16()
-            full = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), Wb.to(dev), sid.to(torch.int32).to(dev), est, "strict", 1.0, True,
+            full = ops.critic_loss_fwd_bwd(Xb.to(dev), Yb.to(dev), Wb.to(dev), sid.to(torch.int32).to(dev), est, prec, 1.0, True,
                                            two_pass=True)
             out, dX, dY, dW = mdist.sharded_critic_loss_fwd_bwd(Xb[sl].to(dev), Yb[sl].to(dev), Wb.to(dev),
-                                                               sid[sl].to(torch.int32).to(dev), est, "strict", 1.0, True)
+                                                               sid[sl].to(torch.int32).to(dev), est, prec, 1.0, True)
             torch.cuda.synchronize()
             ops.set_ref_sample_columns(2048)
             r = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
-            errs[(est, planted, impl)] = [abs(float(out["loss"]) - float(full[0][0])) / abs(float(full[0][0])), r(dX, full[1][sl]),
+            errs[(est, planted, impl, prec)] = [abs(float(out["loss"]) - float(full[0][0])) / abs(float(full[0][0])), r(dX, full[1][sl]),
                                           r(dY, full[2][sl]), r(dW, full[3]), float(out.get("guard", 0.0))]
         ret[rank] = errs
     finally:
@@ -588,9 +611,10 @@ def test_sharded_path_nccl_2gpu_equals_single_gpu(env):
     mp.spawn(_nccl_worker, args=(2, port, ret), nprocs=2, join=True)
     assert len(ret) == 2
     for rank in range(2):
-        for (est, planted, impl), e in ret[rank].items():
-            assert e[0] < 1e-5 and max(e[1:4]) < 1e-4, (rank, est, planted, impl, e)
-            assert (e[4] != 0.0) == planted, (rank, est, planted, impl, e)
+        for (est, planted, impl, prec), e in ret[rank].items():
+            # strict: both sides carry 16 significant bits; fast: a 1-ulp fp32 difference in a row sum may flip a bf16 rounding
+            assert e[0] < 1e-5 and max(e[1:4]) < (1e-4 if prec == "strict" else 1e-2), (rank, est, planted, impl, prec, e)
+            assert (e[4] != 0.0) == planted, (rank, est, planted, impl, prec, e)
 
 
 def test_cuda_graph_replay_equals_direct_call(env):
