@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("MI_LIB_PATH") or os.path.join(_HERE, "libmi_b200.so")     # (MI_LIB_PATH: experiment builds)
+LIB_PATH = os.path.join(_HERE, "libmi_b200.so")
 
 c_i64, c_int, c_f32, c_sz, c_vp = C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_void_p
 

@@ -186,10 +186,14 @@ class FusedCritic(nn.Module):
     Called with a ``PairBatch`` it returns a ``ScoreHandle`` (fused path).  Called with an explicit
     ``[N, 2D]`` pair tensor (the reference's ``mi_input``) it evaluates the same critic row by row with
     torch ops and returns ``[N, 1]`` logits — the compatibility path for small batches.
+
+    The fused loss call never synchronises with the host (the reference adds two syncs per step on this path:
+    mi_critics.py:10 and main_utils.py:233).  A batch without any negative pair gives ``nan`` (dv) / ``-inf`` (infonce)
+    exactly like the reference; ``check_negatives=True`` turns that into an ``MIError`` at the price of one host read.
     """
 
     def __init__(self, dim: int, critic: str = "bilinear", temperature: Optional[float] = None,
-                 precision: str = "fast", check_negatives: bool = True):
+                 precision: str = "fast", check_negatives: bool = False):
         super().__init__()
         if critic not in ("dot", "bilinear"):
             raise ValueError("critic must be 'dot' or 'bilinear'")
@@ -251,7 +255,7 @@ class FusedMLPCritic(nn.Sequential):
     functions run the fused CUDA path: layer 1 is evaluated once per image and once per text
     (``W1 [x;y] = W1x x + W1y y``), layers 2-3 on tensor cores for all B^2 pairs, the pair tensor is never built."""
 
-    def __init__(self, dim: int = 768, hidden_dims=(1024, 512), precision: str = "strict", check_negatives: bool = True):
+    def __init__(self, dim: int = 768, hidden_dims=(1024, 512), precision: str = "strict", check_negatives: bool = False):
         if len(hidden_dims) != 2:
             raise ValueError("the fused path implements the reference's two-hidden-layer critic")
         h1, h2 = int(hidden_dims[0]), int(hidden_dims[1])

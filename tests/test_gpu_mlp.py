@@ -199,6 +199,6 @@ def test_forward_only_and_no_negatives(env):
     assert g is None and S is None
     ref = mlp_oracle.mlp_loss_matrix_form(X.float(), Y.float(), [int(v) for v in sid], p, "dv")
     assert _loss_rel(loss[0].item(), ref["loss"]) < 1e-4
-    critic = mi_b200.FusedMLPCritic(D, (64, 32)).to(dev)
+    critic = mi_b200.FusedMLPCritic(D, (64, 32), check_negatives=True).to(dev)
     with pytest.raises(mi_b200.MIError):
         mi_b200.dv_bound_loss(critic(mi_b200.create_mi_pairs(X.to(dev).float(), Y.to(dev).float(), ["same"] * B, dev)), B, dev)

@@ -162,14 +162,20 @@ def test_edge_cases(env):
     mi_b200, ops, mo, dev = env
     D = 16
     x = torch.randn(8, D, device=dev)
-    critic = mi_b200.FusedCritic(D, "dot").to(dev)
-    # every study id equal -> no negatives: reference gives nan / -inf, the fused path refuses
+    critic = mi_b200.FusedCritic(D, "dot", check_negatives=True).to(dev)
+    # every study id equal -> no negatives: with check_negatives the fused path refuses ...
     pairs = mi_b200.create_mi_pairs(x, x, ["7"] * 8, dev)
     with pytest.raises(ops.MIError):
         mi_b200.dv_bound_loss(critic(pairs), 8, dev)
     # B = 1 likewise
     with pytest.raises(ops.MIError):
         mi_b200.dv_bound_loss(critic(mi_b200.create_mi_pairs(x[:1], x[:1], ["1"], dev)), 1, dev)
+    # ... and by default (no host read at all) it returns what the reference returns: nan (dv, mi_critics.py:9-12) / -inf (infonce)
+    plain = mi_b200.FusedCritic(D, "dot").to(dev)
+    xg = x.clone().requires_grad_(True)
+    l_dv = mi_b200.dv_bound_loss(plain(mi_b200.create_mi_pairs(xg, xg, ["7"] * 8, dev)), 8, dev)
+    l_nce = mi_b200.infonce_bound_loss(plain(mi_b200.create_mi_pairs(xg, xg, ["7"] * 8, dev)), 8, dev)
+    assert tuple(l_dv.shape) == (1,) and math.isnan(float(l_dv)) and float(l_nce) == float("-inf")
     # D not a multiple of 8 is rejected by the ABI (TMA needs 16-byte row pitch)
     with pytest.raises(ops.MIError):
         c2 = mi_b200.FusedCritic(12, "dot").to(dev)
