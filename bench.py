@@ -499,6 +499,31 @@ def run_ours(a):
                          "frac_of_burst_peak": f_alg(4096, 768, True) / (g_ms * 1e-3) / 1e12 / pk_v["burst"],
                          "loss": float(gr[0][0]), "guard_rows": float(gr[0][7]), "path": "single pass (exact references), graph replay"})
 
+        # the reference's own critic (main_utils.py:77: make_mlp(1536, [1024, 512]) on every pair) + DV, B = 4096
+        Bm, Dm, H1m, H2m = 4096, 768, 1024, 512
+        gm = torch.Generator().manual_seed(5)
+        Xm = torch.relu(torch.randn(Bm, Dm, generator=gm)).to(dev)
+        Ym = torch.tanh(torch.randn(Bm, Dm, generator=gm)).to(dev)
+        sm = torch.arange(Bm, dtype=torch.int32, device=dev)
+        torch.manual_seed(1)
+        mlp = mi_b200.FusedMLPCritic(Dm, (H1m, H2m)).to(dev)
+        pm = tuple(t.detach() for t in (mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, mlp[4].weight, mlp[4].bias))
+        fa_m = 3 * 2.0 * Bm * Bm * H1m * H2m + 3 * 2.0 * (2 * Bm) * Dm * H1m
+        for prec in ("fast", "strict"):
+            fn = lambda: ops.mlp_critic_loss_fwd_bwd(Xm, Ym, pm, sm, "dv", prec, True, False)
+            for _ in range(2):
+                fn()
+            m_ms, _, _, mr = timed(fn, 3)
+            m_ms /= 3
+            lo = mr[0].cpu()
+            variants.append({"name": "concat-MLP critic make_mlp(1536, [1024, 512]) + DV, " + prec, "B": Bm, "D": Dm, "critic": "mlp",
+                             "estimator": "dv", "precision": prec, "ms_per_step": m_ms, "pairs_per_s": Bm * Bm / (m_ms * 1e-3),
+                             "f_alg_tflops": fa_m / (m_ms * 1e-3) / 1e12,
+                             "frac_of_sustained_peak": fa_m / (m_ms * 1e-3) / 1e12 / pk_v["sustained"],
+                             "frac_of_burst_peak": fa_m / (m_ms * 1e-3) / 1e12 / pk_v["burst"],
+                             "loss": float(lo[0]), "guard_rows": float(lo[7]),
+                             "path": "two-pass repeat (guard tripped)" if float(lo[7]) != 0.0 else "single pass"})
+
     launches_t = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(launches_t)

@@ -285,11 +285,18 @@ int64_t mi_launch_count(void);
  * mi_profile_read drains the records: ms[k] / launches[k], k = 0 score statistics, 1 dS panel, 2 GEMM. */
 void mi_set_profiling(int on);
 int mi_profile_read(double* ms /*[3]*/, int64_t* launches /*[3]*/);
+/* the same with n_kinds <= 6 buckets: 3 = MLP-critic single pass (forward + dZ2), 4 = MLP-critic dZ1 contraction with fused
+ * reductions, 5 = MLP-critic two-pass epilogues (logits / dZ2) */
+int mi_profile_read_kinds(double* ms, int64_t* launches, int n_kinds);
 
 /* bring-up / A-B knob: 2 (default) = CTA pairs, cta_group::2 MMAs with M = 256; 1 = single-CTA M = 128.
  * Also settable through the environment variable MI_CTA_GROUP before the first call. */
 void mi_set_cta_group(int group);
 void mi_set_mlp_panel_pairs(int64_t pairs); /* pairs per row panel of the MLP-critic path (default 2^20; tests use small values) */
+/* MLP-critic A/B knob.  bit 0: dv / infonce run as a single pass (reference logit from a sample of pairs, Z2 formed once,
+ * device-predicated two-pass repeat if the guard trips); bit 1: the dZ1 reductions are fused into their GEMM's epilogue.
+ * Default 3; 0 = the two-pass sequence for every estimator; negative = default. */
+void mi_set_mlp_mode(int mode);
 /* Multi-GPU overlap: the tile-engine launches that follow `event_after_outk` inside mi_score_single_pass / mi_score_grad
  * use (SM count - n) SMs, so the collective the caller starts at that event (reduce-scatter of the dY contributions)
  * finds free SMs instead of queueing behind a persistent 148-CTA grid.  0 (default) = use every SM. */

@@ -18,10 +18,12 @@ PROTOTYPES = {
     "mi_launch_count": (c_i64, []),
     "mi_set_profiling": (None, [c_int]),
     "mi_profile_read": (c_int, [c_vp, c_vp]),
+    "mi_profile_read_kinds": (c_int, [c_vp, c_vp, c_int]),
     "mi_set_cta_group": (None, [c_int]),
     "mi_set_ref_sample_columns": (None, [c_i64]),
     "mi_set_overlap_reserve_sms": (None, [c_int]),
     "mi_set_mlp_panel_pairs": (None, [c_i64]),
+    "mi_set_mlp_mode": (None, [c_int]),
     "mi_get_cta_group": (c_int, []),
     "mi_gemm_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_i64,
                              c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),

@@ -15,6 +15,7 @@
 // each CTA loads its own 128 A rows and one 128-row half of the 256-row B tile, the leader issues
 // cta_group::2 MMAs with M = 256 and commits are multicast to both CTAs.
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace mi {
@@ -55,7 +56,8 @@ struct Sched {
   int n_split;    // contiguous N-range splits per M block
   int n_ksplit;   // K splits (split-K GEMM), 1 otherwise
   int nt_base;    // first N tile of this launch (a launch may cover a sub-range of the columns)
-  int order;      // 0: m fastest (concurrent units share the N range), 1: ksplit, split fastest
+  int order;      // 0: m fastest (concurrent units share the N range), 1: ksplit, split fastest,
+                  // 2: "column walk" (below)
   int k_blocks;   // number of K blocks (block_k wide) per tile, all segments
   // K segments: block kb belongs to segment kb / seg_len and reads A at K block a_seg[seg] + kb % seg_len,
   // B at b_seg[seg] + kb % seg_len.  One segment = plain GEMM; more = sums of products of hi/lo splits,
@@ -68,15 +70,34 @@ struct Sched {
   // Device-side launch predicate: when non-null and *run_if == 0 the whole grid returns at once.  The exact
   // fallback of the single pass is enqueued behind such a flag, so it costs a few empty launches unless needed.
   const int* run_if;
+  // order 2: the M blocks form a grid [n_il][grp] (m = il * grp + jb).  A unit is (N tile, jb, chunk of chunk_len
+  // consecutive il) and its items are the M blocks il * grp + jb of the chunk, all on the SAME N tile: the rows of
+  // consecutive items are `grp` M blocks apart, so an epilogue thread meets the same (jb-local row, column) cell of
+  // every il and can sum over il in registers (EpiMlpDa).
+  int grp, chunk_len, n_chunks, n_il;
 };
 
-struct Unit { int m, s, ks, nt0, nt1, kb0, kb1; };
+// A unit's work items: item `it` is the accumulator tile (M block m + it * m_step, N tile nt0 + it * nt_step).
+struct Unit { int m, s, ks, nt0, nt1, kb0, kb1, n_items, m_step, nt_step; };
 
-__device__ __forceinline__ int num_units(const Sched& sc) { return sc.n_mblk * sc.n_split * sc.n_ksplit; }
+__host__ __device__ __forceinline__ int num_units(const Sched& sc) {
+  return sc.order == 2 ? sc.n_ntile * sc.grp * sc.n_chunks : sc.n_mblk * sc.n_split * sc.n_ksplit;
+}
 __device__ __forceinline__ int sel4(const int (&a)[4], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
 
+template <bool kWalk>
 __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
   Unit r;
+  if (kWalk && sc.order == 2) {
+    const int nt = u % sc.n_ntile; int t = u / sc.n_ntile;      // the N tiles of an M block run concurrently (A tile from L2)
+    const int jb = t % sc.grp, il0 = (t / sc.grp) * sc.chunk_len;
+    r.m = il0 * sc.grp + jb; r.s = 0; r.ks = 0;
+    r.nt0 = sc.nt_base + nt; r.nt1 = r.nt0 + 1;
+    r.kb0 = 0; r.kb1 = sc.k_blocks;
+    r.n_items = sc.n_il - il0 < sc.chunk_len ? sc.n_il - il0 : sc.chunk_len;
+    r.m_step = sc.grp; r.nt_step = 0;
+    return r;
+  }
   if (sc.order == 0) {
     r.m = u % sc.n_mblk; int t = u / sc.n_mblk;
     r.s = t % sc.n_split; r.ks = t / sc.n_split;
@@ -88,6 +109,7 @@ __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
   r.nt1 = sc.nt_base + (int)(((long long)(r.s + 1) * sc.n_ntile) / sc.n_split);
   r.kb0 = (int)(((long long)r.ks * sc.k_blocks) / sc.n_ksplit);
   r.kb1 = (int)(((long long)(r.ks + 1) * sc.k_blocks) / sc.n_ksplit);
+  r.n_items = r.nt1 - r.nt0; r.m_step = 0; r.nt_step = 1;
   return r;
 }
 
@@ -151,10 +173,11 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t full0_lead = (kCG == 2) ? ptx::mapa(full0, 0) : full0;
     const uint64_t ta = reinterpret_cast<uint64_t>(&tmap_a), tb = reinterpret_cast<uint64_t>(&tmap_b);
     for (int u = pair_id; u < n_units; u += n_pairs) {
-      const Unit un = decode_unit(sc, u);
-      const int a_row = (un.m * kCG + (int)cta_rank) * BLOCK_M;
-      for (int nt = un.nt0; nt < un.nt1; ++nt) {
-        const int b_row = nt * TILE_N + (int)cta_rank * C::kBRows;
+      const Unit un = decode_unit<Epi::kWalk>(sc, u);
+      const int n_items = Epi::kWalk ? un.n_items : un.nt1 - un.nt0;
+      for (int it = 0; it < n_items; ++it) {
+        const int a_row = ((Epi::kWalk ? un.m + it * un.m_step : un.m) * kCG + (int)cta_rank) * BLOCK_M;
+        const int b_row = (Epi::kWalk ? un.nt0 : un.nt0 + it) * TILE_N + (int)cta_rank * C::kBRows;
         int seg = un.kb0 / sc.seg_len, w = un.kb0 - seg * sc.seg_len;
         int a_k = (sel4(sc.a_seg, seg) + w) * C::kBK, b_k = (sel4(sc.b_seg, seg) + w) * C::kBK;
         int a_m = a_row + sel4(sc.a_moff, seg);
@@ -206,8 +229,9 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint64_t db_hi = kBMN ? ptx::make_smem_desc_mn128(0, C::kBK * 128) : ptx::make_smem_desc_k128(0);
       uint32_t stage = 0, phase = 0, tile_cnt = 0;
       for (int u = pair_id; u < n_units; u += n_pairs) {
-        const Unit un = decode_unit(sc, u);
-        for (int nt = un.nt0; nt < un.nt1; ++nt) {
+        const Unit un = decode_unit<Epi::kWalk>(sc, u);
+        const int n_items = Epi::kWalk ? un.n_items : un.nt1 - un.nt0;
+        for (int it = 0; it < n_items; ++it) {
           const uint32_t as = tile_cnt & 1u, aphase = (tile_cnt >> 1) & 1u;
           ptx::mbar_wait_addr(tempty0 + as * 8u, aphase ^ 1u, 2);
           ptx::tc_fence_after();
@@ -243,7 +267,7 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ------------------------------------------------------------ epilogue (8 warps)
+    // ------------------------------------------------------------ epilogue (16 warps)
     const uint32_t quarter = warp & 3u;                 // TMEM lanes 32*quarter .. +31 (hardware: warp % 4)
     const uint32_t colq = (warp - kEpiWarp0) >> 2;        // 64-column quarter of the 256-column tile
     uint32_t tile_cnt = 0;
@@ -251,23 +275,48 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     Epi::init(ep, st);
     st.stage_smem = epi_smem + (warp - kEpiWarp0) * (Epi::kEpiSmemBytes / kNumEpiWarps);
     for (int u = pair_id; u < n_units; u += n_pairs) {
-      const Unit un = decode_unit(sc, u);
-      const int row = (un.m * kCG + (int)cta_rank) * BLOCK_M + (int)(quarter * 32u + lane);
-      Epi::unit_begin(ep, st, un, row, (int)colq);
-      for (int nt = un.nt0; nt < un.nt1; ++nt) {
-        const uint32_t as = tile_cnt & 1u, aphase = (tile_cnt >> 1) & 1u;
-        ptx::mbar_wait(&tmem_full_bar[as], aphase, 4);
-        ptx::tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t col_in_tile = colq * 64u + (uint32_t)c * 32u;
-          const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * TILE_N + col_in_tile;
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr, v);
+      const Unit un = decode_unit<Epi::kWalk>(sc, u);
+      const int row0 = (un.m * kCG + (int)cta_rank) * BLOCK_M + (int)(quarter * 32u + lane);
+      const int n_items = Epi::kWalk ? un.n_items : un.nt1 - un.nt0;
+      Epi::unit_begin(ep, st, un, row0, (int)colq);
+      if constexpr (Epi::kJoint) {
+        // The unit's (<= 2) N tiles are ONE logical tile: a first pass over both accumulator stages forms a per-row
+        // quantity that needs every column (Epi::pass1 ... Epi::mid, which may synchronise the 16 epilogue warps), the
+        // second pass re-reads the stages from TMEM, hands them back and runs Epi::chunk.
+        const uint32_t lane_addr = tmem_base + ((quarter * 32u) << 16) + colq * 64u;
+        for (int it = 0; it < n_items; ++it) {
+          const uint32_t tc = tile_cnt + (uint32_t)it, as = tc & 1u, aphase = (tc >> 1) & 1u;
+          ptx::mbar_wait(&tmem_full_bar[as], aphase, 4);
+          ptx::tc_fence_after();
+          {   // both 32-column chunks in flight before the wait: the first pass is short, TMEM latency would dominate it
+            uint32_t v0[32], v1[32];
+            ptx::tmem_ld_32x32(lane_addr + as * TILE_N, v0);
+            ptx::tmem_ld_32x32(lane_addr + as * TILE_N + 32u, v1);
+            ptx::tmem_ld_wait();
+            const int col = (un.nt0 + it) * TILE_N + (int)(colq * 64u);
+            Epi::pass1(ep, st, col, v0);
+            Epi::pass1(ep, st, col + 32, v1);
+          }
+        }
+        Epi::mid(ep, st, un, row0, (int)colq, epi_smem);
+        for (int it = 0; it < n_items; ++it) {
+          const uint32_t as = (tile_cnt + (uint32_t)it) & 1u;
+          const uint32_t base = lane_addr + as * TILE_N;
+          const int col = (un.nt0 + it) * TILE_N + (int)(colq * 64u);
+          // 16-column pieces; the next piece's TMEM read is in flight while the current one is processed
+          uint32_t va[16], vb[16];
+          ptx::tmem_ld_32x16(base, va);
           ptx::tmem_ld_wait();
-          if (c == 1) {
-            // this warp's last read of the accumulator stage is in registers: hand the stage back to the MMA
-            // issuer BEFORE the chunk is processed, so the MMAs of tile t+2 never wait for epilogue math / stores
+          ptx::tmem_ld_32x16(base + 16u, vb);
+          Epi::template chunk16<0>(ep, st, un, row0, col, va);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x16(base + 32u, va);
+          Epi::template chunk16<1>(ep, st, un, row0, col + 16, vb);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x16(base + 48u, vb);
+          Epi::template chunk16<2>(ep, st, un, row0, col + 32, va);
+          ptx::tmem_ld_wait();
+          {   // the stage's last read is in registers: hand it back to the MMA issuer
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -275,11 +324,60 @@ tile_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               else ptx::mbar_arrive_remote(&tmem_empty_bar[as], 0);
             }
           }
-          Epi::chunk(ep, st, un, row, nt * TILE_N + (int)col_in_tile, v);
+          Epi::template chunk16<3>(ep, st, un, row0, col + 48, vb);
         }
-        ++tile_cnt;
+        tile_cnt += (uint32_t)n_items;
+      } else {
+        for (int it = 0; it < n_items; ++it) {
+          const int row = Epi::kWalk ? row0 + it * un.m_step * (kCG * BLOCK_M) : row0;
+          const int nt = Epi::kWalk ? un.nt0 : un.nt0 + it;
+          const uint32_t as = tile_cnt & 1u, aphase = (tile_cnt >> 1) & 1u;
+          if constexpr (Epi::kChunk16) Epi::item_begin(ep, st, row, nt * TILE_N + (int)(colq * 64u));   // loads issued before the wait
+          ptx::mbar_wait(&tmem_full_bar[as], aphase, 4);
+          ptx::tc_fence_after();
+          if constexpr (Epi::kChunk16) {
+            auto quarter16 = [&](auto qc) {
+              constexpr int c = decltype(qc)::value;
+              const uint32_t col_in_tile = colq * 64u + (uint32_t)c * 16u;
+              uint32_t v[16];
+              ptx::tmem_ld_32x16(tmem_base + ((quarter * 32u) << 16) + as * TILE_N + col_in_tile, v);
+              ptx::tmem_ld_wait();
+              if (c == 3) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if constexpr (kCG == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
+                  else ptx::mbar_arrive_remote(&tmem_empty_bar[as], 0);
+                }
+              }
+              Epi::template chunk16<c>(ep, st, un, row, nt * TILE_N + (int)col_in_tile, v);
+            };
+            quarter16(std::integral_constant<int, 0>{}); quarter16(std::integral_constant<int, 1>{});
+            quarter16(std::integral_constant<int, 2>{}); quarter16(std::integral_constant<int, 3>{});
+          } else
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t col_in_tile = colq * 64u + (uint32_t)c * 32u;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * TILE_N + col_in_tile;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr, v);
+            ptx::tmem_ld_wait();
+            if (c == 1) {
+              // this warp's last read of the accumulator stage is in registers: hand the stage back to the MMA
+              // issuer BEFORE the chunk is processed, so the MMAs of tile t+2 never wait for epilogue math / stores
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (kCG == 1) ptx::mbar_arrive(&tmem_empty_bar[as]);
+                else ptx::mbar_arrive_remote(&tmem_empty_bar[as], 0);
+              }
+            }
+            Epi::chunk(ep, st, un, row, nt * TILE_N + (int)col_in_tile, v);
+          }
+          ++tile_cnt;
+        }
       }
-      Epi::unit_end(ep, st, un, row, (int)colq);
+      Epi::unit_end(ep, st, un, row0, (int)colq);
     }
     Epi::finish(ep, st, (int)colq);
   }
@@ -350,6 +448,9 @@ __device__ __forceinline__ uint32_t chunk_mask(const MaskInfo& mi, const MaskSta
 // ---- score statistics: per row online (max, sum-exp) over the negatives (the positive-pair scores
 //      S[q, q_offset+q] are O(B D) work and come from a separate dot-product kernel)
 struct EpiStats {
+  static constexpr bool kJoint = false;
+  static constexpr bool kWalk = false;
+  static constexpr bool kChunk16 = false;
   static constexpr int kEpiSmemBytes = 0;
   struct Params {
     MaskInfo mask;
@@ -407,6 +508,9 @@ struct EpiStats {
 //      Output: colpart[row block of 32][column] = log2-sum-exp2 of the column over those 32 rows (-inf if all excluded),
 //      merged over the row blocks by a small kernel.  S itself is never stored.
 struct EpiStatsRC {
+  static constexpr bool kJoint = false;
+  static constexpr bool kWalk = false;
+  static constexpr bool kChunk16 = false;
   static constexpr int kEpiSmemBytes = kNumEpiWarps * 2048;
   struct Params {
     MaskInfo mask;
@@ -504,6 +608,9 @@ struct EpiStatsRC {
 // shared memory and ONE lane hands the tile to the TMA engine (cp.async.bulk.tensor store): no per-thread global stores,
 // no address arithmetic, rows beyond the panel clipped by the tensor map.
 struct EpiPStore {
+  static constexpr bool kJoint = false;
+  static constexpr bool kWalk = false;
+  static constexpr bool kChunk16 = false;
   static constexpr int kEpiSmemBytes = kNumEpiWarps * 2048;
   struct Params {
     alignas(64) CUtensorMap tmap_p;   // the panel [q_rows, pitch] bf16, box 32 x 32, SWIZZLE_64B
@@ -615,6 +722,9 @@ struct EpiPStore {
 
 // ---- plain GEMM epilogue: C = alpha * (ACC - gamma * SUB) [+ C_prev]
 struct EpiStore {
+  static constexpr bool kJoint = false;
+  static constexpr bool kWalk = false;
+  static constexpr bool kChunk16 = false;
   static constexpr int kEpiSmemBytes = 0;
   struct Params {
     float* out_f32;            // optional
@@ -794,9 +904,27 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
   return v[0];      // column index = lane (bit s of the lane selected the half at every step)
 }
 
+// the same for 16 columns: lanes l and l ^ 16 both end with the sum over the 32 rows of column (l & 15)
+__device__ __forceinline__ float warp_column_sums16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int c = 0; c < s; ++c) {
+      const float send = up ? v[c] : v[c + s];
+      const float keep = up ? v[c + s] : v[c];
+      v[c] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 // ---- forward: logit[pair] = b3 + sum_n w3[n] relu(Z2[pair, n] + b2[n]); each epilogue warp owns a 64-column
 //      quarter of every 256-column tile, so it writes one partial per (pair, column quarter)
 struct EpiMlpFwd {
+  static constexpr bool kJoint = false;
+  static constexpr bool kWalk = false;
+  static constexpr bool kChunk16 = false;
   static constexpr int kEpiSmemBytes = 0;
   struct Params {
     const float* b2;       // [n_ntile * 256] zero padded
@@ -831,6 +959,9 @@ struct EpiMlpFwd {
 //      dW2 / dH1 contractions;  dw3[n] += sum_pairs g relu(Z2 + b2),  db2[n] += sum_pairs dZ2  (column sums over
 //      the warp's rows, kept per lane across the whole launch, one atomicAdd per column at the end).
 struct EpiMlpDz {
+  static constexpr bool kJoint = false;
+  static constexpr bool kWalk = false;
+  static constexpr bool kChunk16 = false;
   static constexpr int kEpiSmemBytes = 0;
   static constexpr int kMaxTiles = 2;       // H2 <= 512
   struct Params {
@@ -928,9 +1059,237 @@ struct EpiMlpDz {
   }
 };
 
+// ---- single pass (dv-like estimators): forward AND the backward through layer 3 / ReLU 2 from ONE Z2 accumulator.
+//      The softmax weights of the negatives are taken relative to a reference logit `ref` that is fixed BEFORE the
+//      pass (g~ = incl e^{S - ref}; every gradient is linear in g~, the caller multiplies by e^{ref - LSE} at the end),
+//      so nothing has to wait for the global log-sum-exp and Z2 is never recomputed.
+//      Rows are pairs in the padded panel order p = il * Bp + j (Bp = B rounded up to the M block): an M block has ONE
+//      image row i = r0 + il and consecutive text columns j.  Joint policy: pass1 forms this warp's share of the logit
+//      (64 of the up to 512 columns per tile), `mid` adds the four column quarters through shared memory (one named
+//      barrier of the 16 epilogue warps per unit, double-buffered slots), derives g~ and the row statistics, and the
+//      second pass is EpiMlpDz's chunk with that g~.
+constexpr float kMlpSpScale = 1.6940658945086007e-21f;    // 2^-69: g~ = e^{S - max_sample} 2^-69
+constexpr double kMlpSpMargin = 47.82715406979468;        // 69 ln 2
+struct EpiMlpSp {
+  static constexpr bool kJoint = true;
+  static constexpr bool kWalk = false;
+  static constexpr bool kChunk16 = false;
+  static constexpr int kEpiSmemBytes = 2 * kColQuarters * BLOCK_M * 4;     // 2 slots x [4 column quarters][128 rows] fp32
+  static constexpr int kMaxTiles = 2;       // H2 <= 512
+  struct Params {
+    const float* b2;       // [n_ntile * 256] zero padded
+    const float* w3;       // [n_ntile * 256] zero padded
+    const float* b3;       // [1]
+    const float* ref;      // [1] maximum logit of the sample (the reference logit is this + kMlpSpMargin)
+    const int* sid;        // [B] study ids (negatives: sid[i] != sid[j], main_utils.py:105)
+    int B, Bp, r0, rr;     // batch, padded batch, first image row of the panel, image rows in the panel
+    int cols;              // H2
+    __nv_bfloat16* dz;     // [rr * Bp, pitch]  g~ w3 [Z2 + b2 > 0]
+    __nv_bfloat16* dz_lo;  // residual half (strict) or nullptr
+    long long pitch;
+    float* dw3;            // [n_ntile * 256] accumulators (atomicAdd), in g~ units
+    float* db2;
+    float* rowsum;         // [B] += sum_j g~          (atomicAdd)
+    float* rowcnt;         // [B] += number of negatives of the row
+    float* diag_out;       // [B] logit of the positive pair
+    float* S_out;          // optional [B, B]: every logit
+  };
+  struct State { uint8_t* stage_smem; float acc; float g; int slot; float sw[kMaxTiles][2]; float sb[kMaxTiles][2]; };
+  static __device__ __forceinline__ void init(const Params&, State& st) {
+    st.slot = 0;
+#pragma unroll
+    for (int t = 0; t < kMaxTiles; ++t) { st.sw[t][0] = st.sw[t][1] = 0.f; st.sb[t][0] = st.sb[t][1] = 0.f; }
+  }
+  static __device__ __forceinline__ void unit_begin(const Params&, State& st, const Unit&, int, int) { st.acc = 0.f; }
+  static __device__ __forceinline__ void pass1(const Params& p, State& st, int col0, uint32_t (&v)[32]) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col0);
+    const float4* w4 = reinterpret_cast<const float4*>(p.w3 + col0);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = __ldg(b4 + g), w = __ldg(w4 + g);
+      a0 = fmaf(w.x, fmaxf(__uint_as_float(v[4 * g]) + b.x, 0.f), a0);
+      a1 = fmaf(w.y, fmaxf(__uint_as_float(v[4 * g + 1]) + b.y, 0.f), a1);
+      a2 = fmaf(w.z, fmaxf(__uint_as_float(v[4 * g + 2]) + b.z, 0.f), a2);
+      a3 = fmaf(w.w, fmaxf(__uint_as_float(v[4 * g + 3]) + b.w, 0.f), a3);
+    }
+    st.acc += (a0 + a1) + (a2 + a3);
+  }
+  static __device__ __forceinline__ void mid(const Params& p, State& st, const Unit&, int row, int colq, uint8_t* epi_smem) {
+    const int lane = (int)(threadIdx.x & 31);
+    const int r = (int)(((threadIdx.x >> 5) & 3u) * 32u) + lane;            // row inside the CTA's 128
+    float* slot = reinterpret_cast<float*>(epi_smem) + st.slot * (kColQuarters * BLOCK_M);
+    slot[colq * BLOCK_M + r] = st.acc;
+    ptx::named_bar_sync(1, kNumEpiWarps * 32);
+    // every warp adds the quarters in the same order: the four threads of a row agree bit for bit
+    const float S = __ldg(p.b3) + ((slot[r] + slot[BLOCK_M + r]) + (slot[2 * BLOCK_M + r] + slot[3 * BLOCK_M + r]));
+    st.slot ^= 1;       // the next unit writes the other slot; this one is rewritten two barriers from now
+    const int il = row / p.Bp, j = row - il * p.Bp, i = p.r0 + il;
+    const bool valid = j < p.B && il < p.rr;
+    const bool incl = valid && __ldg(p.sid + i) != __ldg(p.sid + j);
+    // e^{S - ref} with ref = (sample maximum) + 69 ln 2: the subtraction stays near the logits (no absolute rounding at
+    // the size of the margin) and the margin is an exact power of two
+    const float g = incl ? expf(S - __ldg(p.ref)) * kMlpSpScale : 0.f;
+    st.g = g;
+    if (colq == 0) {
+      if (valid) {
+        if (p.S_out != nullptr) p.S_out[(size_t)i * p.B + j] = S;
+        if (i == j) p.diag_out[i] = S;
+      }
+      float gs = g;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+      const int cnt = __popc(__ballot_sync(0xffffffffu, incl));
+      if (lane == 0 && il < p.rr && cnt > 0) {        // the warp's 32 rows share the image row i
+        atomicAdd(p.rowsum + i, gs);
+        atomicAdd(p.rowcnt + i, (float)cnt);
+      }
+    }
+  }
+  // second pass over 16 columns (kQ = piece of the thread's 64 columns)
+  template <int kQ>
+  static __device__ __forceinline__ void chunk16(const Params& p, State& st, const Unit&, int row, int col0, uint32_t (&v)[16]) {
+    const int lane = (int)(threadIdx.x & 31);
+    const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col0);
+    const float4* w4 = reinterpret_cast<const float4*>(p.w3 + col0);
+    float dz[16], hw[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 b = __ldg(b4 + g), w = __ldg(w4 + g);
+      const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = __uint_as_float(v[4 * g + j]) + bb[j];
+        dz[4 * g + j] = z > 0.f ? st.g * ww[j] : 0.f;                       // padded columns: w3 = 0
+        hw[4 * g + j] = z > 0.f ? st.g * z : 0.f;                           // g relu(z2): the dw3 summand
+      }
+    }
+    if (col0 < p.cols) {                                    // every row of the panel exists (padded pairs carry g~ = 0)
+      uint32_t hi[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) hi[c] = ptx::pack_bf16(dz[2 * c], dz[2 * c + 1]);
+      const bool full = col0 + 16 <= p.cols;
+      __nv_bfloat16* d = p.dz + (size_t)row * p.pitch + col0;
+      if (full) {
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+        d4[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        d4[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      } else {
+        for (int c = 0; c < 16; ++c) if (col0 + c < p.cols) d[c] = __float2bfloat16(dz[c]);
+      }
+      if (p.dz_lo != nullptr) {
+        __nv_bfloat16* dl = p.dz_lo + (size_t)row * p.pitch + col0;
+        uint32_t lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float h0 = __uint_as_float(hi[c] << 16), h1 = __uint_as_float(hi[c] & 0xffff0000u);
+          lo[c] = ptx::pack_bf16(dz[2 * c] - h0, dz[2 * c + 1] - h1);
+        }
+        if (full) {
+          uint4* d4 = reinterpret_cast<uint4*>(dl);
+          d4[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          d4[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        } else {
+          for (int c = 0; c < 16; ++c)
+            if (col0 + c < p.cols) dl[c] = __float2bfloat16(dz[c] - __bfloat162float(__float2bfloat16(dz[c])));
+        }
+      }
+    }
+    // column sums over this warp's 32 pairs; a warp whose rows are all excluded (g~ = 0) has nothing to add.
+    // Lanes l and l ^ 16 receive the same column (l & 15); lane l keeps it when its upper bit names this piece's
+    // half of the 32-column group, so that lane l ends up owning column l of the group (as finish() expects).
+    if (__any_sync(0xffffffffu, st.g != 0.f)) {
+      const float cb = warp_column_sums16(dz, lane);
+      const float cw = warp_column_sums16(hw, lane);
+      if ((lane >> 4) == (kQ & 1)) {
+        const int t = col0 >> 8;
+#pragma unroll
+        for (int tt = 0; tt < kMaxTiles; ++tt)
+          if (tt == t) { st.sb[tt][kQ >> 1] += cb; st.sw[tt][kQ >> 1] += cw; }
+      }
+    }
+  }
+  static __device__ __forceinline__ void unit_end(const Params&, State&, const Unit&, int, int) {}
+  static __device__ __forceinline__ void finish(const Params& p, State& st, int colq) {
+    const int lane = (int)(threadIdx.x & 31);
+#pragma unroll
+    for (int t = 0; t < kMaxTiles; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = t * TILE_N + colq * 64 + h * 32 + lane;
+        if (col < p.cols && (st.sb[t][h] != 0.f || st.sw[t][h] != 0.f)) {
+          atomicAdd(p.db2 + col, st.sb[t][h]);
+          atomicAdd(p.dw3 + col, st.sw[t][h]);
+        }
+      }
+  }
+};
+
+// ---- backward through ReLU 1 with both reductions fused:  dZ1 = (dZ2 W2) . [H > 0]  is never stored;
+//      dA[i, k] += sum_j dZ1[(i, j), k]  (column sums over the warp's 32 rows: one image row per M block) and
+//      dC[j, k] += sum_i dZ1[(i, j), k]  (order-2 schedule: a unit walks the image rows of ONE (text block, N tile), so each
+//      thread adds its (j, 64 columns) cells in registers and flushes them once per unit).
+//      The ReLU mask comes as bits (one 32-bit word per pair and 32 columns, written by the H generator).
+struct EpiMlpDa {
+  static constexpr bool kJoint = false;
+  static constexpr bool kWalk = true;
+  static constexpr bool kChunk16 = true;      // 16-column accumulator reads: 64 running sums + a chunk fit the register file
+  static constexpr int kEpiSmemBytes = 0;
+  struct Params {
+    const uint32_t* mask;  // [rr * Bp][wpr]
+    int wpr;               // mask words per pair = ceil(H1 / 32) rounded up to an even number (8 B loads)
+    int B, Bp, r0, rr;
+    int cols;              // H1
+    float* dA;             // [B, cols]   (atomicAdd)
+    float* dC;             // [B, cols]   (atomicAdd)
+  };
+  struct State { uint8_t* stage_smem; float dc[64]; uint32_t mw0, mw1; int il; };
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+  static __device__ __forceinline__ void unit_begin(const Params&, State& st, const Unit&, int, int) {
+#pragma unroll
+    for (int c = 0; c < 64; ++c) st.dc[c] = 0.f;
+  }
+  // before the accumulator is awaited: the item's image row and the thread's 64 mask bits (two words, 8 B aligned)
+  static __device__ __forceinline__ void item_begin(const Params& p, State& st, int row, int col0) {
+    st.il = row / p.Bp;
+    st.mw0 = 0u; st.mw1 = 0u;
+    if (st.il < p.rr) {
+      const uint32_t* m = p.mask + (size_t)row * p.wpr + (col0 >> 5);
+      if (col0 < p.cols) { const uint2 w = __ldg(reinterpret_cast<const uint2*>(m)); st.mw0 = w.x; st.mw1 = w.y; }   // wpr is even
+    }
+  }
+  // kQ = which 16-column quarter of the thread's 64 columns (compile time: the running sums stay in registers)
+  template <int kQ>
+  static __device__ __forceinline__ void chunk16(const Params& p, State& st, const Unit&, int, int col0, uint32_t (&v)[16]) {
+    const int lane = (int)(threadIdx.x & 31);
+    const uint32_t mw = ((kQ & 2) ? st.mw1 : st.mw0) >> ((kQ & 1) * 16);
+    float x[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      x[c] = ((mw >> c) & 1u) ? __uint_as_float(v[c]) : 0.f;
+      st.dc[16 * kQ + c] += x[c];
+    }
+    const float cs = warp_column_sums16(x, lane);
+    if (lane < 16 && st.il < p.rr && col0 + lane < p.cols) atomicAdd(p.dA + (size_t)(p.r0 + st.il) * p.cols + col0 + lane, cs);
+  }
+  static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit& un, int row, int colq) {
+    const int j = row % p.Bp;
+    if (j >= p.B) return;
+    float* d = p.dC + (size_t)j * p.cols;
+    const int c0 = un.nt0 * TILE_N + colq * 64;
+#pragma unroll
+    for (int c = 0; c < 64; ++c)
+      if (c0 + c < p.cols) atomicAdd(d + c0 + c, st.dc[c]);
+  }
+};
+
 // ---- pairwise Euclidean distance sums (GDV, validate.py:23-34): acc = <a_row, b_col>,
 //      d = sqrt(max(|a|^2 + |b|^2 - 2 acc, 0)); the epilogue keeps one running sum per thread, S is never stored
 struct EpiDist {
+  static constexpr bool kJoint = false;
+  static constexpr bool kWalk = false;
+  static constexpr bool kChunk16 = false;
   static constexpr int kEpiSmemBytes = 0;
   struct Params {
     const float* na;       // [rows] squared norms of the A rows

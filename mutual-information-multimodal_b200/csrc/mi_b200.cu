@@ -185,7 +185,7 @@ int launch_engine_cg(const MapSpec& a, const MapSpec& b, const Sched& sc, const 
     MI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_devs.fetch_or(bit, std::memory_order_release);
   }
-  const int units = sc.n_mblk * sc.n_split * sc.n_ksplit;
+  const int units = mi::num_units(sc);
   int pairs = (num_sms() - t_reserve_sms) / kCG;
   if (pairs > units) pairs = units;
   if (pairs < 1) pairs = 1;
@@ -221,8 +221,11 @@ template <> struct EpiKind<mi::EpiStats> { static constexpr int value = 0; };
 template <> struct EpiKind<mi::EpiStatsRC> { static constexpr int value = 0; };
 template <> struct EpiKind<mi::EpiPStore> { static constexpr int value = 1; };
 template <> struct EpiKind<mi::EpiStore> { static constexpr int value = 2; };
-template <> struct EpiKind<mi::EpiMlpFwd> { static constexpr int value = 0; };   // (profiling buckets: score-like / panel-like)
-template <> struct EpiKind<mi::EpiMlpDz> { static constexpr int value = 1; };
+template <> struct EpiKind<mi::EpiMlpFwd> { static constexpr int value = 5; };   // MLP critic: two-pass epilogues
+template <> struct EpiKind<mi::EpiMlpDz> { static constexpr int value = 5; };
+template <> struct EpiKind<mi::EpiMlpSp> { static constexpr int value = 3; };    // single pass (forward + dZ2)
+template <> struct EpiKind<mi::EpiMlpDa> { static constexpr int value = 4; };    // dZ1 with fused reductions
+constexpr int kProfKinds = 6;
 template <> struct EpiKind<mi::EpiDist> { static constexpr int value = 0; };
 
 template <class Epi, bool kAMN = false, bool kBMN = false>
@@ -251,9 +254,27 @@ int choose_split(int n_mblk, int n_ntile, int U) {
   return ns;
 }
 
+// K splits of a GEMM with few output tiles: the split that minimises (rounds of the CTA pairs) x (K blocks per unit),
+// with a small charge per split for the partial-sum pass; at least min_ks (strict mode bounds the accumulation chains).
+int choose_ksplit(long long tiles, int k_blocks, long long min_ks = 1) {
+  const long long U = num_pairs();
+  long long hi = k_blocks / 4;
+  if (hi < 1) hi = 1;
+  long long lo = min_ks < 1 ? 1 : min_ks;
+  if (lo > hi) lo = hi;
+  long long best = lo;
+  double best_cost = 1e300;
+  for (long long ks = lo; ks <= hi && ks <= 4 * U; ++ks) {
+    const double cost = static_cast<double>(cdiv(tiles * ks, U)) * static_cast<double>(cdiv(k_blocks, ks)) + 0.25 * static_cast<double>(ks);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
+  }
+  return static_cast<int>(best);
+}
+
 void single_segment(Sched& sc) {
   sc.nt_base = 0;
   sc.seg_len = sc.k_blocks;
+  sc.grp = 1; sc.chunk_len = 1; sc.n_chunks = 1; sc.n_il = 1;
   for (int i = 0; i < 4; ++i) { sc.a_seg[i] = 0; sc.b_seg[i] = 0; sc.a_moff[i] = 0; sc.b_noff[i] = 0; }
 }
 
@@ -959,9 +980,7 @@ int gemm_mn_impl(const Opnd& A, bool a_mn, const Opnd& B, bool b_mn, long long M
   g.k_blocks = seg * kb;
   if (ksplit == 0) {
     const long long tiles = cdiv(M, rows_per_mblk()) * cdiv(N, mi::TILE_N);
-    long long ks = (out_f32 && !out_bf16) ? cdiv(num_pairs(), tiles) : 1;
-    if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
-    ksplit = static_cast<int>(ks < 1 ? 1 : ks);
+    ksplit = (out_f32 && !out_bf16) ? choose_ksplit(tiles, g.k_blocks) : 1;
   }
   g.ksplit = ksplit;
   g.out_f32 = out_f32; g.ld_out = ld_out;
@@ -1738,14 +1757,11 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
       g.M = D; g.N = D; g.seg_len = kb; g.k_blocks = kb;
       if (tsplit == 2) { g.k_blocks = 2 * kb; g.b_noff[1] = static_cast<int>(Dp); }
       const long long tiles = cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N);
-      long long ks = cdiv(num_pairs(), tiles);
       // The batch is the contraction dimension: B / 16 accumulating MMAs per output element.  The tensor core's fp32
       // accumulation of such a long, heavily cancelling sum (dW is tiny against the sum of its terms' magnitudes) loses
       // ~1e-3 of the result at B = 65536 with a few hundred K blocks per accumulator (measured: tests/test_gpu_parity.py
       // full-size case); strict mode therefore cuts the chains to <= 16 K blocks and sums the partials in a separate pass.
-      if (strict) ks = std::max<long long>(ks, cdiv(g.k_blocks, 16));
-      if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
-      if (ks < 1) ks = 1;
+      const long long ks = choose_ksplit(tiles, g.k_blocks, strict ? cdiv(g.k_blocks, 16) : 1);
       g.ksplit = static_cast<int>(ks);
       g.out_f32 = dW; g.ld_out = D;
       MI_TRY(run_gemm(g, ws, stream));
@@ -1814,23 +1830,26 @@ int mi_abi_version(void) { return 4; }
 int mi_device_check(void) { return device_check(); }
 int64_t mi_launch_count(void) { return g_launches.load(); }
 void mi_set_profiling(int on) { g_profiling = on != 0; }
-// ms[k], launches[k] for k = 0 (score statistics), 1 (dS panel), 2 (GEMM); drains the records (synchronises them)
-int mi_profile_read(double* ms, int64_t* launches) {
+// ms[k], launches[k] for k = 0 (score statistics), 1 (dS panel), 2 (GEMM), 3 (MLP single pass), 4 (MLP fused dZ1),
+// 5 (MLP two-pass epilogues); drains the records (synchronises them).  mi_profile_read: the first three kinds.
+int mi_profile_read_kinds(double* ms, int64_t* launches, int n_kinds) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  for (int k = 0; k < 3; ++k) { ms[k] = 0.0; launches[k] = 0; }
+  for (int k = 0; k < n_kinds; ++k) { ms[k] = 0.0; launches[k] = 0; }
   for (auto& r : g_prof) {
     float t = 0.f;
     MI_CUDA(cudaEventSynchronize(r.e1));
     MI_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
-    ms[r.kind] += t; launches[r.kind] += 1;
+    if (r.kind < n_kinds) { ms[r.kind] += t; launches[r.kind] += 1; }
     cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
   }
   g_prof.clear();
   return MI_OK;
 }
+int mi_profile_read(double* ms, int64_t* launches) { return mi_profile_read_kinds(ms, launches, 3); }
 void mi_set_ref_sample_columns(int64_t n) { g_ref_sample_cols.store(n, std::memory_order_relaxed); }
 void mi_set_overlap_reserve_sms(int n) { g_overlap_reserve_sms.store((n > 0 && n < 128) ? (n & ~1) : 0, std::memory_order_relaxed); }
 void mi_set_mlp_panel_pairs(int64_t pairs) { g_mlp_max_pairs = pairs > 0 ? pairs : (1LL << 20); }
+void mi_set_mlp_mode(int mode) { g_mlp_mode.store(mode < 0 ? 3 : (mode & 3), std::memory_order_relaxed); }
 void mi_set_cta_group(int g) { g_cta_group.store((g == 1) ? 1 : 2, std::memory_order_relaxed); }
 int mi_get_cta_group(void) { return cta_group(); }
 

@@ -128,8 +128,7 @@ int sharded_impl(mi_dist_ctx* ctx, int world, int rank, const void* X_, const vo
     ws.release(mk);
     if (bilinear) {        // dW split-K partials
       GemmArgs g; g.M = D; g.N = D; g.k_blocks = static_cast<int>(round_up(Bl, kSplitAlign) / bk()) * tsplit;
-      g.ksplit = std::max<int>(static_cast<int>(cdiv(num_pairs(), cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N))),
-                               strict ? static_cast<int>(cdiv(g.k_blocks, 16)) : 1);
+      g.ksplit = choose_ksplit(cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N), g.k_blocks, strict ? cdiv(g.k_blocks, 16) : 1);
       MI_TRY(run_gemm(g, ws, nullptr));
       ws.release(mk);
     }
@@ -232,11 +231,7 @@ int sharded_impl(mi_dist_ctx* ctx, int world, int rank, const void* X_, const vo
       g.b_mn = true; g.b = MapSpec{b.dT16, Bl, tsplit == 2 ? Dp + D : D, ldT};
       g.M = D; g.N = D; g.seg_len = kb; g.k_blocks = kb;
       if (tsplit == 2) { g.k_blocks = 2 * kb; g.b_noff[1] = static_cast<int>(Dp); }
-      long long ks = cdiv(num_pairs(), cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N));
-      if (strict) ks = std::max<long long>(ks, cdiv(g.k_blocks, 16));
-      if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
-      if (ks < 1) ks = 1;
-      g.ksplit = static_cast<int>(ks);
+      g.ksplit = choose_ksplit(cdiv(D, rows_per_mblk()) * cdiv(D, mi::TILE_N), g.k_blocks, strict ? cdiv(g.k_blocks, 16) : 1);
       g.out_f32 = dW; g.ld_out = D;
       MI_TRY(run_gemm(g, ws, S));
       ws.release(mk);

@@ -563,6 +563,12 @@ def mlp_critic_loss_fwd_bwd(X: torch.Tensor, Y: torch.Tensor, params, sid: torch
     return loss, S, grads
 
 
+def set_mlp_mode(mode: int) -> None:
+    """mi_set_mlp_mode: bit 0 = single pass for dv / infonce, bit 1 = dZ1 reductions fused into their GEMM (default 3;
+    0 = the two-pass sequence; negative = default)."""
+    _lib.load().mi_set_mlp_mode(int(mode))
+
+
 def gdv(pos: torch.Tensor, neg: torch.Tensor, precision: str = "strict") -> torch.Tensor:
     """mi_gdv: fp64[4] = {gdv, intra_pos, intra_neg, inter} of two [N, D] fp32 embedding sets (validate.py:16-49)."""
     _need_cuda(pos, neg)

@@ -84,16 +84,33 @@ def _load_case(mlp_oracle, path):
     return z, X, Y, sid, p
 
 
+# mi_set_mlp_mode: 3 = single pass + fused dZ1 reductions (default), 1 = single pass with the stored dZ1 panel,
+# 0 = the two-pass sequence (what infonce_row always runs, and the guard's repeat)
+MODES = [3, 1, 0]
+
+
+@pytest.fixture
+def mlp_mode(env, request):
+    ops = env[1]
+    ops.set_mlp_mode(request.param)
+    yield request.param
+    ops.set_mlp_mode(-1)
+
+
+@pytest.mark.parametrize("mlp_mode", MODES, indirect=True)
 @pytest.mark.parametrize("precision", ["strict", "fast"])
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-def test_golden_vectors_from_the_reference(env, path, precision):
+def test_golden_vectors_from_the_reference(env, path, precision, mlp_mode):
     mi_b200, ops, mo, mlp_oracle, dev = env
     z, X, Y, sid, p = _load_case(mlp_oracle, path)
     est = str(z["estimator"])
+    if mlp_mode != 3 and est == "infonce_row":
+        pytest.skip("infonce_row always runs the two-pass sequence")
     params = tuple(p[k].to(dev).float() for k in NAMES)
     loss, S, g = ops.mlp_critic_loss_fwd_bwd(X.to(dev).float(), Y.to(dev).float(), params, _sid_tensor(mo, sid, dev), est,
                                              precision, need_grads=True, want_scores=True)
     torch.cuda.synchronize()
+    assert float(loss[7].item()) == 0.0                                             # guard quiet
     mx = GOLDEN_MAX if precision == "strict" else None
     # the reference's logits: the diagonal, then the negatives in gap-major order (main_utils.py:93-108)
     idx = mo.negative_pair_index(sid)
@@ -124,14 +141,18 @@ SWEEP = [
     (100, 40, 192, 96, "infonce_row", 0.05, 3000),         # ragged everything, 4 panels
     (256, 128, 1024, 512, "dv", 0.05, 16384),              # the shipped hidden sizes, 4 panels
     (130, 72, 320, 264, "dv", 0.0, 5000),                  # H2 > 256: two column tiles, one of them ragged
+    (300, 48, 200, 72, "infonce", 0.1, 40000),             # B > one M block and ragged: padded text columns, H1 % 32 != 0
 ]
 
 
+@pytest.mark.parametrize("mlp_mode", MODES, indirect=True)
 @pytest.mark.parametrize("precision", ["strict", "fast"])
 @pytest.mark.parametrize("B,D,H1,H2,est,dup,panel", SWEEP)
-def test_oracle_parity(env, B, D, H1, H2, est, dup, panel, precision):
+def test_oracle_parity(env, B, D, H1, H2, est, dup, panel, precision, mlp_mode):
     mi_b200, ops, mo, mlp_oracle, dev = env
     from mi_b200 import _lib
+    if mlp_mode != 3 and est == "infonce_row":
+        pytest.skip("infonce_row always runs the two-pass sequence")
     X, Y, sid, _ = mo.synthetic_embeddings(B, D, seed=B + D, dup_frac=dup, bilinear=False)
     p = mlp_oracle.init_params(D, H1, H2, seed=H1 + H2)
     p["W2"] = p["W2"] * 2.0
@@ -152,6 +173,44 @@ def test_oracle_parity(env, B, D, H1, H2, est, dup, panel, precision):
     for k in ("dX", "dY", "dW1", "db1", "dW2", "db2", "dW3"):
         assert _grad_ok(g[k], ref[k], precision, GRAD_MAX[precision]), k
     assert abs(float(g["db3"].item()) - float(ref["db3"].reshape(-1)[0])) < 1e-4
+
+
+@pytest.mark.parametrize("precision", ["strict", "fast"])
+def test_single_pass_guard_repeats_with_the_two_pass_sequence(env, precision):
+    """The reference logit of the single pass comes from a strided SAMPLE of the pairs (even rows / columns at B = 512).
+    One unsampled image row with logits ~1e3 above everything else overflows e^{S - ref}: the guard must trip
+    (loss_out[7] > 0) and the library must deliver the two-pass results (mi_critics.py:9: logsumexp never overflows)."""
+    mi_b200, ops, mo, mlp_oracle, dev = env
+    B, D, H1, H2 = 512, 32, 64, 32
+    X, Y, sid, _ = mo.synthetic_embeddings(B, D, seed=77, dup_frac=0.05, bilinear=False)
+    p = mlp_oracle.init_params(D, H1, H2, seed=9)
+    p["W3"] = p["W3"].abs() * 4.0                           # logits grow with the size of the hidden activations
+    X = X.clone().float()
+    X[3] *= 3000.0                                          # row 3 is not in the sample (stride 2)
+    ref = mlp_oracle.mlp_loss_matrix_form(X, Y.float(), [int(s) for s in sid], p, "dv", dtype=torch.float64)
+    Sr = ref["S"]
+    assert float(Sr[3].max() - Sr[::2, ::2].max()) > 200.0, "the test input must defeat the sampled reference"
+    params = tuple(p[k].to(dev).float() for k in NAMES)
+    args = (X.to(dev), Y.to(dev).float(), params, torch.as_tensor(sid).to(torch.int32).to(dev), "dv", precision)
+    loss, S, g = ops.mlp_critic_loss_fwd_bwd(*args, need_grads=True, want_scores=True)
+    torch.cuda.synchronize()
+    ops.set_mlp_mode(0)
+    try:
+        loss0, S0, g0 = ops.mlp_critic_loss_fwd_bwd(*args, need_grads=True, want_scores=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_mlp_mode(-1)
+    assert float(loss[7].item()) > 0.0 and float(loss0[7].item()) == 0.0
+    # the repeat IS the two-pass sequence: same logits and loss bit for bit, gradients up to the order of the atomic adds
+    assert torch.equal(S, S0) and float(loss[0].item()) == float(loss0[0].item())
+    for k in ("dX", "dY", "dW1", "db1", "dW2", "db2", "dW3"):
+        assert _rel(g[k], g0[k].cpu()) < 1e-4, k
+    # and it is right (the hidden activations of row 3 are ~1e3: 16-bit operands leave ~1e-2 absolute errors next to the
+    # O(1) text-side terms, so the gradients are held to the fast-mode Frobenius bound only)
+    assert float((S.cpu().double() - Sr).abs().max()) < LOGIT_TOL[precision] * max(1.0, float(Sr.abs().max()))
+    assert _loss_rel(loss[0].item(), ref["loss"]) < LOSS_TOL[precision]
+    for k in ("dX", "dY", "dW1", "db1", "dW2", "db2", "dW3"):
+        assert _fro(g[k], ref[k]) < GRAD_FRO["fast"], k
 
 
 def test_adapter_in_the_mi_discriminator_slot(env):
