@@ -875,6 +875,8 @@ struct GemmArgs {
   int seg_len = 0;            // 0: one segment
   int a_seg[4] = {0, 0, 0, 0}, b_seg[4] = {0, 0, 0, 0}, a_moff[4] = {0, 0, 0, 0}, b_noff[4] = {0, 0, 0, 0};
   int ksplit = 1;
+  int order = 1;              // Sched::order of the units: 1 = the K splits of a tile on neighbouring CTA pairs, 0 = the tiles of a
+                              // K split on neighbouring pairs (they read the same operand rows at the same time: L2 sharing)
   float alpha = 1.f, gamma = 0.f;
   const __nv_bfloat16* sub = nullptr; const __nv_bfloat16* sub_lo = nullptr; long long ld_sub = 0;
   long long sub_row0 = 0, sub_rows = -1;   // SUB row r applies to output row sub_row0 + r (default: all rows)
@@ -894,7 +896,7 @@ int run_gemm(const GemmArgs& g, Bump& ws, cudaStream_t stream) {
   sc.n_split = sc.n_ntile;           // one tile per unit
   sc.k_blocks = g.k_blocks;
   sc.n_ksplit = g.ksplit < 1 ? 1 : (g.ksplit > sc.k_blocks ? sc.k_blocks : g.ksplit);
-  sc.order = 1;                      // all N tiles (and K splits) of an M block run concurrently
+  sc.order = g.order;                // 1: all N tiles (and K splits) of an M block run concurrently
   single_segment(sc);
   if (g.seg_len > 0) {
     sc.seg_len = g.seg_len;

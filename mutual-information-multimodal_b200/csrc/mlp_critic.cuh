@@ -410,6 +410,7 @@ int mlp_dw2_gemm(const MlpCtx& c, long long P, bool accumulate, Bump& ws) {
   if (c.sp == 2) { g.k_blocks = 3 * kb; g.a_moff[1] = static_cast<int>(c.H2p); g.b_noff[2] = static_cast<int>(c.Hp); }
   const long long tiles = cdiv(c.H2, rows_per_mblk()) * cdiv(c.H1, mi::TILE_N);
   g.ksplit = choose_ksplit(tiles, g.k_blocks);
+  g.order = 0;      // the 8 tiles of a K split stream the same rows of dZ2 / H: neighbours share them in L2
   g.out_f32 = c.dW2; g.ld_out = c.H1; g.accumulate = accumulate;
   if (ws.dry) g.out_f32 = reinterpret_cast<float*>(16);
   MI_TRY(run_gemm(g, ws, c.stream));
