@@ -1234,7 +1234,7 @@ struct EpiMlpDa {
   static constexpr bool kJoint = false;
   static constexpr bool kWalk = true;
   static constexpr bool kChunk16 = true;      // 16-column accumulator reads: 64 running sums + a chunk fit the register file
-  static constexpr int kEpiSmemBytes = 0;
+  static constexpr int kEpiSmemBytes = kNumEpiWarps * 2048;   // staging of the dC flush
   struct Params {
     const uint32_t* mask;  // [rr * Bp][wpr]
     int wpr;               // mask words per pair = ceil(H1 / 32) rounded up to an even number (8 B loads)
@@ -1273,14 +1273,32 @@ struct EpiMlpDa {
     const float cs = warp_column_sums16(x, lane);
     if (lane < 16 && st.il < p.rr && col0 + lane < p.cols) atomicAdd(p.dA + (size_t)(p.r0 + st.il) * p.cols + col0 + lane, cs);
   }
+  // Flush of the unit's running sums.  A lane owns ONE text row, so a direct red per column would touch 32 rows 4 KB apart
+  // per instruction; instead each 16-column quarter goes through the warp's 2 KB of shared memory ([32 rows][16] floats,
+  // 16 B groups XOR-swizzled by the row as in EpiStatsRC) and is sent out as 64 B row segments: a half warp per row.
   static __device__ __forceinline__ void unit_end(const Params& p, State& st, const Unit& un, int row, int colq) {
-    const int j = row % p.Bp;
-    if (j >= p.B) return;
-    float* d = p.dC + (size_t)j * p.cols;
+    const int lane = (int)(threadIdx.x & 31);
+    const int j0 = (row - lane) % p.Bp;                 // text row of lane 0 (the warp's 32 rows are consecutive text rows)
     const int c0 = un.nt0 * TILE_N + colq * 64;
+    float* sm = reinterpret_cast<float*>(st.stage_smem);
+    const int sw = (lane >> 1) & 3;
+    const int cc = lane & 15, rh = lane >> 4;
 #pragma unroll
-    for (int c = 0; c < 64; ++c)
-      if (c0 + c < p.cols) atomicAdd(d + c0 + c, st.dc[c]);
+    for (int q = 0; q < 4; ++q) {
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<float4*>(sm + lane * 16 + 4 * (g ^ sw)) =
+            make_float4(st.dc[16 * q + 4 * g], st.dc[16 * q + 4 * g + 1], st.dc[16 * q + 4 * g + 2], st.dc[16 * q + 4 * g + 3]);
+      __syncwarp();
+      const int col = c0 + 16 * q + cc;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int r = 2 * t + rh;
+        const float v = sm[r * 16 + 4 * ((cc >> 2) ^ ((r >> 1) & 3)) + (cc & 3)];
+        if (j0 + r < p.B && col < p.cols) atomicAdd(p.dC + (size_t)(j0 + r) * p.cols + col, v);
+      }
+    }
   }
 };
 

@@ -538,7 +538,7 @@ int mlp_reference_logit(const MlpCtx& c, float* As, float* Cs, float* Ssmp, floa
 // image rows walked per unit of the fused dZ1 kernel: the unit count should fill whole rounds of the CTA pairs
 void mlp_da_chunks(long long rr, long long per_chunk_units, int& chunk_len, int& n_chunks) {
   const long long U = num_pairs();
-  const long long min_len = rr < 16 ? rr : 16;
+  const long long min_len = rr < 32 ? rr : 32;          // the flush of a unit's running sums is amortised over >= 32 tiles
   double best = -1.0;
   chunk_len = static_cast<int>(rr); n_chunks = 1;
   for (long long nc = 1; nc <= cdiv(rr, min_len); ++nc) {
