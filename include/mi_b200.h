@@ -257,7 +257,10 @@ int mi_sharded_critic_loss_fwd_bwd(mi_dist_ctx* ctx, const void* X_local, const 
  * embedding), b1 [H1], W2 [H2, H1], b2 [H2], W3 [1, H2], b3 [1].   D, H1, H2 multiples of 8, H2 <= 512.
  * estimator: MI_EST_DV, MI_EST_INFONCE_REF or MI_EST_INFONCE_ROW.  precision: MI_PREC_BF16_FAST (bf16 operands of
  * the tensor-core contractions, fp32 accumulate) or MI_PREC_BF16_STRICT (hi/lo bf16 pairs, 16 significant bits).
- * loss_out (fp64[8]) as mi_critic_loss_fwd_bwd.  S_out (optional, [B, B]) receives the logit of EVERY pair
+ * loss_out (fp64[8]) as mi_critic_loss_fwd_bwd.  dv / infonce with gradients run as a single pass (softmax weights against
+ * the maximum logit of a sample of pairs, Z2 formed once; see mi_set_mlp_mode); if its guard trips, the two-pass sequence
+ * repeats the step behind a device-side predicate and loss_out[7] > 0 reports it.  The call never synchronises.
+ * S_out (optional, [B, B]) receives the logit of EVERY pair
  * (S[i,j] = mlp([x_i ; y_j]); the reference's logits are its diagonal followed by its negatives in gap-major
  * order).  Every gradient pointer may be NULL; all NULL = forward only. */
 size_t mi_mlp_critic_workspace_bytes(int64_t B, int64_t D, int64_t H1, int64_t H2, int precision);
