@@ -154,53 +154,93 @@ def run_reference(a):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled every 50 ms while the benchmark runs.  Reads NVML in-process
+    (the library nvidia-smi is built on: clocks.sm, clocks.max.sm, clocks_event_reasons.*, power.draw) — a separate
+    `nvidia-smi -lms` process attaches to every GPU of the box and its polls showed up as 1-25 ms stalls inside short
+    multi-GPU timed regions; if NVML cannot be loaded in-process the sampler falls back to that process."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []          # (time, sm_mhz, max_mhz, power_w or None, set(reasons))
         self.proc = None
+        self.nvml = None
         self.idx = gpu_index
+        self.stop_flag = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th = threading.Thread(target=self._read_smi, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown")
+                else n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        k = 0
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                pw = float(n.nvmlDeviceGetPowerUsage(self.h)) / 1e3 if (k % 4) == 0 else None      # the slow query: every 200 ms
+                self.rows.append((time.time(), sm, self.max_mhz, pw, {name for name, b in bits.items() if b and (r & b)}))
+            except Exception:
+                pass
+            k += 1
+            time.sleep(0.05)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, pw = [], [], set(), []
+    def _read_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 8:
                 continue
-            inside = t0 - 0.05 <= ts <= t1 + 0.15
             try:
-                if inside:
-                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                self.rows.append((time.time(), float(f[1]), float(f[2]), float(f[3]),
+                                  {n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            if inside:
-                for n, v in zip(names, f[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+
+    def stop(self, t0, t1):
+        if self.proc is None and self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, s_mhz, m_mhz, p_w, rs in self.rows:
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(s_mhz); mx.append(m_mhz); reasons |= rs
+                if p_w is not None:
+                    pw.append(p_w)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "NVML in-process, 50 ms period" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -241,8 +281,8 @@ def run_ours(a):
     from mi_b200 import dist as mdist
     lib = _lib.load()
 
-    # the clock sampler starts HERE, seconds before the timed region: nvidia-smi's own start-up (NVML attaching to every GPU
-    # of the box) stalls the GPUs for ~100 ms once — measured as a one-step spike when it was started right before the timing
+    # the clock sampler starts HERE, seconds before the timed region: NVML's start-up (attaching to the GPU) stalls it for
+    # ~100 ms once — measured as a one-step spike when the sampler was started right before the timing
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get('MI_BENCH_NOSMI'):
         sampler.start()
