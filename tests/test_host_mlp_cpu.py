@@ -64,3 +64,76 @@ def test_mlp_and_gdv_workspace_planning_without_gpu():
     assert lib.mi_mlp_critic_workspace_bytes(256, 770, 1024, 512, 0) == 0          # D % 8
     assert lib.mi_gdv_workspace_bytes(1000, 1200, 768, 1) > 0
     assert lib.mi_gdv_workspace_bytes(1, 1200, 768, 1) == 0                        # at least two samples per class
+
+
+def _single_pass_emulation(X, Y, sid, p, panel_rows, sample, dtype=torch.float64):
+    """Plain-torch restatement of csrc/mlp_critic.cuh::mlp_single_pass (dv): the algebra the kernels implement, panel by
+    panel — softmax weights against the maximum logit of a strided SAMPLE of the pairs times 2^-69, every sum kept in those
+    reference units, one multiplication by 1 / sum at the end, the positive pairs as a separate panel with weight -1/B."""
+    X, Y = X.to(dtype), Y.to(dtype)
+    W1, b1, W2, b2, W3, b3 = (p[k].to(dtype) for k in mlp_oracle.PARAM_NAMES)
+    B, D = X.shape
+    w3 = W3.reshape(-1)
+    A = X @ W1[:, :D].T + b1                                   # layer 1 is separable: W1 [x ; y] + b1 = A_i + C_j
+    C = Y @ W1[:, D:].T
+    ids = torch.as_tensor(sid)
+    incl = ids[:, None] != ids[None, :]                        # main_utils.py:105
+    ns = min(B, sample)
+    st = B // ns
+    rows = torch.arange(ns) * st
+
+    def logits(a_rows, c_rows):
+        h = torch.relu(a_rows[:, None, :] + c_rows[None, :, :])
+        z2 = h @ W2.T + b2
+        return h, z2, torch.relu(z2) @ w3 + b3
+
+    m_s = logits(A[rows], C[rows])[2].max()
+    scale = 2.0 ** -69
+    dW2 = torch.zeros_like(W2); dw3 = torch.zeros_like(w3); db2 = torch.zeros_like(b2)
+    dA = torch.zeros_like(A); dC = torch.zeros_like(C)
+    rowsum = torch.zeros(B, dtype=dtype); diag = torch.zeros(B, dtype=dtype)
+    for r0 in range(0, B, panel_rows):
+        r1 = min(B, r0 + panel_rows)
+        h, z2, S = logits(A[r0:r1], C)                         # [rr, B, H1], [rr, B, H2], [rr, B]
+        g = torch.where(incl[r0:r1], torch.exp(S - m_s) * scale, torch.zeros_like(S))
+        rowsum[r0:r1] = g.sum(1)
+        diag[r0:r1] = S[torch.arange(r1 - r0), torch.arange(r0, r1)]
+        pos = (z2 > 0).to(dtype)
+        dz2 = g[..., None] * w3 * pos
+        dw3 += (g[..., None] * torch.relu(z2)).sum((0, 1)); db2 += dz2.sum((0, 1))
+        dW2 += torch.einsum("ijn,ijk->nk", dz2, h)
+        dz1 = (dz2 @ W2) * (h > 0).to(dtype)
+        dA[r0:r1] += dz1.sum(1); dC += dz1.sum(0)
+    total = rowsum.sum()
+    c = 1.0 / total
+    for t in (dW2, dw3, db2, dA, dC):
+        t *= c
+    # the positive pairs (i, i): dL/dlogit = -1/B (mi_critics.py:6)
+    h = torch.relu(A + C); z2 = h @ W2.T + b2
+    dz2 = (-1.0 / B) * w3 * (z2 > 0).to(dtype)
+    dw3 += (-1.0 / B) * torch.relu(z2).sum(0); db2 += dz2.sum(0)
+    dW2 += dz2.T @ h
+    dz1 = (dz2 @ W2) * (h > 0).to(dtype)
+    dA += dz1; dC += dz1
+    n_neg = incl.sum().to(dtype)
+    lse = m_s + 69.0 * np.log(2.0) + torch.log(total)
+    loss = lse - torch.log(n_neg) - diag.mean()               # mi_critics.py:3-12
+    return {"loss": loss, "dX": dA @ W1[:, :D], "dY": dC @ W1[:, D:], "dW1": torch.cat([dA.T @ X, dC.T @ Y], 1),
+            "db1": dA.sum(0), "dW2": dW2, "db2": db2, "dW3": dw3.reshape(1, -1)}
+
+
+@pytest.mark.parametrize("B,panel,sample", [(24, 24, 256), (37, 5, 8), (64, 16, 16)])
+def test_single_pass_algebra_matches_the_autograd_oracle(B, panel, sample):
+    """Reference units + one final 1/sum + a separate positive-pair panel give exactly the gradients autograd takes of
+    dv_bound_loss over the reference's pair rows — for one panel, ragged panels and a sample that misses the maximum."""
+    from oracle import matrix_oracle as mo
+    D, H1, H2 = 12, 40, 24
+    X, Y, sid, _ = mo.synthetic_embeddings(B, D, seed=B, dup_frac=0.1, bilinear=False)
+    p = mlp_oracle.init_params(D, H1, H2, seed=3, dtype=torch.float64)
+    p["W2"] = p["W2"] * 2.0
+    p["W3"] = p["W3"] * 6.0
+    ref = mlp_oracle.mlp_loss_matrix_form(X.double(), Y.double(), [int(s) for s in sid], p, "dv", dtype=torch.float64)
+    got = _single_pass_emulation(X, Y, [int(s) for s in sid], p, panel, sample)
+    assert abs(float(got["loss"]) - float(ref["loss"])) < 1e-6 * max(1.0, abs(float(ref["loss"])))      # log N_neg is taken in fp32 (mi_critics.py:10)
+    for k in ("dX", "dY", "dW1", "db1", "dW2", "db2", "dW3"):
+        torch.testing.assert_close(got[k], ref[k].reshape(got[k].shape).double(), rtol=1e-8, atol=1e-12, msg=k)
