@@ -104,6 +104,17 @@ int mi_score_stats(const void* Q, int64_t ldq, int q_split, const void* K, int64
                    float* row_out /*[Bq,4]*/, double* scal_out /*[8]*/,
                    void* workspace, size_t workspace_bytes, mi_stream_t stream);
 
+/* Row statistics as mi_score_stats AND, from the same score tiles, the column statistics of the row block: col_lse_out[c]
+ * (c < Bk) = log-sum-exp over the block's rows r with sid_q[r] != sid_k[c] of S[r, c] (-inf if there is none).  This is the
+ * statistics pass of the symmetric InfoNCE estimator in the batch-sharded step (a rank holds Bq rows at q_offset of the
+ * [Bk, Bk] score matrix): the ranks' col_lse vectors are merged with a log-sum-exp by the caller, so the columns cost no
+ * second pass and no all-gather of the projected image embeddings (mi_critics.py has no symmetric form; BASELINE config 3). */
+size_t mi_score_stats_rc_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D);
+int mi_score_stats_rc(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
+                      const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                      int64_t Bq, int64_t Bk, int64_t D, float scale, float* row_out, double* scal_out, float* col_lse_out,
+                      void* workspace, size_t workspace_bytes, mi_stream_t stream);
+
 /* Fused gradient pass (replaces loss.backward() through mi_critics.py and the pair tensor,
  * main_utils.py:226): recomputes score tiles, forms
  *   G[q,k] = incl[q,k] * ( wq * exp(S - refq[q]) + wk * exp(S - refk[k]) )

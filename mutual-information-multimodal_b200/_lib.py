@@ -33,6 +33,9 @@ PROTOTYPES = {
     "mi_transpose_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "mi_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "mi_score_stats_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
+    "mi_score_stats_rc_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
+    "mi_score_stats_rc": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
+                                  c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mi_score_stats": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32,
                                c_vp, c_vp, c_vp, c_sz, c_vp]),
     "mi_score_grad_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),

@@ -665,6 +665,32 @@ __global__ void col_merge_kernel(const float* __restrict__ colpart, int n_rb, lo
   col_out[col] = make_float4(lse_neg, cnt, diag, lse_all);
 }
 
+// columns of a row BLOCK of the score matrix (a rank's rows in the batch-sharded step): the natural-log log-sum-exp of
+// column j over the block's negatives (-inf if it has none); the ranks' values are merged by the caller.
+__global__ void col_lse_kernel(const float* __restrict__ colpart, int n_rb, long long pitch, int k_cols, float* __restrict__ col_lse) {
+  __shared__ float shm[8][33], shs[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float m = mi::neg_inf(), s = 0.f;
+  if (col < k_cols) {
+    for (int rb = threadIdx.y; rb < n_rb; rb += 8) {
+      const float x = colpart[(size_t)rb * pitch + col];
+      if (x > mi::neg_inf()) {
+        const float mn = fmaxf(m, x);
+        s = s * exp2f(m - mn) + exp2f(x - mn);
+        m = mn;
+      }
+    }
+  }
+  shm[threadIdx.y][threadIdx.x] = m; shs[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || col >= k_cols) return;
+  float gm = mi::neg_inf();
+  for (int y = 0; y < 8; ++y) gm = fmaxf(gm, shm[y][threadIdx.x]);
+  float gs = 0.f;
+  for (int y = 0; y < 8; ++y) if (shs[y][threadIdx.x] > 0.f) gs += shs[y][threadIdx.x] * exp2f(shm[y][threadIdx.x] - gm);
+  col_lse[col] = gs > 0.f ? (gm + log2f(gs)) * mi::kLn2 : mi::neg_inf();
+}
+
 // one block: scal = {max lse_neg, sum exp(lse_neg - max), sum n_neg, sum diag, sum (lse_all - diag), #rows w/o neg, 0, 0}
 __global__ void stats_reduce_kernel(const float4* __restrict__ row_out, int q_rows, double* __restrict__ scal,
                                     const int* __restrict__ run_if) {
@@ -1082,45 +1108,58 @@ int stats_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k,
 
 // Row AND column statistics of the SQUARE score matrix S = scale Q K^T (same study ids on both sides) from ONE score
 // computation (EpiStatsRC) — the symmetric estimator's statistics for 2 B^2 D instead of 4 B^2 D.
-int stats_rc_impl(const Opnd& Q, const Opnd& K, const int* sid, long long B, long long D, float scale,
-                  float* row_out, double* scal_row, float* col_out, double* scal_col, Bump& ws, cudaStream_t stream) {
-  if (B <= 0 || D <= 0 || (D % 8) != 0) return MI_ERR_BAD_ARG;
+// Row AND column statistics of the score block S[q_offset + r, c] = scale <Q_r, K_c>, r < Bq, c < Bk, from ONE pass.
+// Square use (Bq == Bk, q_offset = 0; the 1-GPU symmetric estimator): col_out / scal_col receive the columns in the layout of
+// the rows.  Row-block use (a rank's rows of the batch-sharded step): col_lse receives, for every column, the log-sum-exp
+// over this block's negatives; the caller merges the ranks.
+int stats_rc_impl(const Opnd& Q, const Opnd& K, const int* sid_q, const int* sid_k, long long q_offset, long long Bq, long long Bk,
+                  long long D, float scale, float* row_out, double* scal_row, float* col_out, double* scal_col, float* col_lse,
+                  Bump& ws, cudaStream_t stream) {
+  if (Bq <= 0 || Bk <= 0 || D <= 0 || (D % 8) != 0 || q_offset < 0 || q_offset + Bq > Bk) return MI_ERR_BAD_ARG;
+  const bool square = col_lse == nullptr;
+  if (square && (Bq != Bk || q_offset != 0) && !ws.dry) return MI_ERR_BAD_ARG;
   Sched sc;
-  sc.n_mblk = static_cast<int>(cdiv(B, rows_per_mblk()));
-  sc.n_ntile = static_cast<int>(cdiv(B, mi::TILE_N));
+  sc.n_mblk = static_cast<int>(cdiv(Bq, rows_per_mblk()));
+  sc.n_ntile = static_cast<int>(cdiv(Bk, mi::TILE_N));
   sc.n_split = choose_split(sc.n_mblk, sc.n_ntile, num_pairs());
   sc.n_ksplit = 1; sc.order = 0;
   MI_TRY(score_segments(sc, Q, K, D));
   const long long k_pad = static_cast<long long>(sc.n_ntile) * mi::TILE_N;
   const int rows_padded = sc.n_mblk * rows_per_mblk();
   const int n_rb = rows_padded / 32;
-  const MaskBuf mb = take_mask(ws, B, k_pad, B);
+  const MaskBuf mb = take_mask(ws, Bq, k_pad, Bk);
   float4* part = ws.take<float4>(static_cast<size_t>(sc.n_split) * mi::kColQuarters * rows_padded);
-  float* diag = ws.take<float>(B);
+  float* diag = ws.take<float>(Bq);
   float* colpart = ws.take<float>(static_cast<size_t>(n_rb) * k_pad);
   const RedScratch red = take_red(ws);
   if (!ws.ok()) return MI_ERR_WORKSPACE;
   if (ws.dry) return MI_OK;
-  if (!Q.p || !K.p || !sid || !row_out || !scal_row || !col_out || !scal_col || !(scale > 0.f)) return MI_ERR_BAD_ARG;
-  MI_TRY(build_mask(mb, sid, sid, B, B, k_pad, stream));
-  diag_kernel<<<blocks_for(B * 32, 256), 256, 0, stream>>>(Q.p, Q.ld, Q.split, K.p, K.ld, K.split, 0, B, D,
-                                                            round_up(D, kSplitAlign), scale, diag, t_run_if);
+  if (!Q.p || !K.p || !sid_q || !sid_k || !row_out || !scal_row || !(scale > 0.f)) return MI_ERR_BAD_ARG;
+  if (square && (!col_out || !scal_col)) return MI_ERR_BAD_ARG;
+  MI_TRY(build_mask(mb, sid_q, sid_k, Bq, Bk, k_pad, stream));
+  diag_kernel<<<blocks_for(Bq * 32, 256), 256, 0, stream>>>(Q.p, Q.ld, Q.split, K.p, K.ld, K.split, q_offset, Bq, D,
+                                                             round_up(D, kSplitAlign), scale, diag, t_run_if);
   MI_LAUNCH_CHECK("diag_kernel");
   mi::EpiStatsRC::Params ep;
-  ep.mask = mi::MaskInfo{mb.excl, mb.n_same, sid, mb.sidk_pad};
-  ep.q_rows = static_cast<int>(B); ep.k_cols = static_cast<int>(B);
+  ep.mask = mi::MaskInfo{mb.excl, mb.n_same, sid_q, mb.sidk_pad};
+  ep.q_rows = static_cast<int>(Bq); ep.k_cols = static_cast<int>(Bk);
   ep.scale = scale; ep.part = part; ep.rows_padded = rows_padded;
   ep.colpart = colpart; ep.col_pitch = k_pad;
-  MI_TRY(launch_engine<mi::EpiStatsRC>(MapSpec{Q.p, B, opnd_k_extent(Q, D), Q.ld}, MapSpec{K.p, B, opnd_k_extent(K, D), K.ld},
+  MI_TRY(launch_engine<mi::EpiStatsRC>(MapSpec{Q.p, Bq, opnd_k_extent(Q, D), Q.ld}, MapSpec{K.p, Bk, opnd_k_extent(K, D), K.ld},
                                        sc, ep, stream));
-  stats_merge_kernel<<<blocks_for(B, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(B),
-                                                             mb.n_same, static_cast<int>(B), diag, reinterpret_cast<float4*>(row_out));
+  stats_merge_kernel<<<blocks_for(Bq, 128), 128, 0, stream>>>(part, sc.n_split * mi::kColQuarters, rows_padded, static_cast<int>(Bq),
+                                                              mb.n_same, static_cast<int>(Bk), diag, reinterpret_cast<float4*>(row_out));
   MI_LAUNCH_CHECK("stats_merge_kernel");
-  MI_TRY(reduce_rows(row_out, B, scal_row, red, stream));
-  col_merge_kernel<<<static_cast<unsigned>(cdiv(B, 32)), dim3(32, 8), 0, stream>>>(colpart, n_rb, k_pad, static_cast<int>(B), mb.n_same,
-                                                                                    static_cast<int>(B), diag, reinterpret_cast<float4*>(col_out));
-  MI_LAUNCH_CHECK("col_merge_kernel");
-  MI_TRY(reduce_rows(col_out, B, scal_col, red, stream));
+  MI_TRY(reduce_rows(row_out, Bq, scal_row, red, stream));
+  if (square) {
+    col_merge_kernel<<<static_cast<unsigned>(cdiv(Bk, 32)), dim3(32, 8), 0, stream>>>(colpart, n_rb, k_pad, static_cast<int>(Bk), mb.n_same,
+                                                                                       static_cast<int>(Bq), diag, reinterpret_cast<float4*>(col_out));
+    MI_LAUNCH_CHECK("col_merge_kernel");
+    MI_TRY(reduce_rows(col_out, Bk, scal_col, red, stream));
+  } else {
+    col_lse_kernel<<<static_cast<unsigned>(cdiv(Bk, 32)), dim3(32, 8), 0, stream>>>(colpart, n_rb, k_pad, static_cast<int>(Bk), col_lse);
+    MI_LAUNCH_CHECK("col_lse_kernel");
+  }
   return MI_OK;
 }
 
@@ -1699,7 +1738,7 @@ int critic_impl(const void* X_, const void* Y_, const void* W_, const int* sid, 
   }
   if (!single || ws.dry) {        // statistics pass(es) + gradient pass with exact references (planning covers both paths)
     if (sym) {      // rows and columns from one score computation
-      MI_TRY(stats_rc_impl(To, Yo, sid, B, D, inv_tau, rows_r, scal_r, rows_c, scal_c, ws, stream));
+      MI_TRY(stats_rc_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, rows_c, scal_c, nullptr, ws, stream));
     } else {
       MI_TRY(stats_impl(To, Yo, sid, sid, 0, B, B, D, inv_tau, rows_r, scal_r, ws, stream));
     }
@@ -1910,6 +1949,26 @@ int mi_score_stats(const void* Q, int64_t ldq, int q_split, const void* K, int64
   return stats_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
                     Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
                     sid_q, sid_k, q_offset, Bq, Bk, D, scale, row_out, scal_out, ws, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t mi_score_stats_rc_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D) {
+  Bump ws(nullptr, 0, true);
+  float dummy = 0.f;
+  if (stats_rc_impl(Opnd{nullptr, D, 1}, Opnd{nullptr, D, 1}, nullptr, nullptr, 0, Bq, Bk, D, 1.f, nullptr, nullptr, nullptr, nullptr,
+                    &dummy, ws, nullptr) != MI_OK) return 0;
+  return ws.peak + 256;
+}
+int mi_score_stats_rc(const void* Q, int64_t ldq, int q_split, const void* K, int64_t ldk, int k_split,
+                      const int32_t* sid_q, const int32_t* sid_k, int64_t q_offset,
+                      int64_t Bq, int64_t Bk, int64_t D, float scale, float* row_out, double* scal_out, float* col_lse_out,
+                      void* workspace, size_t workspace_bytes, mi_stream_t stream) {
+  MI_TRY(device_check());
+  if (!col_lse_out) return MI_ERR_BAD_ARG;
+  Bump ws(workspace, workspace_bytes, false);
+  return stats_rc_impl(Opnd{static_cast<const __nv_bfloat16*>(Q), ldq, q_split == 2 ? 2 : 1},
+                       Opnd{static_cast<const __nv_bfloat16*>(K), ldk, k_split == 2 ? 2 : 1},
+                       sid_q, sid_k, q_offset, Bq, Bk, D, scale, row_out, scal_out, nullptr, nullptr, col_lse_out, ws,
+                       reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t mi_score_grad_workspace_bytes(int64_t Bq, int64_t Bk, int64_t D, int precision) {

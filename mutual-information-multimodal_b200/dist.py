@@ -305,7 +305,11 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
                 ev_y.record(side)
         else:
             y_work.wait()
-    T_all = _gather_mat(T_local, world, group) if sym else None
+    # symmetric InfoNCE: the column statistics come out of the SAME pass as the rows (mi_score_stats_rc) and the ranks'
+    # column partials (B floats each) are merged below; the older form ran a second pass over the transposed block and
+    # all-gathered T for it (MI_SYM_RC=0 keeps it for A/B)
+    sym_rc = sym and hasattr(backend, "score_stats_rc") and os.environ.get("MI_SYM_RC", "1") != "0"
+    T_all = _gather_mat(T_local, world, group) if (sym and not sym_rc) else None
     if sid_all is None:
         if sid_local.dtype == torch.int32:                       # already exact int32 ids: use as they are
             sid_all = _all_gather_rows(sid_local.contiguous(), world, group)
@@ -330,12 +334,23 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
             return out, dX, dY, dW
 
     # ---- statistics (S never materialised)
-    rows_r, scal_r = backend.score_stats(T_local, Y_all, sid_loc, sid_all, off, inv_tau)
+    col_lse = None
+    if sym_rc:
+        rows_r, scal_r, col_lse = backend.score_stats_rc(T_local, Y_all, sid_loc, sid_all, off, inv_tau)
+    else:
+        rows_r, scal_r = backend.score_stats(T_local, Y_all, sid_loc, sid_all, off, inv_tau)
     g_r = merge_scalars(_all_gather_rows(scal_r.reshape(1, 8), world, group))
     out = {"pos_mean": g_r["diag_sum"] / Bg, "lse_neg": g_r["lse_neg"], "n_neg": g_r["n_neg"],
            "loss_row": g_r["rowloss_sum"] / Bg}
-    rows_c = None
-    if sym:
+    rows_c, c_all = None, None
+    if sym_rc:
+        # column j over ALL rows = log-sum-exp of the ranks' block values; its positive pair S[j, j] lives with the rows
+        col_all = _all_gather_rows(col_lse.reshape(1, Bg), world, group).double()                 # [world, B]
+        diag_all = _all_gather_rows(rows_r[:, 2].contiguous(), world, group).double()             # [B]
+        lse_c = torch.logaddexp(torch.logsumexp(col_all, 0), diag_all)
+        out["loss_col"] = (lse_c - diag_all).sum() / Bg
+        c_all = lse_c.to(torch.float32)
+    elif sym:
         rows_c, scal_c = backend.score_stats(Yb, T_all, sid_loc, sid_all, off, inv_tau)
         g_c = merge_scalars(_all_gather_rows(scal_c.reshape(1, 8), world, group))
         out["loss_col"] = g_c["rowloss_sum"] / Bg
@@ -360,7 +375,8 @@ def sharded_critic_loss_fwd_bwd(X_local: torch.Tensor, Y_local: torch.Tensor, W:
         ref = out["lse_neg"].to(torch.float32).expand(Bl).contiguous()
         args = dict(refq=ref, wq=1.0, refk=None, wk=0.0, include_diag=False)
     elif sym:
-        c_all = _all_gather_rows(rows_c[:, 3].contiguous(), world, group)
+        if c_all is None:
+            c_all = _all_gather_rows(rows_c[:, 3].contiguous(), world, group)
         args = dict(refq=rows_r[:, 3].contiguous(), wq=0.5 / Bg, refk=c_all, wk=0.5 / Bg, include_diag=True)
     else:
         args = dict(refq=rows_r[:, 3].contiguous(), wq=1.0 / Bg, refk=None, wk=0.0, include_diag=True)

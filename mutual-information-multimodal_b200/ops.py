@@ -223,6 +223,27 @@ def score_stats(Q: Mat, K: Mat, sid_q: torch.Tensor, sid_k: torch.Tensor,
     return rows, scal
 
 
+def score_stats_rc(Q: Mat, K: Mat, sid_q: torch.Tensor, sid_k: torch.Tensor,
+                   q_offset: int = 0, scale: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """mi_score_stats_rc: rows / scal as score_stats, plus col_lse [Bk] (fp32) = log-sum-exp of every column over this row
+    block's negatives, from the same score tiles (the symmetric estimator's statistics in the batch-sharded step)."""
+    _need_cuda(Q, K, sid_q, sid_k)
+    lib = _lib.load()
+    Qt, ldq, qsp, D = _opnd(Q)
+    Kt, ldk, ksp, Dk = _opnd(K)
+    assert D == Dk
+    sid_q, sid_k = sid_q.to(torch.int32).contiguous(), sid_k.to(torch.int32).contiguous()
+    Bq, Bk = Qt.shape[0], Kt.shape[0]
+    rows = torch.empty((Bq, 4), dtype=torch.float32, device=Qt.device)
+    scal = torch.empty(8, dtype=torch.float64, device=Qt.device)
+    col = torch.empty(Bk, dtype=torch.float32, device=Qt.device)
+    nbytes = lib.mi_score_stats_rc_workspace_bytes(Bq, Bk, D)
+    ws = workspace(nbytes, Qt.device)
+    _check(lib.mi_score_stats_rc(_ptr(Qt), ldq, qsp, _ptr(Kt), ldk, ksp, _ptr(sid_q), _ptr(sid_k), q_offset, Bq, Bk, D,
+                                 scale, _ptr(rows), _ptr(scal), _ptr(col), _ptr(ws), ws.numel(), _stream()), "mi_score_stats_rc")
+    return rows, scal, col
+
+
 def score_grad(Q: Mat, K: Mat, sid_q, sid_k, q_offset: int, scale: float,
                refq: Optional[torch.Tensor], wq: float, refk: Optional[torch.Tensor], wk: float,
                include_diag: bool, precision: str, alpha: float, gamma: float,

@@ -45,6 +45,14 @@ def score_stats(Q, K, sid_q, sid_k, q_offset=0, scale=1.0):
     return rows, scal
 
 
+def score_stats_rc(Q, K, sid_q, sid_k, q_offset=0, scale=1.0):
+    """score_stats plus the block's column statistics: col_lse[c] = log-sum-exp over the block's negatives of column c."""
+    rows, scal = score_stats(Q, K, sid_q, sid_k, q_offset, scale)
+    S, M, _, _ = _scores(Q, K, sid_q, sid_k, q_offset, scale)
+    col_lse = torch.logsumexp(torch.where(M, S, torch.full_like(S, float("-inf"))), 0)
+    return rows, scal, col_lse.to(torch.float32)
+
+
 def score_grad(Q, K, sid_q, sid_k, q_offset, scale, refq, wq, refk, wk, include_diag, precision,
                alpha, gamma, want_f32=True, want_bf16=False, out_split=False, want_k=False):
     S, M, i, j = _scores(Q, K, sid_q, sid_k, q_offset, scale)

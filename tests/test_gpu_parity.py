@@ -217,6 +217,17 @@ def test_stage_ops_with_offsets(env):
     assert float((rows[:, 2].cpu().double() - diag).abs().max()) < 1e-5
     assert abs(float(scal[0] + torch.log(scal[1])) - float(torch.logsumexp(lse_neg, 0))) < 1e-6
     assert float(scal[2]) == float(M.sum())
+    # the same rows plus the block's column statistics from ONE pass (symmetric InfoNCE, sharded step)
+    rows2, scal2, col = ops.score_stats_rc(Q.to(dev), K.to(dev), sid_q.to(dev), sid_k.to(dev), off, 0.6)
+    torch.cuda.synchronize()
+    assert float((rows2.cpu() - rows.cpu()).abs().max()) < 1e-5 and float((scal2.cpu() - scal.cpu()).abs().max()) < 1e-6 * float(scal.abs().max())
+    col_ref = torch.logsumexp(torch.where(M, S, torch.full_like(S, -float("inf"))), 0)
+    assert col.shape == (Bk,) and float((col.cpu().double() - col_ref).abs().max()) < 1e-5
+    # a column whose only same-block rows are excluded: every row of the block shares column `off`'s study -> -inf
+    sid_q1 = torch.full((Bq,), int(sid_k[off]))
+    _, _, col1 = ops.score_stats_rc(Q.to(dev), K.to(dev), sid_q1.to(dev), sid_k.to(dev), off, 0.6)
+    same = sid_k == sid_k[off]
+    assert bool(torch.isinf(col1.cpu()[same]).all()) and bool(torch.isfinite(col1.cpu()[~same]).all())
 
 
 def test_sharded_composition_world1_equals_fused_call(env):
