@@ -1867,7 +1867,7 @@ const char* mi_status_string(int status) {
   }
 }
 const char* mi_last_cuda_error(void) { return g_cuda_err; }
-int mi_abi_version(void) { return 4; }
+int mi_abi_version(void) { return 5; }
 int mi_device_check(void) { return device_check(); }
 int64_t mi_launch_count(void) { return g_launches.load(); }
 void mi_set_profiling(int on) { g_profiling = on != 0; }
@@ -1889,7 +1889,9 @@ int mi_profile_read_kinds(double* ms, int64_t* launches, int n_kinds) {
 int mi_profile_read(double* ms, int64_t* launches) { return mi_profile_read_kinds(ms, launches, 3); }
 void mi_set_ref_sample_columns(int64_t n) { g_ref_sample_cols.store(n, std::memory_order_relaxed); }
 void mi_set_overlap_reserve_sms(int n) { g_overlap_reserve_sms.store((n > 0 && n < 128) ? (n & ~1) : 0, std::memory_order_relaxed); }
-void mi_set_mlp_panel_pairs(int64_t pairs) { g_mlp_max_pairs = pairs > 0 ? pairs : (1LL << 20); }
+void mi_set_mlp_panel_pairs(int64_t pairs) {      // bounded: pair indices inside a panel are 32-bit
+  g_mlp_max_pairs = pairs > 0 ? (pairs < (1LL << 27) ? pairs : (1LL << 27)) : (1LL << 20);
+}
 void mi_set_mlp_mode(int mode) { g_mlp_mode.store(mode < 0 ? 3 : (mode & 3), std::memory_order_relaxed); }
 void mi_set_cta_group(int g) { g_cta_group.store((g == 1) ? 1 : 2, std::memory_order_relaxed); }
 int mi_get_cta_group(void) { return cta_group(); }

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/mi_b200.h but not exported"
         assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
     assert set(_lib.PROTOTYPES) == set(names)
-    assert _lib.load().mi_abi_version() == 4
+    assert _lib.load().mi_abi_version() == 5
 
 
 def test_ctypes_prototypes_match_the_header_signatures():
