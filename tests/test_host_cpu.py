@@ -156,8 +156,9 @@ def _free_port():
     return p
 
 
-def _dist_worker(rank, world, port, est, critic, ret, int32_ids=False, ref_stride=1, outlier=False):
+def _dist_worker(rank, world, port, est, critic, ret, int32_ids=False, ref_stride=1, outlier=False, sym_rc=True):
     import torch.distributed as dist
+    os.environ["MI_SYM_RC"] = "1" if sym_rc else "0"
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cpu_backend
@@ -208,6 +209,18 @@ def test_sharded_path_world2_gloo(est, critic):
         assert errs[0] < 1e-6, (rank, errs)           # fp32 log N_neg and fp32 reference vectors
         assert max(errs[1:-1]) < 1e-6, (rank, errs)
         assert errs[-1] == 0
+
+
+def test_sharded_path_world2_gloo_symmetric_two_statistics_passes():
+    """MI_SYM_RC=0: the older symmetric form (one statistics pass per direction, all-gather of T) stays available for A/B."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dist_worker, args=(2, _free_port(), "infonce_sym", "bilinear", ret, False, 1, False, False), nprocs=2, join=True)
+    assert len(ret) == 2
+    for rank in range(2):
+        errs = ret[rank]
+        assert errs[0] < 1e-6 and max(errs[1:-1]) < 1e-6 and errs[-1] == 0, (rank, errs)
 
 
 def test_sharded_path_world2_gloo_packed_int32_ids():
