@@ -211,6 +211,18 @@ def test_sharded_path_world2_gloo(est, critic):
         assert errs[-1] == 0
 
 
+def test_sharded_path_world4_gloo_symmetric_one_statistics_pass():
+    """Four ranks: every column's log-sum-exp is merged from four row-block partials (mi_score_stats_rc per rank)."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dist_worker, args=(4, _free_port(), "infonce_sym", "bilinear", ret), nprocs=4, join=True)
+    assert len(ret) == 4
+    for rank in range(4):
+        errs = ret[rank]
+        assert errs[0] < 1e-6 and max(errs[1:-1]) < 1e-6 and errs[-1] == 0, (rank, errs)
+
+
 def test_sharded_path_world2_gloo_symmetric_two_statistics_passes():
     """MI_SYM_RC=0: the older symmetric form (one statistics pass per direction, all-gather of T) stays available for A/B."""
     import torch.multiprocessing as mp
