@@ -292,6 +292,13 @@ size_t mi_gdv_workspace_bytes(int64_t Np, int64_t Nn, int64_t D, int precision);
 int mi_gdv(const float* pos, const float* neg, int64_t Np, int64_t Nn, int64_t D, int precision, double* out /*[4]*/,
            void* workspace, size_t workspace_bytes, mi_stream_t stream);
 
+/* Introspection of host-side scheduling decisions (used by the CPU tests; no device needed).
+ * mi_plan_ksplit: the K splits a GEMM with `tiles` output tiles and `k_blocks` K blocks is given (>= min_ks).
+ * mi_plan_mlp_walk: the (unit, M block, N tile) work items of the MLP critic's fused dZ1 kernel for a panel of `rr` image
+ * rows at batch B, hidden width H1, in the order the CTA pairs walk them; returns the item count. */
+int mi_plan_ksplit(int64_t tiles, int k_blocks, int64_t min_ks);
+int64_t mi_plan_mlp_walk(int64_t rr, int64_t B, int64_t H1, int32_t* out /*[max_items][3]*/, int64_t max_items);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t mi_launch_count(void);
 

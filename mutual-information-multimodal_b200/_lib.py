@@ -24,6 +24,8 @@ PROTOTYPES = {
     "mi_set_overlap_reserve_sms": (None, [c_int]),
     "mi_set_mlp_panel_pairs": (None, [c_i64]),
     "mi_set_mlp_mode": (None, [c_int]),
+    "mi_plan_ksplit": (c_int, [c_i64, c_int, c_i64]),
+    "mi_plan_mlp_walk": (c_i64, [c_i64, c_i64, c_i64, c_vp, c_i64]),
     "mi_get_cta_group": (c_int, []),
     "mi_gemm_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_i64,
                              c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),

@@ -86,7 +86,7 @@ __host__ __device__ __forceinline__ int num_units(const Sched& sc) {
 __device__ __forceinline__ int sel4(const int (&a)[4], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
 
 template <bool kWalk>
-__device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
+__host__ __device__ __forceinline__ Unit decode_unit(const Sched& sc, int u) {
   Unit r;
   if (kWalk && sc.order == 2) {
     const int nt = u % sc.n_ntile; int t = u / sc.n_ntile;      // the N tiles of an M block run concurrently (A tile from L2)

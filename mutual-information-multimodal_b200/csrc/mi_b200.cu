@@ -2357,6 +2357,33 @@ int mi_mlp_critic_loss_fwd_bwd(const float* X, const float* Y, const float* W1, 
                   MlpGrads{dX, dY, dW1, db1, dW2, db2, dW3, db3}, ws, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ---- introspection of the host-side scheduling decisions (CPU tests; no device needed)
+int mi_plan_ksplit(int64_t tiles, int k_blocks, int64_t min_ks) { return choose_ksplit(tiles, k_blocks, min_ks); }
+// The work items of the fused dZ1 kernel (EpiMlpDa, Sched::order 2) for a panel of `rr` image rows: item t is
+// out[3 t .. 3 t + 2] = {unit, M block, N tile} in the order a CTA pair walks them.  Returns the number of items
+// (> max_items: nothing beyond max_items was written).
+int64_t mi_plan_mlp_walk(int64_t rr, int64_t B, int64_t H1, int32_t* out, int64_t max_items) {
+  if (rr <= 0 || B <= 0 || H1 <= 0) return MI_ERR_BAD_ARG;
+  const long long Bp = round_up(B, rows_per_mblk());
+  Sched sc;
+  single_segment(sc);
+  sc.order = 2;
+  sc.n_ntile = static_cast<int>(cdiv(H1, mi::TILE_N));
+  sc.grp = static_cast<int>(Bp / rows_per_mblk()); sc.n_il = static_cast<int>(rr);
+  mlp_da_chunks(rr, static_cast<long long>(sc.n_ntile) * sc.grp, sc.chunk_len, sc.n_chunks);
+  sc.n_mblk = sc.grp * sc.n_il; sc.n_split = 1; sc.n_ksplit = 1; sc.k_blocks = 1;
+  int64_t n = 0;
+  for (int u = 0; u < mi::num_units(sc); ++u) {
+    const mi::Unit un = mi::decode_unit<true>(sc, u);
+    for (int it = 0; it < un.n_items; ++it, ++n) {
+      if (n < max_items && out != nullptr) {
+        out[3 * n] = u; out[3 * n + 1] = un.m + it * un.m_step; out[3 * n + 2] = un.nt0;
+      }
+    }
+  }
+  return n;
+}
+
 size_t mi_gdv_workspace_bytes(int64_t Np, int64_t Nn, int64_t D, int precision) {
   Bump ws(nullptr, 0, true);
   if (gdv_impl(nullptr, nullptr, Np, Nn, D, precision, nullptr, ws, nullptr) != MI_OK) return 0;

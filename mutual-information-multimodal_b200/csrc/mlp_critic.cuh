@@ -541,7 +541,8 @@ void mlp_da_chunks(long long rr, long long per_chunk_units, int& chunk_len, int&
   const long long min_len = rr < 32 ? rr : 32;          // the flush of a unit's running sums is amortised over >= 32 tiles
   double best = -1.0;
   chunk_len = static_cast<int>(rr); n_chunks = 1;
-  for (long long nc = 1; nc <= cdiv(rr, min_len); ++nc) {
+  const long long nc_max = rr / min_len < 1 ? 1 : rr / min_len;         // full-length chunks stay >= min_len
+  for (long long nc = 1; nc <= nc_max; ++nc) {
     const long long len = cdiv(rr, nc), real_nc = cdiv(rr, len), units = per_chunk_units * real_nc;
     const double eff = static_cast<double>(units) / static_cast<double>(cdiv(units, U) * U);
     if (eff > best + 1e-9) { best = eff; chunk_len = static_cast<int>(len); n_chunks = static_cast<int>(real_nc); }

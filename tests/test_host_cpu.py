@@ -287,3 +287,57 @@ def test_package_synthetic_generator_equals_the_oracles():
         b = mo.synthetic_embeddings(96, 40, seed=5, dup_frac=0.1, bilinear=bil)
         for x, y in zip(a, b):
             assert (x is None and y is None) or torch.equal(x, y)
+
+
+@pytest.mark.parametrize("rr,B,H1", [(256, 4096, 1024), (1024, 1024, 1024), (48, 48, 1024), (11, 100, 192), (37, 300, 200),
+                                     (1, 16, 40), (4096, 256, 320)])
+def test_mlp_walk_schedule_covers_every_tile_exactly_once(rr, B, H1):
+    """Sched::order 2 (fused dZ1 kernel of the MLP critic): the units' work items are an exact cover of
+    {M blocks} x {N tiles}; inside a unit the N tile is fixed and the M blocks are `grp` apart (same text rows, next image
+    row) — the property the epilogue's register-resident dC sums rely on; full-length walks are at least 32 tiles long unless the
+    panel is shorter.  Planned on the host (mi_plan_mlp_walk), no device needed."""
+    import ctypes
+    from mi_b200 import _lib
+    lib = _lib.load()
+    rows_per_mblk = 256 if lib.mi_get_cta_group() == 2 else 128
+    grp = -(-B // rows_per_mblk)
+    n_nt = -(-H1 // 256)
+    total = rr * grp * n_nt
+    buf = (ctypes.c_int32 * (3 * total))()
+    n = lib.mi_plan_mlp_walk(rr, B, H1, buf, total)
+    assert n == total
+    items = np.frombuffer(buf, dtype=np.int32).reshape(total, 3)
+    seen = set()
+    by_unit = {}
+    for u, m, nt in items.tolist():
+        assert 0 <= m < rr * grp and 0 <= nt < n_nt
+        assert (m, nt) not in seen
+        seen.add((m, nt))
+        by_unit.setdefault(u, []).append((m, nt))
+    assert len(seen) == total
+    lens = []
+    for u, its in by_unit.items():
+        assert len({nt for _, nt in its}) == 1                       # one N tile per unit
+        ms = [m for m, _ in its]
+        assert all(b - a == grp for a, b in zip(ms, ms[1:]))        # consecutive image rows of the same text block
+        lens.append(len(its))
+    if rr >= 32:                                                     # the flush of the running sums is amortised over >= 32 tiles
+        assert max(lens) >= 32
+
+
+def test_split_k_plan_fills_whole_rounds():
+    """choose_ksplit: never more splits than k_blocks / 4, at least min_ks, and never worse (in rounds x K blocks per unit)
+    than the old ceil(pairs / tiles) rule that left a nearly empty second round (80 units on 74 CTA pairs)."""
+    from mi_b200 import _lib
+    lib = _lib.load()
+    U = 74 if lib.mi_get_cta_group() == 2 else 148
+    ceil = lambda a, b: -(-a // b)
+    for tiles, kb in [(8, 8192), (16, 512), (12, 512), (1, 64), (3, 7), (40, 4096), (148, 33)]:
+        ks = lib.mi_plan_ksplit(tiles, kb, 1)
+        assert 1 <= ks <= max(1, kb // 4)
+        cost = ceil(tiles * ks, U) * ceil(kb, ks)
+        old = min(max(1, ceil(U, tiles)), max(1, kb // 4))
+        assert cost <= ceil(tiles * old, U) * ceil(kb, old)
+    ks = lib.mi_plan_ksplit(8, 8192, 1)                            # dW2 of the MLP critic (8 tiles, 2^20 pairs): whole rounds,
+    assert ceil(8 * ks, U) * ceil(8192, ks) <= 1.03 * 8 * 8192 / U  # within 3 % of perfectly divisible work
+    assert lib.mi_plan_ksplit(16, 1024, 64) >= 64                   # strict mode: chains of <= 16 K blocks
